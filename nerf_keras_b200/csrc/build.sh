@@ -1,0 +1,18 @@
+#!/bin/bash
+# Builds libnerf_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../libnerf_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr)
+OBJS=()
+for f in ops mlp_fp32 ctx mlp_tc mlp_tc_bwd; do
+  src="$HERE/$f.cu"; obj="$HERE/$f.o"
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/tc5.cuh" -nt "$obj" || "$HERE/ctx.cuh" -nt "$obj" || "$HERE/common.cuh" -nt "$obj" || "$HERE/../../include/nerf_b200.h" -nt "$obj" ]]; then
+    "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj" &
+  fi
+  OBJS+=("$obj")
+done
+wait
+"$NVCC" -shared -o "$OUT" "${OBJS[@]}" -lcudart
+echo "built $OUT"

@@ -1,0 +1,296 @@
+// Context management and the reference-level entry points (models.py) of libnerf_b200.so.
+#include "ctx.cuh"
+
+using namespace nerf;
+
+extern "C" int nerf_volume_render_bwd(const float*, const float*, const float*, const float*, int64_t, int, float*,
+                                      float*, void*);
+extern "C" int nerf_metrics_grad(const float*, const float*, const float*, int64_t, float*, float*, float*, void*);
+extern "C" int nerf_adam_flat(float*, const float*, float*, float*, int64_t, int64_t, float, float, void*);
+
+namespace nerf {
+int64_t tc_save_bytes_per_tile();
+int tc_train_alloc(nerf_ctx* ctx);
+int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
+                const float* d_preds, cudaStream_t st);
+}  // namespace nerf
+
+static int build_layers(const nerf_config& c, std::vector<LayerInfo>& layers, int64_t& n_params) {
+    const int ex = 3 + 6 * c.l_xyz, ed = 3 + 6 * c.l_dir, Hd = c.hidden_dim;
+    layers.clear();
+    int64_t off = 0;
+    auto add = [&](int fi, int fo) {
+        LayerInfo li;
+        li.fan_in = fi; li.fan_out = fo;
+        li.w_off = off; off += (int64_t)fi * fo;
+        li.b_off = off; off += fo;
+        layers.push_back(li);
+    };
+    int fan_in = ex;
+    for (int i = 0; i < c.num_layers; ++i) {
+        add(fan_in, Hd);
+        fan_in = Hd;
+        if (i % c.skip_layer == 0 && i > 0) fan_in = Hd + ex;  // models.py:38-39
+    }
+    add(fan_in, 1);          // sigma   models.py:42
+    add(fan_in, Hd);         // feature models.py:45
+    add(Hd + ed, Hd / 2);    // ddir    models.py:48-54
+    add(Hd / 2, 3);          // rgb     models.py:57
+    n_params = off;
+    return NERF_OK;
+}
+
+static int validate_cfg(const nerf_config* c) {
+    NERF_CHECK_ARG(c != nullptr, "null config");
+    NERF_CHECK_ARG(c->num_layers >= 1 && c->num_layers <= 16, "NUM_LAYERS out of range");
+    NERF_CHECK_ARG(c->hidden_dim >= 2 && c->hidden_dim <= 1024 && c->hidden_dim % 2 == 0, "HIDDEN_DIM out of range");
+    NERF_CHECK_ARG(c->skip_layer >= 1, "SKIP_LAYER must be >= 1");
+    NERF_CHECK_ARG(c->l_xyz >= 0 && c->l_xyz <= 16 && c->l_dir >= 0 && c->l_dir <= 16, "L_XYZ/L_DIR out of range");
+    NERF_CHECK_ARG(c->ns_coarse >= 2 && c->ns_fine >= 1, "NS_COARSE must be >= 2 and NS_FINE >= 1");
+    NERF_CHECK_ARG(c->max_rays >= 1, "max_rays must be >= 1");
+    NERF_CHECK_ARG(c->batch_norm == 0, "BATCH_NORM=true is not supported by the B200 path (see DESIGN.md)");
+    // the skip concat after the LAST trunk layer would change the head fan-in; the reference configs never do this
+    NERF_CHECK_ARG(!((c->num_layers - 1) % c->skip_layer == 0 && c->num_layers - 1 > 0),
+                   "skip connection on the last trunk layer is not supported");
+    return NERF_OK;
+}
+
+extern "C" int64_t nerf_param_count(const nerf_config* cfg) {
+    if (validate_cfg(cfg)) return -1;
+    std::vector<LayerInfo> layers;
+    int64_t n = 0;
+    build_layers(*cfg, layers, n);
+    return n;
+}
+
+extern "C" int nerf_create(const nerf_config* cfg, nerf_ctx** out) {
+    NERF_CHECK_ARG(out != nullptr, "null out pointer");
+    int rc = validate_cfg(cfg);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(NERF_ERR_CUDA, "nerf_create: no CUDA device available (this library has no CPU fallback)");
+    nerf_ctx* ctx = new nerf_ctx();
+    ctx->cfg = *cfg;
+    cudaGetDevice(&ctx->device);
+    build_layers(*cfg, ctx->layers, ctx->n_params);
+    const int64_t np2 = 2 * ctx->n_params;
+    const int64_t R = cfg->max_rays, Nc = cfg->ns_coarse, Na = cfg->ns_coarse + cfg->ns_fine;
+#define ALLOC(ptr, bytes)                                                          \
+    do {                                                                           \
+        cudaError_t _e = cudaMalloc((void**)&(ptr), (size_t)(bytes));              \
+        if (_e != cudaSuccess) {                                                   \
+            nerf_destroy(ctx);                                                     \
+            return fail(NERF_ERR_CUDA, std::string("nerf_create: cudaMalloc failed: ") + cudaGetErrorString(_e)); \
+        }                                                                          \
+    } while (0)
+    ALLOC(ctx->params, np2 * 4);
+    cudaMemset(ctx->params, 0, np2 * 4);
+    ALLOC(ctx->fw_pred_c, R * Nc * 16);
+    ALLOC(ctx->fw_pred_f, R * Na * 16);
+    ALLOC(ctx->fw_w_c, R * Nc * 4);
+    ALLOC(ctx->fw_w_f, R * Na * 4);
+    ALLOC(ctx->fw_t_all, R * Na * 4);
+    ALLOC(ctx->fw_src_idx, R * Na * 4);
+    ALLOC(ctx->fw_rgb_c, R * 12);
+    ALLOC(ctx->fw_rgb_f, R * 12);
+    ALLOC(ctx->fw_dirbias, R * (cfg->hidden_dim / 2) * 4);
+    if (cfg->training) {
+        ALLOC(ctx->grads, np2 * 4);
+        ALLOC(ctx->adam_m, np2 * 4);
+        ALLOC(ctx->adam_v, np2 * 4);
+        cudaMemset(ctx->grads, 0, np2 * 4);
+        cudaMemset(ctx->adam_m, 0, np2 * 4);
+        cudaMemset(ctx->adam_v, 0, np2 * 4);
+        ALLOC(ctx->tr_dpred_c, R * Nc * 16);
+        ALLOC(ctx->tr_dpred_f, R * Na * 16);
+        ALLOC(ctx->tr_drgb_c, R * 12);
+        ALLOC(ctx->tr_drgb_f, R * 12);
+    }
+#undef ALLOC
+    if (tc_supported(*cfg, nullptr)) {
+        rc = tc_alloc(ctx);
+        if (rc) { nerf_destroy(ctx); return rc; }
+        if (cfg->training) {
+            rc = tc_train_alloc(ctx);
+            if (rc) { nerf_destroy(ctx); return rc; }
+        }
+    }
+    *out = ctx;
+    return NERF_OK;
+}
+
+extern "C" int nerf_destroy(nerf_ctx* ctx) {
+    if (!ctx) return NERF_OK;
+    cudaFree(ctx->params); cudaFree(ctx->grads); cudaFree(ctx->adam_m); cudaFree(ctx->adam_v);
+    cudaFree(ctx->ws_a); cudaFree(ctx->ws_b); cudaFree(ctx->ws_c); cudaFree(ctx->ws_encx); cudaFree(ctx->ws_encd);
+    cudaFree(ctx->fw_pred_c); cudaFree(ctx->fw_pred_f); cudaFree(ctx->fw_w_c); cudaFree(ctx->fw_w_f);
+    cudaFree(ctx->fw_t_all); cudaFree(ctx->fw_src_idx); cudaFree(ctx->fw_rgb_c); cudaFree(ctx->fw_rgb_f);
+    cudaFree(ctx->fw_dirbias);
+    cudaFree(ctx->tr_dpred_c); cudaFree(ctx->tr_dpred_f); cudaFree(ctx->tr_drgb_c); cudaFree(ctx->tr_drgb_f);
+    cudaFree(ctx->tr_ddirbias);
+    for (int n = 0; n < 2; ++n) { cudaFree(ctx->act_save[n]); cudaFree(ctx->dz_save[n]); }
+    tc_free(ctx);
+    delete ctx;
+    return NERF_OK;
+}
+
+extern "C" int nerf_set_weights(nerf_ctx* ctx, int net, const float* blob, int64_t n, void* stream) {
+    NERF_CHECK_ARG(ctx && blob, "null pointer");
+    NERF_CHECK_ARG(net == 0 || net == 1, "net must be NERF_NET_COARSE or NERF_NET_FINE");
+    NERF_CHECK_ARG(n == ctx->n_params, "blob size does not match nerf_param_count()");
+    NERF_CUDA(cudaMemcpyAsync(ctx->params + (int64_t)net * ctx->n_params, blob, n * 4, cudaMemcpyDefault,
+                              (cudaStream_t)stream));
+    ctx->weights_set[net] = true;
+    ctx->packed_valid[net] = false;
+    return NERF_OK;
+}
+
+extern "C" int nerf_get_weights(nerf_ctx* ctx, int net, float* blob, int64_t n, void* stream) {
+    NERF_CHECK_ARG(ctx && blob, "null pointer");
+    NERF_CHECK_ARG(net == 0 || net == 1, "net must be NERF_NET_COARSE or NERF_NET_FINE");
+    NERF_CHECK_ARG(n == ctx->n_params, "blob size does not match nerf_param_count()");
+    NERF_CUDA(cudaMemcpyAsync(blob, ctx->params + (int64_t)net * ctx->n_params, n * 4, cudaMemcpyDefault,
+                              (cudaStream_t)stream));
+    return NERF_OK;
+}
+
+extern "C" int nerf_grad_buffer(nerf_ctx* ctx, float** grads, int64_t* n) {
+    NERF_CHECK_ARG(ctx && grads && n, "null pointer");
+    if (!ctx->grads) return fail(NERF_ERR_STATE, "nerf_grad_buffer: ctx was not created with training=1");
+    *grads = ctx->grads;
+    *n = 2 * ctx->n_params;
+    return NERF_OK;
+}
+
+namespace nerf {
+int ensure_fp32_workspace(nerf_ctx* ctx) {
+    if (ctx->ws_a) return NERF_OK;
+    const nerf_config& c = ctx->cfg;
+    const int64_t chunk = 65536;
+    const int Cx = 3 + 6 * c.l_xyz, Cd = 3 + 6 * c.l_dir, Hd = c.hidden_dim;
+    NERF_CUDA(cudaMalloc(&ctx->ws_a, chunk * (Hd + Cx) * 4));
+    NERF_CUDA(cudaMalloc(&ctx->ws_b, chunk * (Hd + Cx) * 4));
+    NERF_CUDA(cudaMalloc(&ctx->ws_c, chunk * (Hd + Cd) * 4));
+    NERF_CUDA(cudaMalloc(&ctx->ws_encx, chunk * Cx * 4));
+    NERF_CUDA(cudaMalloc(&ctx->ws_encd, chunk * Cd * 4));
+    ctx->fp32_chunk = chunk;
+    return NERF_OK;
+}
+}  // namespace nerf
+
+static int check_ready(nerf_ctx* ctx, int net) {
+    if (!ctx->weights_set[net]) return fail(NERF_ERR_STATE, "weights of this net were never set (nerf_set_weights)");
+    return NERF_OK;
+}
+
+extern "C" int nerf_mlp_forward_encoded(nerf_ctx* ctx, int net, const float* rays_enc, const float* dirs_enc,
+                                        int64_t n, float* preds, void* stream) {
+    NERF_CHECK_ARG(ctx && rays_enc && dirs_enc && preds && n >= 0, "bad arguments");
+    NERF_CHECK_ARG(net == 0 || net == 1, "net must be 0 or 1");
+    int rc = check_ready(ctx, net);
+    if (rc) return rc;
+    if (n == 0) return NERF_OK;
+    return mlp_fp32_forward_encoded(ctx, net, rays_enc, dirs_enc, n, preds, (cudaStream_t)stream);
+}
+
+extern "C" int nerf_mlp_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t,
+                                     int64_t batch, int num_samples, int precision, float* preds, void* stream) {
+    NERF_CHECK_ARG(ctx && o && d && t && preds && batch >= 0 && num_samples >= 1, "bad arguments");
+    NERF_CHECK_ARG(net == 0 || net == 1, "net must be 0 or 1");
+    int rc = check_ready(ctx, net);
+    if (rc) return rc;
+    if (batch == 0) return NERF_OK;
+    if (precision == NERF_PRECISION_FP32)
+        return mlp_fp32_forward_rays(ctx, net, o, d, t, batch, num_samples, preds, (cudaStream_t)stream);
+    NERF_CHECK_ARG(precision == NERF_PRECISION_BF16_TC, "unknown precision");
+    std::string why;
+    if (!tc_supported(ctx->cfg, &why)) return fail(NERF_ERR_INVALID, why);
+    return tc_forward_rays(ctx, net, o, d, t, batch, num_samples, preds, false, (cudaStream_t)stream);
+}
+
+// NeRFTrainer.forward_pass (models.py:151-176)
+static int forward_pass_impl(nerf_ctx* ctx, const float* o, const float* d, const float* t, const float* u_pdf,
+                             int64_t B, int precision, bool save, const nerf_forward_out* out, cudaStream_t st) {
+    const nerf_config& c = ctx->cfg;
+    const int Nc = c.ns_coarse, Nf = c.ns_fine, Na = Nc + Nf;
+    nerf_forward_out z = {};
+    if (out) z = *out;
+    float* pred_c = z.pred_c ? z.pred_c : ctx->fw_pred_c;
+    float* pred_f = z.pred_f ? z.pred_f : ctx->fw_pred_f;
+    float* w_c = z.w_c ? z.w_c : ctx->fw_w_c;
+    float* w_f = z.w_f ? z.w_f : ctx->fw_w_f;
+    float* t_all = z.t_all ? z.t_all : ctx->fw_t_all;
+    float* rgb_c = z.rgb_c ? z.rgb_c : ctx->fw_rgb_c;
+    float* rgb_f = z.rgb_f ? z.rgb_f : ctx->fw_rgb_f;
+    int rc;
+    auto mlp = [&](int net, const float* tt, int N, float* preds) -> int {
+        if (precision == NERF_PRECISION_FP32) return mlp_fp32_forward_rays(ctx, net, o, d, tt, B, N, preds, st);
+        return tc_forward_rays(ctx, net, o, d, tt, B, N, preds, save, st);
+    };
+    if ((rc = mlp(NERF_NET_COARSE, t, Nc, pred_c))) return rc;                                       // :152-157
+    if ((rc = nerf_volume_render(pred_c, t, B, Nc, rgb_c, z.depth_c, w_c, z.acc_c, st))) return rc;  // :164
+    if ((rc = nerf_resample_merge(t, w_c, u_pdf, B, Nc, Nf, t_all, ctx->fw_src_idx, st))) return rc; // :165-167
+    if ((rc = mlp(NERF_NET_FINE, t_all, Na, pred_f))) return rc;                                     // :169-173
+    if ((rc = nerf_volume_render(pred_f, t_all, B, Na, rgb_f, z.depth_f, w_f, z.acc_f, st))) return rc;  // :175
+    return NERF_OK;
+}
+
+extern "C" int nerf_forward_pass(nerf_ctx* ctx, const float* o, const float* d, const float* t, const float* u_pdf,
+                                 int64_t batch, int precision, const nerf_forward_out* out, void* stream) {
+    NERF_CHECK_ARG(ctx && o && d && t && u_pdf && batch >= 0, "bad arguments");
+    NERF_CHECK_ARG(batch <= ctx->cfg.max_rays, "batch exceeds cfg.max_rays");
+    NERF_CHECK_ARG(precision == NERF_PRECISION_FP32 || precision == NERF_PRECISION_BF16_TC, "unknown precision");
+    int rc = check_ready(ctx, 0);
+    if (rc) return rc;
+    if ((rc = check_ready(ctx, 1))) return rc;
+    if (precision == NERF_PRECISION_BF16_TC) {
+        std::string why;
+        if (!tc_supported(ctx->cfg, &why)) return fail(NERF_ERR_INVALID, why);
+    }
+    if (batch == 0) return NERF_OK;
+    return forward_pass_impl(ctx, o, d, t, u_pdf, batch, precision, false, out, (cudaStream_t)stream);
+}
+
+// NeRFTrainer.train_step up to (not including) apply_gradients  (models.py:88-106)
+extern "C" int nerf_train_forward_backward(nerf_ctx* ctx, const float* images, const float* o, const float* d,
+                                           const float* t, const float* u_pdf, int64_t batch, float* metrics_dev,
+                                           void* stream) {
+    NERF_CHECK_ARG(ctx && images && o && d && t && u_pdf && metrics_dev && batch >= 1, "bad arguments");
+    NERF_CHECK_ARG(batch <= ctx->cfg.max_rays, "batch exceeds cfg.max_rays");
+    if (!ctx->cfg.training || !ctx->grads) return fail(NERF_ERR_STATE, "ctx was not created with training=1");
+    std::string why;
+    if (!tc_supported(ctx->cfg, &why)) return fail(NERF_ERR_INVALID, why);
+    if (!ctx->cfg.stop_grad_samples)
+        return fail(NERF_ERR_INVALID,
+                    "the CUDA backward implements stop_grad_samples=1 only this round (reference quirk Q5, DESIGN.md)");
+    int rc = check_ready(ctx, 0);
+    if (rc) return rc;
+    if ((rc = check_ready(ctx, 1))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Nc = ctx->cfg.ns_coarse, Na = Nc + ctx->cfg.ns_fine;
+    if ((rc = forward_pass_impl(ctx, o, d, t, u_pdf, batch, NERF_PRECISION_BF16_TC, true, nullptr, st))) return rc;
+    if ((rc = nerf_metrics_grad(images, ctx->fw_rgb_c, ctx->fw_rgb_f, batch, metrics_dev, ctx->tr_drgb_c,
+                                ctx->tr_drgb_f, st)))
+        return rc;
+    if ((rc = nerf_volume_render_bwd(ctx->fw_pred_c, t, ctx->tr_drgb_c, nullptr, batch, Nc, ctx->tr_dpred_c, nullptr, st)))
+        return rc;
+    if ((rc = nerf_volume_render_bwd(ctx->fw_pred_f, ctx->fw_t_all, ctx->tr_drgb_f, nullptr, batch, Na,
+                                     ctx->tr_dpred_f, nullptr, st)))
+        return rc;
+    NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * ctx->n_params * 4, st));
+    if ((rc = tc_backward(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dpred_f, st))) return rc;
+    if ((rc = tc_backward(ctx, NERF_NET_COARSE, o, d, t, batch, Nc, ctx->tr_dpred_c, st))) return rc;
+    return NERF_OK;
+}
+
+extern "C" int nerf_adam_step(nerf_ctx* ctx, float grad_scale, void* stream) {
+    NERF_CHECK_ARG(ctx != nullptr, "null ctx");
+    if (!ctx->grads) return fail(NERF_ERR_STATE, "nerf_adam_step: ctx was not created with training=1");
+    ctx->adam_step += 1;
+    int rc = nerf_adam_flat(ctx->params, ctx->grads, ctx->adam_m, ctx->adam_v, 2 * ctx->n_params, ctx->adam_step,
+                            ctx->cfg.learning_rate, grad_scale, stream);
+    ctx->packed_valid[0] = ctx->packed_valid[1] = false;
+    return rc;
+}

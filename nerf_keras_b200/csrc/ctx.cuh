@@ -1,0 +1,71 @@
+// nerf_ctx: per-GPU state of the B200 NeRF path.  The library owns weights (fp32 master + packed bf16
+// operand images), gradients, Adam moments and all workspaces; callers own every I/O buffer.
+#pragma once
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace nerf {
+
+struct LayerInfo {
+    int fan_in, fan_out;
+    int64_t w_off, b_off;  // float offsets inside one net's flat blob
+};
+
+}  // namespace nerf
+
+struct nerf_ctx {
+    nerf_config cfg;
+    int device = 0;
+    std::vector<nerf::LayerInfo> layers;  // d0..d{L-1}, sigma, feature, ddir, rgb
+    int64_t n_params = 0;                 // per net
+
+    // fp32 master state, [coarse | fine]
+    float* params = nullptr;
+    float* grads = nullptr;
+    float* adam_m = nullptr;
+    float* adam_v = nullptr;
+    int64_t adam_step = 0;
+    bool weights_set[2] = {false, false};
+
+    // tcgen05 operand images (bf16, 128B-swizzled 16 KB chunks) + fp32 side tables, per net
+    __nv_bfloat16* w_fwd[2] = {nullptr, nullptr};  // forward chunk stream  (72 chunks)
+    __nv_bfloat16* w_bwd[2] = {nullptr, nullptr};  // backward (transposed) chunk stream
+    float* side[2] = {nullptr, nullptr};           // biases + fp32 head weights (see mlp_tc.cu)
+    bool packed_valid[2] = {false, false};
+
+    // fp32 path workspace (allocated on first use)
+    int64_t fp32_chunk = 0;
+    float *ws_a = nullptr, *ws_b = nullptr, *ws_c = nullptr, *ws_encx = nullptr, *ws_encd = nullptr;
+
+    // forward_pass / train workspace, sized for cfg.max_rays
+    float *fw_pred_c = nullptr, *fw_pred_f = nullptr, *fw_w_c = nullptr, *fw_w_f = nullptr, *fw_t_all = nullptr;
+    float *fw_rgb_c = nullptr, *fw_rgb_f = nullptr, *fw_dirbias = nullptr;
+    int32_t* fw_src_idx = nullptr;
+
+    // training workspace (cfg.training): saved activation images and gradient images, per net
+    __nv_bfloat16* act_save[2] = {nullptr, nullptr};
+    __nv_bfloat16* dz_save[2] = {nullptr, nullptr};
+    float *tr_dpred_c = nullptr, *tr_dpred_f = nullptr, *tr_drgb_c = nullptr, *tr_drgb_f = nullptr;
+    float* tr_ddirbias = nullptr;
+};
+
+namespace nerf {
+
+int ensure_fp32_workspace(nerf_ctx* ctx);
+int mlp_fp32_forward_encoded(nerf_ctx* ctx, int net, const float* enc_x, const float* enc_d, int64_t n, float* preds,
+                             cudaStream_t st);
+int mlp_fp32_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
+                          float* preds, cudaStream_t st);
+
+// mlp_tc.cu
+int tc_supported(const nerf_config& cfg, std::string* why);
+int tc_alloc(nerf_ctx* ctx);
+void tc_free(nerf_ctx* ctx);
+int tc_pack_weights(nerf_ctx* ctx, int net, cudaStream_t st);
+int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
+                    float* preds, bool save_acts, cudaStream_t st);
+
+}  // namespace nerf

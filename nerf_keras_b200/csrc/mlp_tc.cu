@@ -1,0 +1,660 @@
+// Fused NeRF MLP forward on Blackwell tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// One persistent CTA per SM processes pairs of 128-sample sub-tiles (A, B).  Per sub-tile the whole
+// network of models.py:24-62 runs without leaving the SM:
+//   positional encoding (data_utils.py:7-21, fused sample_rays :68-70) is computed in registers and
+//   written as the bf16 A-operand tile of the first GEMM; every Dense layer is a chain of
+//   tcgen05.mma (M=128, N=128, K=16, bf16 in / fp32 accumulate in TMEM) over weight chunks that a
+//   producer warp streams from L2 with bulk async copies (TMA engine) through a 5-stage ring; the
+//   epilogue warps read the accumulator with tcgen05.ld, add bias, apply ReLU, round to bf16 and
+//   write the next layer's A-operand tile straight back into shared memory (128B-swizzled,
+//   K-major).  The two sub-tiles share every weight chunk (halving L2->SMEM traffic) and are kept
+//   a few chunks apart so that one sub-tile's epilogue overlaps the other's MMAs.
+//   sigma (256->1) and rgb (128->3) heads are fp32 dot products in the epilogues of the layers that
+//   feed them; the direction encoding is constant along a ray, so its contribution to the `ddir`
+//   layer (models.py:48-54) is hoisted into a per-ray fp32 bias computed by dirbias_kernel.
+//
+// Shared memory (225.4 KB): 2 x 64 KB activation tiles, 5 x 16 KB weight ring, 12 KB fp32 side
+// table (biases + head weights), mbarriers.  TMEM: 2 x 256 fp32 columns (all 512).
+#include "common.cuh"
+#include "ctx.cuh"
+#include "tc5.cuh"
+
+using namespace nerf;
+using namespace tc5;
+
+namespace {
+
+constexpr int H = 256;            // hidden width
+constexpr int ENC_X = 63;         // 3 + 6*10
+constexpr int ENC_D = 27;         // 3 + 6*4
+constexpr int TILE_M = 128;       // rows per sub-tile
+constexpr int CHUNK_BYTES = 16384;  // [128 n-rows x 64 k] bf16, 128B swizzle
+constexpr int CHUNK_ELEMS = CHUNK_BYTES / 2;
+constexpr int N_PHASES = 11;
+constexpr int N_CHUNKS = 72;
+constexpr int STAGES = 5;
+constexpr int LAG_MAX = 4;        // sub-tile A may run at most this many chunks ahead of B
+constexpr int LAG_TARGET = 3;
+
+// phases: L0, L1, L2, L3, L4, L5a (h part), L5b (skip part), L6, L7, feature, ddir
+__constant__ int c_ph_chunks[N_PHASES] = {2, 8, 8, 8, 8, 8, 2, 8, 8, 8, 4};
+__constant__ int c_ph_kb[N_PHASES] = {1, 4, 4, 4, 4, 4, 1, 4, 4, 4, 4};
+__constant__ int c_ph_first[N_PHASES] = {0, 2, 10, 18, 26, 34, 42, 44, 52, 60, 68};
+__constant__ int c_chunk_phase[N_CHUNKS] = {
+    0, 0,
+    1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4,
+    5, 5, 5, 5, 5, 5, 5, 5, 6, 6,
+    7, 7, 7, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8, 9, 9, 9, 9, 9, 9, 9, 9, 10, 10, 10, 10};
+
+// fp32 side table offsets (floats)
+constexpr int SIDE_BIAS = 0;        // 8 x 256 trunk biases
+constexpr int SIDE_BFEAT = 2048;    // 256
+constexpr int SIDE_BDDIR = 2304;    // 128
+constexpr int SIDE_WSIG = 2432;     // 256
+constexpr int SIDE_WRGB = 2688;     // 3 x 128 ([channel][k])
+constexpr int SIDE_BSIG = 3072;     // 1
+constexpr int SIDE_BRGB = 3073;     // 3
+constexpr int SIDE_FLOATS = 3080;
+
+// shared memory map (bytes, relative to the 1024-aligned base)
+constexpr int SM_ACT = 0;                                  // 2 x 65536
+constexpr int SM_RING = 131072;                            // STAGES x 16384
+constexpr int SM_SIDE = SM_RING + STAGES * CHUNK_BYTES;    // 12320
+constexpr int SM_BAR = SM_SIDE + SIDE_FLOATS * 4;          // mbarriers
+constexpr int SM_FULL = SM_BAR;                            // STAGES
+constexpr int SM_EMPTY = SM_FULL + 8 * STAGES;             // STAGES
+constexpr int SM_ACCF = SM_EMPTY + 8 * STAGES;             // 2
+constexpr int SM_ACTR = SM_ACCF + 16;                      // 2
+constexpr int SM_TMEM = SM_ACTR + 16;                      // u32
+constexpr int SM_TOTAL = SM_TMEM + 16;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
+
+constexpr int NUM_THREADS = 320;  // 8 worker warps (4 per sub-tile) + producer warp + MMA warp
+
+// per-net layer offsets inside the flat fp32 blob (floats), filled by the host
+struct BlobOffsets {
+    int64_t w[12];  // d0..d7, sigma, feature, ddir, rgb
+    int64_t b[12];
+};
+
+struct FwdParams {
+    const float* o;
+    const float* d;
+    const float* t;
+    int N;                 // samples per ray
+    int64_t M;             // total samples = rays * N
+    int64_t n_pairs;       // ceil(M / 256)
+    const __nv_bfloat16* w_chunks;
+    const float* side;
+    const float* dirbias;  // (rays, 128)
+    float4* preds;         // (M) [r,g,b,sigma] raw
+    __nv_bfloat16* act_save;  // optional saved-activation images (training)
+};
+
+// saved activation image layout per 128-row tile (bytes): enc 16 KB, h1..h8 8 x 64 KB, feature 64 KB, hd 32 KB
+constexpr int64_t SAVE_ENC = 0;
+constexpr int64_t SAVE_H = 16384;            // + 65536 * i, i = 0..7  (outputs of L0..L7)
+constexpr int64_t SAVE_FEAT = 16384 + 8 * 65536;
+constexpr int64_t SAVE_HD = SAVE_FEAT + 65536;
+constexpr int64_t SAVE_TILE_BYTES = SAVE_HD + 32768;  // 638976
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 master blob -> bf16 chunk stream (K-major B operand, B[n][k] = W[k][n])
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fwd_weight_at(const float* __restrict__ blob, const BlobOffsets& off, int phase,
+                                               int n, int k) {
+    // returns W_phase[k][n] with zero padding
+    switch (phase) {
+        case 0: return (k < ENC_X) ? blob[off.w[0] + (int64_t)k * H + n] : 0.f;
+        case 1: case 2: case 3: case 4: return blob[off.w[phase] + (int64_t)k * H + n];
+        case 5: return blob[off.w[5] + (int64_t)k * H + n];
+        case 6: return (k < ENC_X) ? blob[off.w[5] + (int64_t)(H + k) * H + n] : 0.f;
+        case 7: return blob[off.w[6] + (int64_t)k * H + n];
+        case 8: return blob[off.w[7] + (int64_t)k * H + n];
+        case 9: return blob[off.w[9] + (int64_t)k * H + n];                 // feature
+        default: return blob[off.w[10] + (int64_t)k * (H / 2) + n];         // ddir rows 0..255, n < 128
+    }
+}
+
+__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ blob, BlobOffsets off,
+                                                       __nv_bfloat16* __restrict__ chunks, float* __restrict__ side) {
+    // one thread per 16-byte group: chunk g, row n (0..127), k-group kg (0..7)
+    const int total = N_CHUNKS * 128 * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int g = i / (128 * 8);
+        int rem = i - g * 128 * 8;
+        int n = rem >> 3, kg = rem & 7;
+        int phase = c_chunk_phase[g];
+        int j = g - c_ph_first[phase];
+        int kbs = c_ph_kb[phase];
+        int h = j / kbs, kb = j - h * kbs;
+        uint32_t packed[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int k0 = kb * 64 + kg * 8 + 2 * q;
+            float a = fwd_weight_at(blob, off, phase, h * 128 + n, k0);
+            float b = fwd_weight_at(blob, off, phase, h * 128 + n, k0 + 1);
+            packed[q] = pack_bf16x2(a, b);
+        }
+        uint8_t* dst = reinterpret_cast<uint8_t*>(chunks) + (size_t)g * CHUNK_BYTES + sw128_offset(n, kg * 8);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    // side table
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < SIDE_FLOATS; i += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (i < SIDE_BFEAT) v = blob[off.b[i >> 8] + (i & 255)];
+        else if (i < SIDE_BDDIR) v = blob[off.b[9] + (i - SIDE_BFEAT)];
+        else if (i < SIDE_WSIG) v = blob[off.b[10] + (i - SIDE_BDDIR)];
+        else if (i < SIDE_WRGB) v = blob[off.w[8] + (i - SIDE_WSIG)];                    // sigma W (256,1)
+        else if (i < SIDE_BSIG) { int q = i - SIDE_WRGB; int ch = q >> 7, k = q & 127; v = blob[off.w[11] + k * 3 + ch]; }
+        else if (i == SIDE_BSIG) v = blob[off.b[8]];
+        else if (i < SIDE_BRGB + 3) v = blob[off.b[11] + (i - SIDE_BRGB)];
+        side[i] = v;
+    }
+}
+
+// per-ray fp32 bias of the ddir layer: dirbias[ray][j] = sum_k enc_dir(d_ray)[k] * Wddir[256+k][j]
+__global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ d, int64_t rays,
+                                                      const float* __restrict__ wddir /* (283,128) */,
+                                                      float* __restrict__ dirbias) {
+    __shared__ float enc[ENC_D];
+    for (int64_t ray = blockIdx.x; ray < rays; ray += gridDim.x) {
+        if (threadIdx.x < ENC_D) {
+            int c = threadIdx.x;
+            float v;
+            if (c < 3) v = d[ray * 3 + c];
+            else {
+                int q = c - 3, i = q / 6, r = q - i * 6, comp = r % 3;
+                float arg = __fmul_rn(exp2f((float)i), d[ray * 3 + comp]);
+                v = (r >= 3) ? cosf(arg) : sinf(arg);
+            }
+            enc[c] = v;
+        }
+        __syncthreads();
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < ENC_D; ++k) acc = fmaf(enc[k], wddir[(int64_t)(H + k) * (H / 2) + threadIdx.x], acc);
+        dirbias[ray * (H / 2) + threadIdx.x] = acc;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused forward kernel
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_row_chunk(uint32_t act_base, int kblock, int row, int chunk16, uint32_t a,
+                                                uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t addr = act_base + kblock * (TILE_M * 128) + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const FwdParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t bar_full = base + SM_FULL, bar_empty = base + SM_EMPTY, bar_accf = base + SM_ACCF,
+                   bar_actr = base + SM_ACTR;
+    float* side = reinterpret_cast<float*>(smem + SM_SIDE);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_accf + 8 * s, 1);
+            mbar_init(bar_actr + 8 * s, TILE_M);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(base + SM_TMEM, 512);
+    for (int i = threadIdx.x; i < SIDE_FLOATS; i += NUM_THREADS) side[i] = P.side[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t my_pairs = (P.n_pairs > blockIdx.x) ? (P.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_chunks = my_pairs * N_CHUNKS;
+
+    if (warp == 8) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            for (int64_t g = 0; g < total_chunks; ++g) {
+                int slot = (int)(g % STAGES);
+                int64_t k = g / STAGES;
+                if (k > 0) mbar_wait(bar_empty + 8 * slot, (uint32_t)((k - 1) & 1), 1);
+                mbar_arrive_expect_tx(bar_full + 8 * slot, CHUNK_BYTES);
+                bulk_g2s(base + SM_RING + slot * CHUNK_BYTES, P.w_chunks + (size_t)(g % N_CHUNKS) * CHUNK_ELEMS,
+                         CHUNK_BYTES, bar_full + 8 * slot);
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+            int64_t g[2] = {0, 0};       // next chunk (global counter) per sub-tile
+            int64_t nstart[2] = {0, 0};  // number of phase starts consumed per sub-tile
+            uint32_t spins = 0;
+            while (g[0] < total_chunks || g[1] < total_chunks) {
+                int pick = -1;
+                bool can[2];
+                can[0] = g[0] < total_chunks && (g[0] - g[1]) < LAG_MAX;
+                can[1] = g[1] < g[0];
+                int first = ((g[0] - g[1]) < LAG_TARGET) ? 0 : 1;
+                for (int a = 0; a < 2 && pick < 0; ++a) {
+                    int s = a == 0 ? first : 1 - first;
+                    if (!can[s]) continue;
+                    int c = (int)(g[s] % N_CHUNKS);
+                    int ph = c_chunk_phase[c];
+                    bool ready = true;
+                    if (c == c_ph_first[ph]) ready = mbar_test(bar_actr + 8 * s, (uint32_t)(nstart[s] & 1));
+                    if (ready && s == 0) {
+                        int slot = (int)(g[0] % STAGES);
+                        ready = mbar_test(bar_full + 8 * slot, (uint32_t)((g[0] / STAGES) & 1));
+                    }
+                    if (ready) pick = s;
+                }
+                if (pick < 0) {
+                    if (++spins > TC5_SPIN_LIMIT) {
+                        printf("tc5: MMA issuer stalled block=%d gA=%lld gB=%lld\n", blockIdx.x, (long long)g[0],
+                               (long long)g[1]);
+                        __trap();
+                    }
+                    continue;
+                }
+                spins = 0;
+                const int s = pick;
+                const int c = (int)(g[s] % N_CHUNKS);
+                const int ph = c_chunk_phase[c];
+                const int j = c - c_ph_first[ph];
+                const int kbs = c_ph_kb[ph];
+                const int h = j / kbs, kb = j - h * kbs;
+                if (j == 0) ++nstart[s];
+                tc_fence_after();
+                const int slot = (int)(g[s] % STAGES);
+                const uint32_t a_base = base + SM_ACT + s * 65536 + (kbs == 1 ? 0 : kb) * (TILE_M * 128);
+                const uint32_t b_base = base + SM_RING + slot * CHUNK_BYTES;
+                const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
+                const bool acc0 = (kb > 0) || (ph == 6);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint64_t ad = make_sdesc_sw128(a_base + k * 32, 16, 1024);
+                    uint64_t bd = make_sdesc_sw128(b_base + k * 32, 16, 1024);
+                    mma_bf16_ss(d_tmem, ad, bd, idesc, (acc0 || k > 0) ? 1u : 0u);
+                }
+                if (s == 1) mma_commit(bar_empty + 8 * slot);               // both sub-tiles have used this chunk
+                if (j == c_ph_chunks[ph] - 1) mma_commit(bar_accf + 8 * s);  // accumulator of this phase complete
+                ++g[s];
+            }
+        }
+    } else {
+        // ===================== workers: PE prologue + epilogues =====================
+        const int s = warp >> 2;
+        const int row = threadIdx.x - s * TILE_M;
+        const uint32_t act_base = base + SM_ACT + s * 65536;
+        const uint32_t t_lane = tmem_base + (uint32_t(32 * (warp & 3)) << 16) + s * 256;
+        const bool elected = (row == 0);
+        uint32_t accf_par = 0;
+        uint32_t E[32];
+
+        for (int64_t it = 0; it < my_pairs; ++it) {
+            const int64_t pair = blockIdx.x + it * gridDim.x;
+            const int64_t tile = pair * 2 + s;
+            const int64_t g_row = tile * TILE_M + row;
+            const bool valid = g_row < P.M;
+            const int64_t gr = valid ? g_row : (P.M - 1);
+            const int64_t ray = gr / P.N;
+            uint8_t* save_tile = SAVE ? reinterpret_cast<uint8_t*>(P.act_save) + tile * SAVE_TILE_BYTES : nullptr;
+
+            // ---- positional encoding of this row's sample point (fp32, accurate sincosf) ----
+            {
+                const float tv = P.t[gr];
+                float p[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(P.o[ray * 3 + c], __fmul_rn(P.d[ray * 3 + c], tv));
+                float e[64];
+                e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) {
+                    const float sc = (float)(1 << i);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float sv, cv;
+                        sincosf(sc * p[c], &sv, &cv);
+                        e[3 + 6 * i + c] = sv;
+                        e[3 + 6 * i + 3 + c] = cv;
+                    }
+                }
+                e[63] = 0.f;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) E[q] = pack_bf16x2(e[2 * q], e[2 * q + 1]);
+            }
+            if (SAVE) {  // previous tile's last bulk store must have finished reading act before we overwrite it
+                if (elected) bulk_wait_read0();
+                named_bar_sync(1 + s, TILE_M);
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) store_row_chunk(act_base, 0, row, c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            if (SAVE) {
+                named_bar_sync(1 + s, TILE_M);
+                if (elected) { bulk_s2g(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
+            }
+            mbar_arrive(bar_actr + 8 * s);
+
+            float sig = 0.f;
+            for (int ph = 0; ph < N_PHASES; ++ph) {
+                mbar_wait(bar_accf + 8 * s, accf_par, 2);
+                accf_par ^= 1;
+                tc_fence_after();
+                if (SAVE) {
+                    if (elected) bulk_wait_read0();
+                    named_bar_sync(1 + s, TILE_M);
+                }
+                if (ph == 5) {
+                    // L5a done: stage the skip-connection encoding as K-block 0 for L5b
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        store_row_chunk(act_base, 0, row, c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    mbar_arrive(bar_actr + 8 * s);
+                    continue;
+                }
+                if (ph < 10) {
+                    // trunk layer / feature epilogue: bias (+ReLU) -> bf16 -> next A tile
+                    const int layer = (ph <= 4) ? ph : (ph == 6 ? 5 : (ph == 7 ? 6 : (ph == 8 ? 7 : 8)));
+                    const float* bias = side + (layer < 8 ? SIDE_BIAS + layer * H : SIDE_BFEAT);
+                    const bool relu = layer < 8;
+#pragma unroll 1
+                    for (int cg = 0; cg < 8; ++cg) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + cg * 32, v);
+                        tmem_ld_wait();
+                        uint32_t pk[16];
+                        const float4* b4 = reinterpret_cast<const float4*>(bias + cg * 32);
+                        const float4* s4 = reinterpret_cast<const float4*>(side + SIDE_WSIG + cg * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 bb = b4[q];
+                            float x0 = __uint_as_float(v[4 * q]) + bb.x;
+                            float x1 = __uint_as_float(v[4 * q + 1]) + bb.y;
+                            float x2 = __uint_as_float(v[4 * q + 2]) + bb.z;
+                            float x3 = __uint_as_float(v[4 * q + 3]) + bb.w;
+                            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+                            if (ph == 8) {
+                                const float4 ws = s4[q];
+                                sig = fmaf(x0, ws.x, sig); sig = fmaf(x1, ws.y, sig);
+                                sig = fmaf(x2, ws.z, sig); sig = fmaf(x3, ws.w, sig);
+                            }
+                            pk[2 * q] = pack_bf16x2(x0, x1);
+                            pk[2 * q + 1] = pack_bf16x2(x2, x3);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1],
+                                            pk[4 * c + 2], pk[4 * c + 3]);
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    if (SAVE) {
+                        named_bar_sync(1 + s, TILE_M);
+                        if (elected) {
+                            int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
+                            bulk_s2g(save_tile + off, act_base, 65536);
+                            bulk_commit();
+                        }
+                    }
+                    mbar_arrive(bar_actr + 8 * s);
+                } else {
+                    // ddir epilogue: + bias + per-ray direction bias, ReLU, rgb head (fp32), write preds
+                    float r = 0.f, gch = 0.f, b = 0.f;
+                    const float* db = P.dirbias + ray * (H / 2);
+#pragma unroll 1
+                    for (int cg = 0; cg < 4; ++cg) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + cg * 32, v);
+                        tmem_ld_wait();
+                        uint32_t pk[16];
+                        const float4* bd4 = reinterpret_cast<const float4*>(side + SIDE_BDDIR + cg * 32);
+                        const float4* wr4 = reinterpret_cast<const float4*>(side + SIDE_WRGB + cg * 32);
+                        const float4* wg4 = reinterpret_cast<const float4*>(side + SIDE_WRGB + 128 + cg * 32);
+                        const float4* wb4 = reinterpret_cast<const float4*>(side + SIDE_WRGB + 256 + cg * 32);
+                        const float4* db4 = reinterpret_cast<const float4*>(db + cg * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 bb = bd4[q], dd = __ldg(db4 + q), wr = wr4[q], wg = wg4[q], wb = wb4[q];
+                            float x0 = fmaxf(__uint_as_float(v[4 * q]) + bb.x + dd.x, 0.f);
+                            float x1 = fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y + dd.y, 0.f);
+                            float x2 = fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z + dd.z, 0.f);
+                            float x3 = fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w + dd.w, 0.f);
+                            r = fmaf(x0, wr.x, r); r = fmaf(x1, wr.y, r); r = fmaf(x2, wr.z, r); r = fmaf(x3, wr.w, r);
+                            gch = fmaf(x0, wg.x, gch); gch = fmaf(x1, wg.y, gch); gch = fmaf(x2, wg.z, gch); gch = fmaf(x3, wg.w, gch);
+                            b = fmaf(x0, wb.x, b); b = fmaf(x1, wb.y, b); b = fmaf(x2, wb.z, b); b = fmaf(x3, wb.w, b);
+                            v[4 * q] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
+                            v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
+                        }
+                        if (SAVE) {
+#pragma unroll
+                            for (int q = 0; q < 16; ++q)
+                                pk[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1],
+                                                pk[4 * c + 2], pk[4 * c + 3]);
+                        }
+                    }
+                    if (valid)
+                        P.preds[g_row] = make_float4(r + side[SIDE_BRGB], gch + side[SIDE_BRGB + 1],
+                                                     b + side[SIDE_BRGB + 2], sig + side[SIDE_BSIG]);
+                    tc_fence_before();
+                    if (SAVE) {
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + s, TILE_M);
+                        if (elected) { bulk_s2g(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
+                    }
+                }
+            }
+        }
+        if (SAVE && elected) bulk_wait_all0();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// self-test GEMM (single CTA): validates descriptor / swizzle / TMEM conventions on hardware.
+// mode 0: A (128,K) , B (N,K)  row-major fp32 -> C = A * B^T      (K-major operands)
+// mode 1: A (K,128) , B (K,N)  row-major fp32 -> C = A^T * B      (MN-major operands)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                               float* __restrict__ C, int N, int K, int mode) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // layout: A image, B image, barrier, tmem slot
+    const uint32_t a_bytes = 128 * K * 2, b_bytes = N * K * 2;
+    uint8_t* a_img = smem;
+    uint8_t* b_img = smem + a_bytes;
+    const uint32_t bar = base + a_bytes + b_bytes;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + a_bytes + b_bytes + 16);
+
+    if (mode == 0) {
+        // K-major: K-blocks of 64, each [rows x 128 B]
+        for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+            int r = i / K, k = i - r * K;
+            uint32_t off = (k >> 6) * (128 * 128) + sw128_offset(r, k & 63);
+            *reinterpret_cast<__nv_bfloat16*>(a_img + off) = __float2bfloat16(A[i]);
+        }
+        for (int i = threadIdx.x; i < N * K; i += blockDim.x) {
+            int r = i / K, k = i - r * K;
+            uint32_t off = (k >> 6) * (N * 128) + sw128_offset(r, k & 63);
+            *reinterpret_cast<__nv_bfloat16*>(b_img + off) = __float2bfloat16(B[i]);
+        }
+    } else {
+        // MN-major: blocks of 64 MN-elements, each [K rows x 128 B]
+        for (int i = threadIdx.x; i < K * 128; i += blockDim.x) {
+            int k = i / 128, m = i - k * 128;
+            uint32_t off = (m >> 6) * (K * 128) + sw128_offset(k, m & 63);
+            *reinterpret_cast<__nv_bfloat16*>(a_img + off) = __float2bfloat16(A[i]);
+        }
+        for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
+            int k = i / N, n = i - k * N;
+            uint32_t off = (n >> 6) * (K * 128) + sw128_offset(k, n & 63);
+            *reinterpret_cast<__nv_bfloat16*>(b_img + off) = __float2bfloat16(B[i]);
+        }
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(base + a_bytes + b_bytes + 16, 256);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N, mode, mode);
+        for (int k16 = 0; k16 < K / 16; ++k16) {
+            uint64_t ad, bd;
+            if (mode == 0) {
+                int kb = k16 >> 2, kk = k16 & 3;
+                ad = make_sdesc_sw128(base + kb * (128 * 128) + kk * 32, 16, 1024);
+                bd = make_sdesc_sw128(base + a_bytes + kb * (N * 128) + kk * 32, 16, 1024);
+            } else {
+                ad = make_sdesc_sw128(base + k16 * 2048, K * 128, 1024);
+                bd = make_sdesc_sw128(base + a_bytes + k16 * 2048, K * 128, 1024);
+            }
+            mma_bf16_ss(tmem_base, ad, bd, idesc, k16 > 0 ? 1u : 0u);
+        }
+        mma_commit(bar);
+    }
+    mbar_wait(bar, 0, 9);
+    tc_fence_after();
+    const int row = threadIdx.x;
+    for (int cg = 0; cg < N / 32; ++cg) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(32 * warp) << 16) + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) C[(int64_t)row * N + cg * 32 + q] = __uint_as_float(v[q]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    (void)lane;
+}
+
+BlobOffsets make_offsets(const nerf_ctx* ctx) {
+    BlobOffsets off;
+    for (int i = 0; i < 12; ++i) {
+        off.w[i] = ctx->layers[i].w_off;
+        off.b[i] = ctx->layers[i].b_off;
+    }
+    return off;
+}
+
+}  // namespace
+
+namespace nerf {
+
+int tc_supported(const nerf_config& c, std::string* why) {
+    if (c.num_layers != 8 || c.hidden_dim != 256 || c.skip_layer != 4 || c.l_xyz != 10 || c.l_dir != 4) {
+        if (why) *why = "tcgen05 path is specialised to NUM_LAYERS=8, HIDDEN_DIM=256, SKIP_LAYER=4, L_XYZ=10, L_DIR=4";
+        return 0;
+    }
+    return 1;
+}
+
+int tc_alloc(nerf_ctx* ctx) {
+    for (int net = 0; net < 2; ++net) {
+        NERF_CUDA(cudaMalloc(&ctx->w_fwd[net], (size_t)N_CHUNKS * CHUNK_BYTES));
+        NERF_CUDA(cudaMalloc(&ctx->side[net], SIDE_FLOATS * sizeof(float)));
+    }
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    return NERF_OK;
+}
+
+void tc_free(nerf_ctx* ctx) {
+    for (int net = 0; net < 2; ++net) {
+        cudaFree(ctx->w_fwd[net]);
+        cudaFree(ctx->w_bwd[net]);
+        cudaFree(ctx->side[net]);
+    }
+}
+
+int tc_pack_weights(nerf_ctx* ctx, int net, cudaStream_t st) {
+    BlobOffsets off = make_offsets(ctx);
+    pack_fwd_kernel<<<num_sms(), 256, 0, st>>>(ctx->params + (int64_t)net * ctx->n_params, off, ctx->w_fwd[net],
+                                               ctx->side[net]);
+    NERF_LAUNCHED();
+    ctx->packed_valid[net] = true;
+    return NERF_OK;
+}
+
+int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
+                    float* preds, bool save_acts, cudaStream_t st) {
+    if (!ctx->packed_valid[net]) {
+        int rc = tc_pack_weights(ctx, net, st);
+        if (rc) return rc;
+    }
+    if (B > ctx->cfg.max_rays) return fail(NERF_ERR_INVALID, "tc_forward_rays: batch exceeds cfg.max_rays");
+    const float* blob = ctx->params + (int64_t)net * ctx->n_params;
+    dirbias_kernel<<<(unsigned)(B < 4 * num_sms() ? B : 4 * num_sms()), 128, 0, st>>>(
+        d, B, blob + ctx->layers[10].w_off, ctx->fw_dirbias);
+    NERF_LAUNCHED();
+    FwdParams P;
+    P.o = o; P.d = d; P.t = t; P.N = N;
+    P.M = B * (int64_t)N;
+    P.n_pairs = ceil_div(P.M, 2 * TILE_M);
+    P.w_chunks = ctx->w_fwd[net];
+    P.side = ctx->side[net];
+    P.dirbias = ctx->fw_dirbias;
+    P.preds = reinterpret_cast<float4*>(preds);
+    P.act_save = save_acts ? ctx->act_save[net] : nullptr;
+    int grid = (int)(P.n_pairs < num_sms() ? P.n_pairs : num_sms());
+    if (save_acts) {
+        if (!ctx->act_save[net]) return fail(NERF_ERR_STATE, "tc_forward_rays: ctx was not created with training=1");
+        nerf_mlp_fwd_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
+    } else {
+        nerf_mlp_fwd_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
+    }
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+
+int64_t tc_save_bytes_per_tile() { return SAVE_TILE_BYTES; }
+
+}  // namespace nerf
+
+extern "C" int nerf_selftest_gemm(const float* a, const float* b, float* c, int m, int n, int k, int mode,
+                                  void* stream) {
+    NERF_CHECK_ARG(a && b && c, "null pointer");
+    NERF_CHECK_ARG(m == 128 && (n == 128 || n == 256 || n == 64) && k >= 16 && k <= 256 && (k % 16) == 0,
+                   "supported: m=128, n in {64,128,256}, k multiple of 16 up to 256");
+    NERF_CHECK_ARG(mode == 1 || (k % 64) == 0, "mode 0 needs k % 64 == 0");
+    NERF_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 or 1");
+    size_t smem = (size_t)(128 + n) * k * 2 + 64 + 1024;
+    NERF_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selftest_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b, c, n, k, mode);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}

@@ -1,0 +1,401 @@
+"""Drop-in for the reference's `models.py`: `create_nerf_complete_model` and `NeRFTrainer` with the
+reference's signatures, running on the sm_100a kernels of libnerf_b200.so (no Keras, no TF).
+
+Differences that are forced by the platform and documented in DESIGN.md:
+  * random draws (`u_pdf` for sample_pdf) may be passed explicitly; otherwise torch's CUDA RNG;
+  * BATCH_NORM=true configs are rejected (out of scope this round);
+  * weights are saved as `.npz` keyed by layer role (h5py is not available).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .data_utils import _dev, _f32, _ptr, _stream
+
+PRECISION_BF16_TC = 0
+PRECISION_FP32 = 1
+
+_seed_state = {"rng": np.random.default_rng(42)}
+
+
+def set_random_seed(seed: int):
+    """keras.utils.set_random_seed (train_lego.py:22)."""
+    _seed_state["rng"] = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def layer_roles(num_layers: int) -> List[str]:
+    return [f"d{i}" for i in range(num_layers)] + ["sigma", "feature", "ddir", "rgb"]
+
+
+def layer_shapes(num_layers, hidden_dim, skip_layer, lxyz, ldir) -> List[Tuple[str, int, int]]:
+    """(role, fan_in, fan_out) in creation order -- models.py:24-62."""
+    exyz, edir = 3 + 6 * lxyz, 3 + 6 * ldir
+    out, fan_in = [], exyz
+    for i in range(num_layers):
+        out.append((f"d{i}", fan_in, hidden_dim))
+        fan_in = hidden_dim
+        if i % skip_layer == 0 and i > 0:
+            fan_in = hidden_dim + exyz
+    out += [("sigma", fan_in, 1), ("feature", fan_in, hidden_dim),
+            ("ddir", hidden_dim + edir, hidden_dim // 2), ("rgb", hidden_dim // 2, 3)]
+    return out
+
+
+class Adam:
+    """keras.optimizers.Adam(learning_rate=...) (train_lego.py:149-151); Keras defaults otherwise."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        if (beta_1, beta_2, epsilon) != (0.9, 0.999, 1e-7):
+            raise ValueError("the fused Adam kernel implements the Keras defaults beta_1=0.9, beta_2=0.999, epsilon=1e-7")
+        self.learning_rate = float(learning_rate)
+
+
+class MeanSquaredError:
+    """keras.losses.MeanSquaredError (train_lego.py:154): mean over every element."""
+
+    def __call__(self, y_true, y_pred):
+        return torch.mean((_f32(y_pred) - _f32(y_true)) ** 2)
+
+
+class _Mean:
+    def __init__(self, name):
+        self.name, self.total, self.count = name, 0.0, 0
+
+    def update_state(self, v):
+        self.total += float(v)
+        self.count += 1
+
+    def result(self):
+        return self.total / self.count if self.count else 0.0
+
+    def reset_state(self):
+        self.total, self.count = 0.0, 0
+
+
+class _Ctx:
+    """Owns one nerf_ctx (C side)."""
+
+    def __init__(self, arch: dict, ns_coarse, ns_fine, max_rays, training, learning_rate, stop_grad_samples=True):
+        _dev()
+        cfg = _lib.NerfConfig(arch["num_layers"], arch["hidden_dim"], arch["skip_layer"], arch["lxyz"], arch["ldir"],
+                              int(ns_coarse), int(ns_fine), int(max_rays), int(bool(arch["bn"])), int(bool(training)),
+                              float(learning_rate), int(bool(stop_grad_samples)))
+        self.cfg = cfg
+        self.handle = C.c_void_p()
+        _lib.check(_lib.lib().nerf_create(C.byref(cfg), C.byref(self.handle)), "nerf_create")
+        self.n_params = int(_lib.lib().nerf_param_count(C.byref(cfg)))
+        self.max_rays = int(max_rays)
+
+    def set_weights(self, net: int, blob: torch.Tensor):
+        blob = _f32(blob).reshape(-1)
+        _lib.check(_lib.lib().nerf_set_weights(self.handle, net, _ptr(blob), blob.numel(), _stream()), "nerf_set_weights")
+        torch.cuda.current_stream().synchronize()  # blob may be a temporary
+
+    def get_weights(self, net: int) -> torch.Tensor:
+        out = torch.empty((self.n_params,), device=_dev(), dtype=torch.float32)
+        _lib.check(_lib.lib().nerf_get_weights(self.handle, net, _ptr(out), out.numel(), _stream()), "nerf_get_weights")
+        return out
+
+    def grad_tensor(self) -> torch.Tensor:
+        """Zero-copy torch view of the ctx-owned flat gradient buffer [coarse | fine]."""
+        p, n = C.c_void_p(), C.c_int64()
+        _lib.check(_lib.lib().nerf_grad_buffer(self.handle, C.byref(p), C.byref(n)), "nerf_grad_buffer")
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (p.value, False), "version": 3}
+
+        self._raw_keepalive = _Raw()
+        return torch.as_tensor(self._raw_keepalive, device=_dev())
+
+    def close(self):
+        if self.handle:
+            _lib.lib().nerf_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NerfModel:
+    """What `create_nerf_complete_model` returns: the 8x256 skip MLP of models.py:24-62.
+
+    Callable like the Keras model: `model([rays_enc, dirs_enc])` -> (..., 4) = [r,g,b,sigma] raw
+    (fp32 kernels).  Weights follow the Keras Dense convention y = x @ W + b, W (in, out)."""
+
+    def __init__(self, num_layers, hidden_dim, skip_layer, lxyz, ldir, bn=False):
+        if bn:
+            raise ValueError("BATCH_NORM=true is not supported by the B200 path (DESIGN.md, out of scope)")
+        self.arch = dict(num_layers=int(num_layers), hidden_dim=int(hidden_dim), skip_layer=int(skip_layer),
+                         lxyz=int(lxyz), ldir=int(ldir), bn=bool(bn))
+        self.shapes = layer_shapes(num_layers, hidden_dim, skip_layer, lxyz, ldir)
+        rng = _seed_state["rng"]
+        parts = []
+        for _, fi, fo in self.shapes:  # Keras defaults: glorot_uniform kernel, zero bias
+            lim = math.sqrt(6.0 / (fi + fo))
+            parts.append(rng.uniform(-lim, lim, size=(fi * fo,)).astype(np.float32))
+            parts.append(np.zeros((fo,), dtype=np.float32))
+        self._host_blob = np.concatenate(parts)
+        self._owner: Optional[Tuple[_Ctx, int]] = None
+        self._own_ctx: Optional[_Ctx] = None
+
+    # -- weights ----------------------------------------------------------------------------------
+    def count_params(self) -> int:
+        return int(self._host_blob.size)
+
+    def get_flat_weights(self) -> np.ndarray:
+        if self._owner is not None:
+            ctx, net = self._owner
+            self._host_blob = ctx.get_weights(net).cpu().numpy()
+        return self._host_blob.copy()
+
+    def set_flat_weights(self, blob):
+        blob = np.asarray(blob, dtype=np.float32).reshape(-1)
+        if blob.size != self._host_blob.size:
+            raise ValueError(f"expected {self._host_blob.size} floats, got {blob.size}")
+        self._host_blob = blob.copy()
+        if self._owner is not None:
+            ctx, net = self._owner
+            ctx.set_weights(net, torch.from_numpy(self._host_blob))
+        if self._own_ctx is not None:
+            self._own_ctx.set_weights(0, torch.from_numpy(self._host_blob))
+
+    def get_weights(self) -> Dict[str, Dict[str, np.ndarray]]:
+        blob, out, off = self.get_flat_weights(), {}, 0
+        for role, fi, fo in self.shapes:
+            W = blob[off:off + fi * fo].reshape(fi, fo); off += fi * fo
+            b = blob[off:off + fo]; off += fo
+            out[role] = {"W": W.copy(), "b": b.copy()}
+        return out
+
+    def set_weights(self, weights: Dict[str, Dict[str, np.ndarray]]):
+        parts = []
+        for role, fi, fo in self.shapes:
+            W = np.asarray(weights[role]["W"], dtype=np.float32)
+            b = np.asarray(weights[role]["b"], dtype=np.float32)
+            if W.shape != (fi, fo) or b.shape != (fo,):
+                raise ValueError(f"bad shape for layer {role}")
+            parts += [W.reshape(-1), b]
+        self.set_flat_weights(np.concatenate(parts))
+
+    # -- call -------------------------------------------------------------------------------------
+    def __call__(self, inputs, training=False):
+        rays_enc, dirs_enc = inputs
+        x, dd = _f32(rays_enc), _f32(dirs_enc)
+        ex, ed = 3 + 6 * self.arch["lxyz"], 3 + 6 * self.arch["ldir"]
+        if x.shape[-1] != ex or dd.shape[-1] != ed or x.shape[:-1] != dd.shape[:-1]:
+            raise ValueError(f"expected inputs [(..., {ex}), (..., {ed})]")
+        if self._owner is not None:
+            ctx, net = self._owner
+        else:
+            if self._own_ctx is None:
+                self._own_ctx = _Ctx(self.arch, 2, 1, 1, False, 0.0)
+                self._own_ctx.set_weights(0, torch.from_numpy(self._host_blob))
+            ctx, net = self._own_ctx, 0
+        n = x.numel() // ex
+        out = torch.empty(x.shape[:-1] + (4,), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.lib().nerf_mlp_forward_encoded(ctx.handle, net, _ptr(x), _ptr(dd), n, _ptr(out), _stream()),
+                   "model call")
+        return out
+
+    predict = __call__
+
+
+def create_nerf_complete_model(num_layers, hidden_dim, skip_layer, lxyz, ldir, bn=False) -> NerfModel:
+    """models.py:24-62."""
+    return NerfModel(num_layers, hidden_dim, skip_layer, lxyz, ldir, bn)
+
+
+class NeRFTrainer:
+    """models.py:64-225 -- coarse->fine forward pass, train/test steps, minibatched rendering."""
+
+    def __init__(self, coarse_model, fine_model, batch_size, ns_coarse, ns_fine, l_xyz, l_dir,
+                 precision=PRECISION_BF16_TC, stop_grad_samples=True, process_group=None):
+        if not isinstance(coarse_model, NerfModel):
+            raise TypeError("coarse_model must be a NerfModel (create_nerf_complete_model) instance")
+        if not isinstance(fine_model, NerfModel):
+            raise TypeError("fine_model must be a NerfModel (create_nerf_complete_model) instance")
+        if coarse_model.arch != fine_model.arch:
+            raise ValueError("coarse and fine models must share one architecture")
+        self.coarse_model, self.fine_model = coarse_model, fine_model
+        self.batch_size, self.ns_coarse, self.ns_fine = int(batch_size), int(ns_coarse), int(ns_fine)
+        self.l_xyz, self.l_dir = int(l_xyz), int(l_dir)
+        self.precision = precision
+        self.stop_grad_samples = bool(stop_grad_samples)
+        self.process_group = process_group
+        self.optimizer = None
+        self.loss_fn = None
+        self._ctx: Optional[_Ctx] = None
+        self.loss_coarse_tracker = _Mean("loss_coarse")
+        self.loss_tracker = _Mean("loss")
+        self.psnr_tracker = _Mean("psnr")
+
+    # -- setup ------------------------------------------------------------------------------------
+    def compile(self, optimizer, loss_fn):
+        """models.py:80-86."""
+        if not isinstance(optimizer, Adam):
+            raise TypeError("optimizer must be nerf_keras_b200.models.Adam")
+        self.optimizer, self.loss_fn = optimizer, loss_fn
+        self._rebuild_ctx()
+
+    def build(self, input_shape=None):
+        if self._ctx is None:
+            self._rebuild_ctx()
+
+    def _rebuild_ctx(self, max_rays=None):
+        blobs = [self.coarse_model.get_flat_weights(), self.fine_model.get_flat_weights()]
+        if self._ctx is not None:
+            self._ctx.close()
+        training = self.optimizer is not None
+        lr = self.optimizer.learning_rate if training else 0.0
+        self._ctx = _Ctx(self.coarse_model.arch, self.ns_coarse, self.ns_fine, max_rays or self.batch_size, training, lr,
+                         self.stop_grad_samples)
+        for net, (m, blob) in enumerate(zip((self.coarse_model, self.fine_model), blobs)):
+            m._owner = (self._ctx, net)
+            self._ctx.set_weights(net, torch.from_numpy(blob))
+
+    @property
+    def metrics(self):
+        return [self.loss_tracker, self.psnr_tracker]  # models.py:147-149 (loss_coarse is not listed, Q15)
+
+    def reset_metrics(self):
+        for m in (self.loss_coarse_tracker, self.loss_tracker, self.psnr_tracker):
+            m.reset_state()
+
+    # -- forward ----------------------------------------------------------------------------------
+    def _forward_tile(self, o, d, t, u_pdf, precision):
+        B = o.shape[0]
+        Nc, Na = self.ns_coarse, self.ns_coarse + self.ns_fine
+        dev = o.device
+        e = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        out = dict(rgb_c=e(B, 3), rgb_f=e(B, 3), depth_c=e(B), depth_f=e(B), w_c=e(B, Nc), w_f=e(B, Na),
+                   pred_c=e(B, Nc, 4), pred_f=e(B, Na, 4), t_all=e(B, Na))
+        fo = _lib.ForwardOut(*[_ptr(out.get(k)) for k, _ in _lib.ForwardOut._fields_])
+        _lib.check(_lib.lib().nerf_forward_pass(self._ctx.handle, _ptr(o), _ptr(d), _ptr(t), _ptr(u_pdf), B, precision,
+                                                C.byref(fo), _stream()), "forward_pass")
+        return out
+
+    def forward_pass(self, ray_origins, ray_directions, t_vals, l_xyz=None, l_dir=None, training=False,
+                     batch_size=None, u_pdf=None, precision=None, return_t_all=False):
+        """models.py:151-176.  Returns ((rgb_c,rgb_f),(depth_c,depth_f),(w_c,w_f),(pred_c,pred_f))."""
+        if (l_xyz not in (None, self.l_xyz)) or (l_dir not in (None, self.l_dir)):
+            raise ValueError("l_xyz / l_dir differ from the trainer's configuration")
+        if self._ctx is None:
+            self._rebuild_ctx()
+        o, d, t = _f32(ray_origins), _f32(ray_directions), _f32(t_vals)
+        if t.shape != (o.shape[0], self.ns_coarse):
+            raise ValueError(f"t_vals must have shape (n_rays, {self.ns_coarse})")
+        B = o.shape[0]
+        u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
+        precision = self.precision if precision is None else precision
+        tile = self._ctx.max_rays
+        outs = [self._forward_tile(o[s:s + tile], d[s:s + tile], t[s:s + tile], u[s:s + tile], precision)
+                for s in range(0, B, tile)]
+        cat = (lambda k: outs[0][k]) if len(outs) == 1 else (lambda k: torch.cat([x[k] for x in outs], dim=0))
+        res = ((cat("rgb_c"), cat("rgb_f")), (cat("depth_c"), cat("depth_f")), (cat("w_c"), cat("w_f")),
+               (cat("pred_c"), cat("pred_f")))
+        return res + (cat("t_all"),) if return_t_all else res
+
+    def forward_pass_with_minibatch(self, ray_origins, ray_directions, t_vals, l_xyz=None, l_dir=None, batch_size=512,
+                                    training=False, u_pdf=None, precision=None):
+        """models.py:178-225 -- ray-tile loop; tiles are `batch_size` rays (capped by the workspace)."""
+        o, d, t = _f32(ray_origins), _f32(ray_directions), _f32(t_vals)
+        B = o.shape[0]
+        u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
+        outs = [self.forward_pass(o[s:s + batch_size], d[s:s + batch_size], t[s:s + batch_size], l_xyz, l_dir,
+                                  training=training, u_pdf=u[s:s + batch_size], precision=precision)
+                for s in range(0, B, batch_size)]
+        cat = lambda i, j: torch.cat([x[i][j] for x in outs], dim=0)
+        return tuple((cat(i, 0), cat(i, 1)) for i in range(4))
+
+    # -- steps ------------------------------------------------------------------------------------
+    def train_step(self, inputs, u_pdf=None):
+        """models.py:88-120.  inputs = (images (B,3), (ray_origins, ray_directions, t_vals))."""
+        if self.optimizer is None:
+            raise RuntimeError("call compile(optimizer, loss_fn) before train_step")
+        images, (o, d, t) = inputs
+        images, o, d, t = _f32(images), _f32(o), _f32(d), _f32(t)
+        B = o.shape[0]
+        if B > self._ctx.max_rays:
+            self._rebuild_ctx(max_rays=B)
+        u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
+        metrics = torch.empty((3,), device=o.device, dtype=torch.float32)
+        L = _lib.lib()
+        _lib.check(L.nerf_train_forward_backward(self._ctx.handle, _ptr(images), _ptr(o), _ptr(d), _ptr(t), _ptr(u), B,
+                                                 _ptr(metrics), _stream()), "train_step")
+        scale = 1.0
+        if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                              and torch.distributed.get_world_size() > 1):
+            from .dist import allreduce_sum_
+            world = allreduce_sum_(self._ctx.grad_tensor(), self.process_group)
+            scale = 1.0 / world
+        _lib.check(L.nerf_adam_step(self._ctx.handle, scale, _stream()), "adam_step")
+        m = metrics.cpu().numpy()
+        return self._update_metrics(m)
+
+    def test_step(self, inputs, u_pdf=None):
+        """models.py:122-145."""
+        images, (o, d, t) = inputs
+        images = _f32(images)
+        rgbs, _, _, _ = self.forward_pass(o, d, t, u_pdf=u_pdf)
+        metrics = torch.empty((3,), device=images.device, dtype=torch.float32)
+        _lib.check(_lib.lib().nerf_metrics(_ptr(images), _ptr(rgbs[0]), _ptr(rgbs[1]), images.shape[0], _ptr(metrics),
+                                           _stream()), "test_step")
+        return self._update_metrics(metrics.cpu().numpy())
+
+    def _update_metrics(self, m):
+        self.loss_coarse_tracker.update_state(m[0])
+        self.loss_tracker.update_state(m[1])  # `loss` is the FINE loss only (models.py:114)
+        self.psnr_tracker.update_state(m[2])
+        return {"loss_coarse": self.loss_coarse_tracker.result(), "loss": self.loss_tracker.result(),
+                "psnr": self.psnr_tracker.result()}
+
+    def fit(self, train_ds: Iterable, validation_data: Optional[Iterable] = None, epochs=1, callbacks=None, verbose=1):
+        """Minimal stand-in for keras Model.fit as used at train_lego.py:279-284."""
+        history: Dict[str, list] = {"loss": [], "psnr": [], "loss_coarse": [], "val_loss": [], "val_psnr": []}
+        for epoch in range(epochs):
+            self.reset_metrics()
+            logs = {}
+            for batch in train_ds:
+                logs = self.train_step(batch)
+            for k in ("loss", "psnr", "loss_coarse"):
+                history[k].append(logs.get(k))
+            if validation_data is not None:
+                self.reset_metrics()
+                vlogs = {}
+                for batch in validation_data:
+                    vlogs = self.test_step(batch)
+                history["val_loss"].append(vlogs.get("loss"))
+                history["val_psnr"].append(vlogs.get("psnr"))
+                logs = dict(logs, val_loss=vlogs.get("loss"), val_psnr=vlogs.get("psnr"))
+            if verbose:
+                print(f"Epoch {epoch + 1}/{epochs} " + " ".join(f"{k}: {v:.5f}" for k, v in logs.items() if v is not None))
+            for cb in callbacks or []:
+                cb.on_epoch_end(epoch, logs)
+        return history
+
+    # -- weights I/O (train_lego.py:199-213, inference.py:170) ------------------------------------
+    def save_weights(self, path: str):
+        data = {}
+        for name, m in (("coarse", self.coarse_model), ("fine", self.fine_model)):
+            for role, wb in m.get_weights().items():
+                data[f"{name}/{role}/W"] = wb["W"]
+                data[f"{name}/{role}/b"] = wb["b"]
+        np.savez(path, **data)
+
+    def load_weights(self, path: str):
+        data = np.load(path if path.endswith(".npz") else path + ".npz")
+        for name, m in (("coarse", self.coarse_model), ("fine", self.fine_model)):
+            m.set_weights({role: {"W": data[f"{name}/{role}/W"], "b": data[f"{name}/{role}/b"]}
+                           for role, _, _ in m.shapes})

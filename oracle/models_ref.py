@@ -231,7 +231,8 @@ def compute_grads(w_coarse, w_fine, images, ray_origins, ray_directions, t_vals,
     for p in params:
         p.requires_grad_(False)
     ps = psnr(images, rgbs[1].detach())
-    return [g.detach() for g in grads], {"loss_coarse": float(loss_c), "loss": float(loss_f), "psnr": float(ps)}
+    return [g.detach() for g in grads], {"loss_coarse": float(loss_c.detach()), "loss": float(loss_f.detach()),
+                                          "psnr": float(ps)}
 
 
 def train_step(w_coarse, w_fine, opt: KerasAdam, images, ray_origins, ray_directions, t_vals, l_xyz, l_dir,

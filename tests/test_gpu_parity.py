@@ -1,0 +1,245 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / the reference-named Python surface) against
+the oracle and the committed golden fixtures.  Tolerances are BASELINE.json's north_star:
+  rays / t-values bit-exact; fp32 compositing <= 1e-5 abs; bf16 tcgen05 MLP render <= 2e-3 abs per
+  pixel and <= 0.05 dB PSNR."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from tests.util import cuda, golden_weights, load_golden, psnr_db
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nk():
+    import nerf_keras_b200 as nk
+    return nk
+
+
+def _trainer(nk, g, wc, wf, precision, batch=None, training=False):
+    mc = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    mf = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    mc.set_flat_weights(O.flatten_weights(wc))
+    mf.set_flat_weights(O.flatten_weights(wf))
+    tr = nk.NeRFTrainer(mc, mf, batch or g["o"].shape[0], int(g["Nc"]), int(g["Nf"]), 10, 4, precision=precision)
+    if training:
+        tr.compile(nk.Adam(learning_rate=5e-4), nk.MeanSquaredError())
+    else:
+        tr.build()
+    return tr
+
+
+# ---------------------------------------------------------------- rays / t-values: bit-exact
+@pytest.mark.parametrize("H,W,focal", [(800, 800, 1111.1111), (378, 504, 407.6), (25, 25, 138.88889), (3, 5, 2.5)])
+def test_get_rays_bit_exact(nk, H, W, focal):
+    pose = O.pose_spherical(-63.0, -41.0, 4.0)
+    pose[:3, 3] += np.array([0.013, -0.2, 0.31], np.float32)
+    o_ref, d_ref = O.get_rays(H, W, focal, pose)
+    o, d = nk.get_rays(H, W, focal, pose)
+    assert o.shape == (H, W, 3) and d.shape == (H, W, 3)
+    assert np.array_equal(o.cpu().numpy().view(np.uint32), o_ref.numpy().view(np.uint32))
+    assert np.array_equal(d.cpu().numpy().view(np.uint32), d_ref.numpy().view(np.uint32))
+
+
+def test_get_rays_known_answer_and_golden(nk):
+    o, d = nk.get_rays(2, 2, 1.0, np.eye(4, dtype=np.float32))
+    exp = np.array([[[-1, 1, -1], [0, 1, -1]], [[-1, 0, -1], [0, 0, -1]]], dtype=np.float32)
+    assert np.array_equal(d.cpu().numpy(), exp) and float(o.abs().max()) == 0
+    for name in ("lego_small", "fern_small"):
+        g = load_golden(name)
+        o, d = nk.get_rays(int(g["H"]), int(g["W"]), g["focal"], g["pose"])
+        assert np.array_equal(o.cpu().numpy(), g["rays_o_full"]) and np.array_equal(d.cpu().numpy(), g["rays_d_full"])
+
+
+@pytest.mark.parametrize("near,far,B,N", [(2.0, 6.0, 4096, 64), (1.2, 12.0, 1000, 64), (2.0, 6.0, 7, 16), (0.0, 1.0, 33, 50),
+                                          (0.9 * 1.3377, 11.7, 5, 3)])
+def test_generate_t_vals_bit_exact(nk, near, far, B, N):
+    rng = np.random.default_rng(3)
+    u = rng.random(N, dtype=np.float32)
+    for uu, per in ((None, False), (u, False), (rng.random((B, N), dtype=np.float32), True)):
+        ref = O.generate_t_vals(near, far, B, N, uu is not None, u=uu).numpy()
+        got = nk.generate_t_vals(near, far, B, N, uu is not None, u=uu).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_sample_rays_and_encode_position(nk):
+    g = load_golden("fern_small")
+    rays, dirs = nk.sample_rays(g["o"], g["d"], g["t"])
+    assert np.array_equal(rays.cpu().numpy(), g["pts"])
+    assert np.array_equal(dirs.cpu().numpy(), np.broadcast_to(g["d"][:, None, :], g["pts"].shape))
+    enc = nk.encode_position(rays, 10)
+    assert enc.shape == g["enc_x"].shape
+    np.testing.assert_allclose(enc.cpu().numpy(), g["enc_x"], atol=1e-6)
+    np.testing.assert_allclose(nk.encode_position(dirs, 4).cpu().numpy(), g["enc_d"], atol=1e-6)
+    z = nk.encode_position(np.zeros((2, 3), np.float32), 10).cpu().numpy()
+    assert np.array_equal(z[0], np.concatenate([np.zeros(3)] + [np.array([0, 0, 0, 1, 1, 1.0])] * 10).astype(np.float32))
+
+
+# ---------------------------------------------------------------- compositing: <= 1e-5
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_volume_render_golden(nk, name):
+    g = load_golden(name)
+    rgb, depth, w, acc = nk.volume_render(g["pred_c"], g["t"], return_acc=True)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g["rgb_c"], atol=1e-5)
+    np.testing.assert_allclose(w.cpu().numpy(), g["wt_c"], atol=1e-5)
+    np.testing.assert_allclose(depth.cpu().numpy(), g["depth_c"], atol=5e-5)
+    np.testing.assert_allclose(acc.cpu().numpy(), g["wt_c"].sum(-1), atol=1e-5)
+    rgb, depth, w = nk.volume_render(g["pred_f"], g["t_all"])
+    np.testing.assert_allclose(rgb.cpu().numpy(), g["rgb_f"], atol=1e-5)
+    np.testing.assert_allclose(w.cpu().numpy(), g["wt_f"], atol=1e-5)
+
+
+@pytest.mark.parametrize("B,N", [(4096, 64), (513, 192), (9, 16), (3, 48), (2, 1), (5, 33)])
+def test_volume_render_random_and_edge_cases(nk, B, N):
+    gen = torch.Generator().manual_seed(B * 1000 + N)
+    preds = torch.randn(B, N, 4, generator=gen) * 3.0
+    preds[0, :, 3] = -1.0          # fully transparent ray
+    preds[-1, N // 2, 3] = 1e4     # opaque sample
+    t = O.generate_t_vals(2.0, 6.0, B, N, False) if N > 1 else torch.full((B, 1), 2.0)
+    t = t + torch.rand(B, 1, generator=gen) * 0.01
+    r_rgb, r_depth, r_w = O.volume_render(preds, t)
+    rgb, depth, w = nk.volume_render(preds, t)
+    np.testing.assert_allclose(rgb.cpu().numpy(), r_rgb.numpy(), atol=1e-5)
+    np.testing.assert_allclose(w.cpu().numpy(), r_w.numpy(), atol=1e-5)
+    np.testing.assert_allclose(depth.cpu().numpy(), r_depth.numpy(), atol=6e-5)
+    assert float(w.sum(-1).max()) <= 1.0 + 1e-5
+
+
+def test_volume_render_backward_matches_autograd(nk):
+    from nerf_keras_b200 import _lib
+    for B, N in [(257, 64), (31, 192), (5, 16)]:
+        gen = torch.Generator().manual_seed(N)
+        preds = (torch.randn(B, N, 4, generator=gen) * 2.0).requires_grad_(True)
+        t = O.generate_t_vals(2.0, 6.0, B, N, False) + torch.rand(B, 1, generator=gen) * 0.01
+        d_rgb = torch.randn(B, 3, generator=gen)
+        d_w = torch.randn(B, N, generator=gen) * 0.1
+        rgb, _, w = O.volume_render(preds, t)
+        (rgb * d_rgb).sum().add((w * d_w).sum()).backward()
+        dp = torch.empty(B, N, 4, device="cuda")
+        p_c, t_c, dr_c, dw_c = cuda(preds.detach().numpy()), cuda(t.numpy()), cuda(d_rgb.numpy()), cuda(d_w.numpy())
+        _lib.check(_lib.lib().nerf_volume_render_bwd(p_c.data_ptr(), t_c.data_ptr(), dr_c.data_ptr(), dw_c.data_ptr(),
+                                                     B, N, dp.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+        ref = preds.grad.numpy()
+        got = dp.cpu().numpy()
+        # last-sample sigma gradient carries the 1e10 delta factor: compare relatively
+        np.testing.assert_allclose(got[..., :3], ref[..., :3], atol=2e-6, rtol=1e-4)
+        np.testing.assert_allclose(got[:, :-1, 3], ref[:, :-1, 3], atol=2e-6, rtol=2e-4)
+        np.testing.assert_allclose(got[:, -1, 3], ref[:, -1, 3], rtol=1e-3, atol=1e-6 * max(1.0, float(np.abs(ref[:, -1, 3]).max())))
+
+
+# ---------------------------------------------------------------- hierarchical resampling
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_sample_pdf_and_merge_golden(nk, name):
+    g = load_golden(name)
+    Nf = int(g["Nf"])
+    t_mid = 0.5 * (g["t"][:, 1:] + g["t"][:, :-1])
+    s = nk.sample_pdf(t_mid, g["wt_c"], Nf, u=g["u_pdf"]).cpu().numpy()
+    np.testing.assert_allclose(s, g["t_fine"], atol=3e-5)
+    t_all, idx = nk.resample_merge(g["t"], g["wt_c"], Nf, u=g["u_pdf"], return_index=True)
+    t_all = t_all.cpu().numpy()
+    np.testing.assert_allclose(t_all, g["t_all"], atol=3e-5)
+    assert (np.diff(t_all, axis=-1) >= 0).all()
+    cat = np.concatenate([g["t"], s], axis=-1)
+    idx = idx.cpu().numpy()
+    assert (np.sort(idx, -1) == np.arange(cat.shape[1])).all()          # a permutation
+    np.testing.assert_allclose(np.take_along_axis(cat, idx, -1), t_all, atol=3e-5)
+
+
+def test_sample_pdf_edge_cases(nk):
+    Nc, Nf, B = 64, 128, 50
+    t = O.generate_t_vals(2.0, 6.0, B, Nc, False)
+    t_mid = 0.5 * (t[:, 1:] + t[:, :-1])
+    rng = np.random.default_rng(0)
+    u = torch.from_numpy(rng.random((B, Nf), dtype=np.float32))
+    u[0, 0], u[0, 1] = 0.0, np.float32(1.0 - 2 ** -24)
+    w = torch.zeros(B, Nc)
+    w[1, 10] = 1.0                       # a single spike
+    w[2:] = torch.from_numpy(rng.random((B - 2, Nc), dtype=np.float32)) ** 8
+    ref = O.sample_pdf(t_mid, w, Nf, u=u).numpy()
+    got = nk.sample_pdf(t_mid, w, Nf, u=u).cpu().numpy()
+    np.testing.assert_allclose(got, ref, atol=5e-5)
+    assert got.min() >= float(t_mid[0, 0]) - 1e-6 and got.max() <= float(t_mid[0, -1]) + 1e-6
+
+
+# ---------------------------------------------------------------- tcgen05 building block
+@pytest.mark.parametrize("mode,N,K", [(0, 128, 64), (0, 128, 256), (0, 256, 128), (1, 128, 16), (1, 128, 128), (1, 256, 128)])
+def test_tcgen05_selftest_gemm(nk, mode, N, K):
+    from nerf_keras_b200 import _lib
+    gen = torch.Generator().manual_seed(mode * 100 + N + K)
+    if mode == 0:
+        a = torch.randn(128, K, generator=gen); b = torch.randn(N, K, generator=gen)
+        ref = a.bfloat16().float() @ b.bfloat16().float().T
+    else:
+        a = torch.randn(K, 128, generator=gen); b = torch.randn(K, N, generator=gen)
+        ref = a.bfloat16().float().T @ b.bfloat16().float()
+    c = torch.zeros(128, N, device="cuda")
+    _lib.check(_lib.lib().nerf_selftest_gemm(a.cuda().data_ptr(), b.cuda().data_ptr(), c.data_ptr(), 128, N, K, mode,
+                                             torch.cuda.current_stream().cuda_stream), "selftest")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(c.cpu().numpy(), ref.numpy(), atol=2e-3, rtol=1e-4)
+
+
+# ---------------------------------------------------------------- MLP
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_mlp_fp32_model_call(nk, name):
+    g = load_golden(name)
+    wc, _ = golden_weights(g)
+    m = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    m.set_flat_weights(O.flatten_weights(wc))
+    out = m([g["enc_x"], g["enc_d"]])
+    assert out.shape == g["pred_c"].shape
+    np.testing.assert_allclose(out.cpu().numpy(), g["pred_c"], atol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_forward_pass_fp32_golden(nk, name):
+    g = load_golden(name)
+    wc, wf = golden_weights(g)
+    tr = _trainer(nk, g, wc, wf, nk.PRECISION_FP32)
+    rgbs, depths, ws, preds = tr.forward_pass(g["o"], g["d"], g["t"], 10, 4, u_pdf=g["u_pdf"])
+    np.testing.assert_allclose(rgbs[0].cpu().numpy(), g["rgb_c"], atol=1e-5)
+    np.testing.assert_allclose(rgbs[1].cpu().numpy(), g["rgb_f"], atol=1e-5)
+    np.testing.assert_allclose(ws[0].cpu().numpy(), g["wt_c"], atol=1e-5)
+    np.testing.assert_allclose(depths[1].cpu().numpy(), g["depth_f"], atol=1e-4)
+    assert preds[1].shape == g["pred_f"].shape
+
+
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_forward_pass_tcgen05_golden(nk, name):
+    """bf16 tensor-core MLP: <= 2e-3 abs per pixel, <= 0.05 dB PSNR vs the fp32 oracle render."""
+    g = load_golden(name)
+    wc, wf = golden_weights(g)
+    tr = _trainer(nk, g, wc, wf, nk.PRECISION_BF16_TC)
+    rgbs, depths, ws, preds = tr.forward_pass(g["o"], g["d"], g["t"], 10, 4, u_pdf=g["u_pdf"])
+    for got, ref in ((rgbs[0], g["rgb_c"]), (rgbs[1], g["rgb_f"])):
+        got = got.cpu().numpy()
+        assert np.abs(got - ref).max() <= 2e-3, np.abs(got - ref).max()
+        assert abs(psnr_db(got, g["img"]) - psnr_db(ref, g["img"])) <= 0.05
+    # the coarse raw predictions see identical inputs: bf16-level agreement
+    np.testing.assert_allclose(preds[0].cpu().numpy(), g["pred_c"], atol=3e-2)
+
+
+def test_tcgen05_mlp_vs_fp32_kernel_large(nk):
+    """Full-size batch (4096 rays x 64 samples, 148+ tiles, ragged tail): tcgen05 vs the fp32 CUDA path."""
+    g = load_golden("fern_small")
+    wc, wf = golden_weights(g)
+    B, Nc = 4096 + 37, 64
+    pose = O.pose_spherical(10.0, -30.0, 4.0)
+    o, d = nk.get_rays(80, 80, 100.0, pose)
+    o, d = o.reshape(-1, 3)[:B].contiguous(), d.reshape(-1, 3)[:B].contiguous()
+    t = nk.generate_t_vals(2.0, 6.0, B, Nc, True, u=g["u_t"])
+    g2 = dict(g); g2["o"] = o
+    tr_tc = _trainer(nk, g2, wc, wf, nk.PRECISION_BF16_TC, batch=B)
+    tr_32 = _trainer(nk, g2, wc, wf, nk.PRECISION_FP32, batch=B)
+    u = torch.rand(B, 128, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    a = tr_tc.forward_pass(o, d, t, u_pdf=u)
+    b = tr_32.forward_pass(o, d, t, u_pdf=u)
+    for i in (0, 1):
+        diff = (a[0][i] - b[0][i]).abs().max().item()
+        assert diff <= 2e-3, (i, diff)
+    assert (a[3][0] - b[3][0]).abs().max().item() <= 5e-2
+    # tiling invariance: forward_pass_with_minibatch == forward_pass
+    c = tr_tc.forward_pass_with_minibatch(o, d, t, batch_size=1000, u_pdf=u)
+    assert (c[0][1] - a[0][1]).abs().max().item() <= 1e-6

@@ -1,0 +1,150 @@
+"""CPU: host-side logic, config schema, C-ABI library loads and exports every declared symbol,
+world_size-2 gloo test of the data-parallel plumbing.  No compute calls (no GPU here)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    from nerf_keras_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "libnerf_b200.so not built: run __graft_entry__.build()"
+    handle = C.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(handle, s), f"missing export {s}"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in _lib.SIGNATURES"
+
+
+def test_param_count_and_loud_failure_without_gpu():
+    from nerf_keras_b200 import _lib
+    L = _lib.lib()
+    cfg = _lib.NerfConfig(8, 256, 4, 10, 4, 64, 128, 4096, 0, 0, 5e-4, 1)
+    assert L.nerf_param_count(C.byref(cfg)) == 595844
+    bad = _lib.NerfConfig(8, 256, 4, 10, 4, 64, 128, 4096, 1, 0, 5e-4, 1)  # BATCH_NORM=true
+    assert L.nerf_param_count(C.byref(bad)) == -1
+    assert b"BATCH_NORM" in L.nerf_last_error()
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert L.nerf_create(C.byref(cfg), C.byref(h)) != 0
+        assert b"no CPU fallback" in L.nerf_last_error()
+        import nerf_keras_b200 as nk
+        with pytest.raises(RuntimeError):
+            nk.get_rays(4, 4, 1.0, np.eye(4, dtype=np.float32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "nerf_keras_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_models_host_logic():
+    import nerf_keras_b200 as nk
+    from nerf_keras_b200.models import layer_shapes
+    nk.set_random_seed(42)
+    m = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=False)
+    assert m.count_params() == 595844
+    shapes = dict((r, (i, o)) for r, i, o in layer_shapes(8, 256, 4, 10, 4))
+    assert shapes["d5"] == (319, 256) and shapes["ddir"] == (283, 128)
+    w = m.get_weights()
+    assert w["d5"]["W"].shape == (319, 256) and float(np.abs(w["d0"]["b"]).max()) == 0.0
+    lim = np.sqrt(6.0 / (63 + 256))
+    assert np.abs(w["d0"]["W"]).max() <= lim
+    w["rgb"]["b"][:] = [1, 2, 3]
+    m.set_weights(w)
+    assert np.array_equal(m.get_weights()["rgb"]["b"], [1, 2, 3])
+    with pytest.raises(ValueError):
+        nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+    with pytest.raises(TypeError):
+        nk.NeRFTrainer(object(), m, 8, 4, 8, 10, 4)
+    oracle_like = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    tr = nk.NeRFTrainer(m, oracle_like, 8, 4, 8, 10, 4)
+    assert [x.name for x in tr.metrics] == ["loss", "psnr"]
+
+
+def test_pose_spherical_matches_reference_formula():
+    import nerf_keras_b200 as nk
+    c2w = nk.pose_spherical(30.0, -30.0, 4.0)
+    assert c2w.shape == (4, 4) and c2w.dtype == np.float32
+    assert abs(np.linalg.norm(c2w[:3, 3]) - 4.0) < 1e-5
+    np.testing.assert_allclose(c2w[:3, :3] @ c2w[:3, :3].T, np.eye(3), atol=1e-6)
+
+
+def test_config_schema_roundtrip():
+    from nerf_keras_b200.config import load_config, REQUIRED_KEYS
+    cfgdir = os.path.join(ROOT, "config")
+    names = sorted(f for f in os.listdir(cfgdir) if f.endswith(".json"))
+    assert "lego_batch_h256.json" in names and "fern_batch_h256_tpu.json" in names
+    for n in names:
+        conf = load_config(os.path.join(cfgdir, n))
+        for k in REQUIRED_KEYS:
+            assert k in conf
+    with pytest.raises(KeyError):
+        load_config(os.path.join(cfgdir, "lego_batch_h256.json"), override={"__drop__": "NS_FINE"})
+
+
+def test_shard_range_partitions():
+    from nerf_keras_b200.dist import shard_range
+    for n, w in [(4096, 8), (10, 3), (7, 8), (0, 2)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        for a, b in zip(spans, spans[1:]):
+            assert a[1] == b[0]
+        sizes = [e - s for s, e in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from nerf_keras_b200.dist import init_from_env, allreduce_sum_, shard_range, gather_rows
+rank, local, world = init_from_env("gloo")
+assert world == 2
+g = torch.full((1000,), float(rank + 1))
+w = allreduce_sum_(g)
+assert w == 2 and torch.allclose(g, torch.full((1000,), 3.0)), g[:4]
+# DP semantics: mean of per-shard mean-gradients == gradient of the global mean (equal shards)
+full = torch.arange(64, dtype=torch.float32)
+s, e = shard_range(64, rank, world)
+local_grad = full[s:e].mean().reshape(1)
+allreduce_sum_(local_grad)
+assert abs(float(local_grad) / world - float(full.mean())) < 1e-6
+rows = torch.full((3, 2), float(rank))
+out = gather_rows(rows)
+if rank == 0:
+    assert out.shape == (6, 2) and float(out[3:].min()) == 1.0
+else:
+    assert out is None
+dist.barrier()
+sys.stdout.write("rank%d_ok\n" % rank); sys.stdout.flush()
+'''
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", str(script), ROOT],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rank0_ok" in r.stdout and "rank1_ok" in r.stdout
