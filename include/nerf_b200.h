@@ -133,6 +133,11 @@ int nerf_metrics(const float* images, const float* rgb_c, const float* rgb_f, in
 /* ---- diagnostics -------------------------------------------------------------------------------- */
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches). */
 int64_t nerf_launch_count(void);
+/* Per-kernel device timing for bench.py's roofline leg: when enabled, every launch of kernel class
+ * `kind` (0 = fused MLP forward, 1 = fused MLP backward chain, 2 = weight-gradient GEMM) is bracketed
+ * by CUDA events on its stream.  nerf_timing_read sums and clears them (synchronises on the events). */
+int nerf_timing_enable(int on);
+int nerf_timing_read(int kind, double* total_ms, int64_t* launches);
 /* Self-test of the tcgen05 building block: C (M,N) fp32 = A (M,K) bf16-rounded x B^T, B (N,K). */
 int nerf_selftest_gemm(const float* a, const float* b, float* c, int m, int n, int k, int mode, void* stream);
 

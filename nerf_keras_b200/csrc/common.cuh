@@ -38,6 +38,11 @@ inline int fail(int code, const std::string& msg) {
         NERF_CUDA(cudaGetLastError());         \
     } while (0)
 
+// optional per-kernel timing of the fused MLP kernels (bench.py's roofline leg): when enabled every
+// fused-MLP launch is bracketed by cudaEvents on its stream; nerf_timing_read() sums them.
+void timing_begin(int kind, cudaStream_t st);
+void timing_end(int kind, cudaStream_t st);
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 inline int num_sms() {

@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
             const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
             int64_t g[2] = {0, 0};       // next chunk (global counter) per sub-tile
             int64_t nstart[2] = {0, 0};  // number of phase starts consumed per sub-tile
-            uint32_t spins = 0;
+            long long stall_t0 = 0;
+            bool stalled = false;
             while (g[0] < total_chunks || g[1] < total_chunks) {
                 int pick = -1;
                 bool can[2];
@@ -258,22 +259,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     int c = (int)(g[s] % N_CHUNKS);
                     int ph = c_chunk_phase[c];
                     bool ready = true;
-                    if (c == c_ph_first[ph]) ready = mbar_test(bar_actr + 8 * s, (uint32_t)(nstart[s] & 1));
+                    if (c == c_ph_first[ph]) ready = mbar_probe(bar_actr + 8 * s, (uint32_t)(nstart[s] & 1));
                     if (ready && s == 0) {
                         int slot = (int)(g[0] % STAGES);
-                        ready = mbar_test(bar_full + 8 * slot, (uint32_t)((g[0] / STAGES) & 1));
+                        ready = mbar_probe(bar_full + 8 * slot, (uint32_t)((g[0] / STAGES) & 1));
                     }
                     if (ready) pick = s;
                 }
                 if (pick < 0) {
-                    if (++spins > TC5_SPIN_LIMIT) {
+                    if (!stalled) { stalled = true; stall_t0 = clock64(); }
+                    else if (clock64() - stall_t0 > TC5_TIMEOUT_CYCLES) {
                         printf("tc5: MMA issuer stalled block=%d gA=%lld gB=%lld\n", blockIdx.x, (long long)g[0],
                                (long long)g[1]);
                         __trap();
                     }
                     continue;
                 }
-                spins = 0;
+                stalled = false;
                 const int s = pick;
                 const int c = (int)(g[s] % N_CHUNKS);
                 const int ph = c_chunk_phase[c];
@@ -631,12 +633,14 @@ int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, cons
     P.preds = reinterpret_cast<float4*>(preds);
     P.act_save = save_acts ? ctx->act_save[net] : nullptr;
     int grid = (int)(P.n_pairs < num_sms() ? P.n_pairs : num_sms());
+    timing_begin(0, st);
     if (save_acts) {
         if (!ctx->act_save[net]) return fail(NERF_ERR_STATE, "tc_forward_rays: ctx was not created with training=1");
         nerf_mlp_fwd_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
     } else {
         nerf_mlp_fwd_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
     }
+    timing_end(0, st);
     NERF_LAUNCHED();
     return NERF_OK;
 }

@@ -682,6 +682,64 @@ extern "C" int nerf_adam_flat(float* params, const float* grads, float* m, float
     return NERF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// kernel timing hooks
+// ------------------------------------------------------------------------------------------------
+#include <mutex>
+#include <vector>
+namespace nerf {
+static bool g_timing_on = false;
+static std::mutex g_timing_mu;
+struct TimedSpan { int kind; cudaEvent_t a, b; };
+static std::vector<TimedSpan> g_spans;
+static std::vector<cudaEvent_t> g_open[8];
+void timing_begin(int kind, cudaStream_t st) {
+    if (!g_timing_on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_open[kind & 7].push_back(e);
+}
+void timing_end(int kind, cudaStream_t st) {
+    if (!g_timing_on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    auto& open = g_open[kind & 7];
+    if (open.empty()) { cudaEventDestroy(e); return; }
+    g_spans.push_back({kind, open.back(), e});
+    open.pop_back();
+}
+}  // namespace nerf
+
+extern "C" int nerf_timing_enable(int on) {
+    std::lock_guard<std::mutex> lk(nerf::g_timing_mu);
+    nerf::g_timing_on = on != 0;
+    return NERF_OK;
+}
+// sums (and clears) the recorded spans of `kind`: total milliseconds and number of launches.
+// Synchronises on the recorded events.
+extern "C" int nerf_timing_read(int kind, double* total_ms, int64_t* launches) {
+    NERF_CHECK_ARG(total_ms && launches, "null pointer");
+    std::lock_guard<std::mutex> lk(nerf::g_timing_mu);
+    double tot = 0;
+    int64_t n = 0;
+    std::vector<nerf::TimedSpan> keep;
+    for (auto& s : nerf::g_spans) {
+        if (s.kind != kind) { keep.push_back(s); continue; }
+        cudaEventSynchronize(s.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        tot += ms; ++n;
+        cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+    }
+    nerf::g_spans.swap(keep);
+    *total_ms = tot; *launches = n;
+    return NERF_OK;
+}
+
 extern "C" const char* nerf_last_error(void) { return nerf::g_last_error.c_str(); }
 extern "C" int nerf_version(void) { return 100; }
 extern "C" int64_t nerf_launch_count(void) { return nerf::g_launches.load(); }

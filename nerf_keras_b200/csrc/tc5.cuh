@@ -15,8 +15,8 @@ namespace tc5 {
 // ------------------------------------------------------------------------------------------------
 // Error flag: spins are bounded so a protocol bug traps instead of hanging the GPU box.
 // ------------------------------------------------------------------------------------------------
-#ifndef TC5_SPIN_LIMIT
-#define TC5_SPIN_LIMIT (1u << 27)
+#ifndef TC5_TIMEOUT_CYCLES
+#define TC5_TIMEOUT_CYCLES (4000000000ll)  // ~2 s at 2 GHz
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -49,11 +49,24 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded blocking wait; on timeout records `code` and traps (the launch fails, the GPU survives).
+// non-blocking probe (test_wait never suspends the thread)
+__device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded blocking wait; on timeout prints `code` and traps (the launch fails, the GPU survives).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code = 0) {
-    uint32_t spins = 0;
+    if (mbar_test(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_test(bar, parity)) {
-        if (++spins > TC5_SPIN_LIMIT) {
+        if (clock64() - t0 > TC5_TIMEOUT_CYCLES) {
             printf("tc5: mbarrier wait timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x,
                    threadIdx.x, parity);
             __trap();

@@ -307,6 +307,22 @@ class NeRFTrainer:
                (cat("pred_c"), cat("pred_f")))
         return res + (cat("t_all"),) if return_t_all else res
 
+    def mlp_forward_rays(self, net, ray_origins, ray_directions, t_vals, precision=None):
+        """Fused sample_rays + encode_position x2 + model call for one net (models.py:152-157 /
+        169-173): returns the raw predictions (B, N, 4).  net: "coarse" | "fine"."""
+        if self._ctx is None:
+            self._rebuild_ctx()
+        o, d, t = _f32(ray_origins), _f32(ray_directions), _f32(t_vals)
+        B, N = t.shape
+        if B > self._ctx.max_rays:
+            self._rebuild_ctx(max_rays=B)
+        idx = {"coarse": 0, "fine": 1}[net]
+        precision = self.precision if precision is None else precision
+        out = torch.empty((B, N, 4), device=o.device, dtype=torch.float32)
+        _lib.check(_lib.lib().nerf_mlp_forward_rays(self._ctx.handle, idx, _ptr(o), _ptr(d), _ptr(t), B, N, precision,
+                                                    _ptr(out), _stream()), "mlp_forward_rays")
+        return out
+
     def forward_pass_with_minibatch(self, ray_origins, ray_directions, t_vals, l_xyz=None, l_dir=None, batch_size=512,
                                     training=False, u_pdf=None, precision=None):
         """models.py:178-225 -- ray-tile loop; tiles are `batch_size` rays (capped by the workspace)."""

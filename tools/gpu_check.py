@@ -49,7 +49,8 @@ def gemm():
             a = torch.randn(K, 128, generator=gen); b = torch.randn(K, N, generator=gen)
             ref = a.bfloat16().float().T @ b.bfloat16().float()
         c = torch.zeros(128, N, device="cuda")
-        _lib.check(_lib.lib().nerf_selftest_gemm(a.cuda().data_ptr(), b.cuda().data_ptr(), c.data_ptr(), 128, N, K, mode,
+        a_d, b_d = a.cuda(), b.cuda()
+        _lib.check(_lib.lib().nerf_selftest_gemm(a_d.data_ptr(), b_d.data_ptr(), c.data_ptr(), 128, N, K, mode,
                                                  torch.cuda.current_stream().cuda_stream), "selftest")
         torch.cuda.synchronize()
         err = (c.cpu() - ref).abs().max().item()
