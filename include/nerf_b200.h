@@ -138,6 +138,13 @@ int64_t nerf_launch_count(void);
  * by CUDA events on its stream.  nerf_timing_read sums and clears them (synchronises on the events). */
 int nerf_timing_enable(int on);
 int nerf_timing_read(int kind, double* total_ms, int64_t* launches);
+/* Diagnostics: d(sum(preds * d_preds))/d(weights of `net`) for given rays and t-values (forward with
+ * saved activations + the tcgen05 backward); preds (B,N,4) is also returned.  Gradients land in the
+ * ctx gradient buffer (nerf_grad_buffer), the other net's half is zero. */
+int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t batch,
+                         int num_samples, const float* d_preds, float* preds, void* stream);
+/* MMA issue-rate probe (cycles for `reps` x 4 back-to-back 128 x n x 16 MMAs). */
+int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycles_dev, void* stream);
 /* Self-test of the tcgen05 building block: C (M,N) fp32 = A (M,K) bf16-rounded x B^T, B (N,K). */
 int nerf_selftest_gemm(const float* a, const float* b, float* c, int m, int n, int k, int mode, void* stream);
 

@@ -130,7 +130,7 @@ extern "C" int nerf_destroy(nerf_ctx* ctx) {
     cudaFree(ctx->fw_dirbias);
     cudaFree(ctx->tr_dpred_c); cudaFree(ctx->tr_dpred_f); cudaFree(ctx->tr_drgb_c); cudaFree(ctx->tr_drgb_f);
     cudaFree(ctx->tr_ddirbias);
-    for (int n = 0; n < 2; ++n) { cudaFree(ctx->act_save[n]); cudaFree(ctx->dz_save[n]); }
+    for (int n = 0; n < 2; ++n) { cudaFree(ctx->act_save[n]); cudaFree(ctx->dz_save[n]); cudaFree(ctx->mask_save[n]); }
     tc_free(ctx);
     delete ctx;
     return NERF_OK;
@@ -293,4 +293,22 @@ extern "C" int nerf_adam_step(nerf_ctx* ctx, float grad_scale, void* stream) {
                             ctx->cfg.learning_rate, grad_scale, stream);
     ctx->packed_valid[0] = ctx->packed_valid[1] = false;
     return rc;
+}
+
+// Diagnostics: gradients of sum(preds * d_preds) wrt one net's weights for given rays / t-values
+// (forward with saved activations + the full tcgen05 backward).  Result lands in the ctx gradient buffer.
+extern "C" int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t,
+                                    int64_t batch, int num_samples, const float* d_preds, float* preds, void* stream) {
+    NERF_CHECK_ARG(ctx && o && d && t && d_preds && preds && batch >= 1, "bad arguments");
+    NERF_CHECK_ARG(net == 0 || net == 1, "net must be 0 or 1");
+    if (!ctx->cfg.training || !ctx->grads) return fail(NERF_ERR_STATE, "ctx was not created with training=1");
+    const int n_max = net == 0 ? ctx->cfg.ns_coarse : ctx->cfg.ns_coarse + ctx->cfg.ns_fine;
+    NERF_CHECK_ARG(batch * (int64_t)num_samples <= (int64_t)ctx->cfg.max_rays * n_max, "batch too large for the workspace");
+    NERF_CHECK_ARG(batch <= ctx->cfg.max_rays, "batch exceeds cfg.max_rays");
+    int rc = check_ready(ctx, net);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = tc_forward_rays(ctx, net, o, d, t, batch, num_samples, preds, true, st))) return rc;
+    NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * ctx->n_params * 4, st));
+    return tc_backward(ctx, net, o, d, t, batch, num_samples, d_preds, st);
 }

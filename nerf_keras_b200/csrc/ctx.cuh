@@ -48,6 +48,7 @@ struct nerf_ctx {
     // training workspace (cfg.training): saved activation images and gradient images, per net
     __nv_bfloat16* act_save[2] = {nullptr, nullptr};
     __nv_bfloat16* dz_save[2] = {nullptr, nullptr};
+    uint32_t* mask_save[2] = {nullptr, nullptr};
     float *tr_dpred_c = nullptr, *tr_dpred_f = nullptr, *tr_drgb_c = nullptr, *tr_drgb_f = nullptr;
     float* tr_ddirbias = nullptr;
 };

@@ -18,65 +18,30 @@
 // table (biases + head weights), mbarriers.  TMEM: 2 x 256 fp32 columns (all 512).
 #include "common.cuh"
 #include "ctx.cuh"
-#include "tc5.cuh"
+#include "mlp_tc_common.cuh"
 
 using namespace nerf;
 using namespace tc5;
+using namespace tcmlp;
 
 namespace {
 
-constexpr int H = 256;            // hidden width
-constexpr int ENC_X = 63;         // 3 + 6*10
-constexpr int ENC_D = 27;         // 3 + 6*4
-constexpr int TILE_M = 128;       // rows per sub-tile
-constexpr int CHUNK_BYTES = 16384;  // [128 n-rows x 64 k] bf16, 128B swizzle
-constexpr int CHUNK_ELEMS = CHUNK_BYTES / 2;
+// forward program: L0, L1, L2, L3, L4, L5a (h part), L5b (skip part), L6, L7, feature, ddir.
+// L0 / L5b consume the encoding as TWO k-blocks: [bf16(enc) | bf16 residual of the raw xyz channels]
+// (the raw coordinates reach |x| ~ 6, where a single bf16 loses ~1e-2; the hi+lo split restores them).
 constexpr int N_PHASES = 11;
-constexpr int N_CHUNKS = 72;
-constexpr int STAGES = 5;
-constexpr int LAG_MAX = 4;        // sub-tile A may run at most this many chunks ahead of B
-constexpr int LAG_TARGET = 3;
-
-// phases: L0, L1, L2, L3, L4, L5a (h part), L5b (skip part), L6, L7, feature, ddir
-__constant__ int c_ph_chunks[N_PHASES] = {2, 8, 8, 8, 8, 8, 2, 8, 8, 8, 4};
-__constant__ int c_ph_kb[N_PHASES] = {1, 4, 4, 4, 4, 4, 1, 4, 4, 4, 4};
-__constant__ int c_ph_first[N_PHASES] = {0, 2, 10, 18, 26, 34, 42, 44, 52, 60, 68};
-__constant__ int c_chunk_phase[N_CHUNKS] = {
-    0, 0,
+constexpr int N_CHUNKS = 76;
+__constant__ Program c_fwd_prog = {
+    N_PHASES, N_CHUNKS,
+    {4, 8, 8, 8, 8, 8, 4, 8, 8, 8, 4, 0},
+    {2, 4, 4, 4, 4, 4, 2, 4, 4, 4, 4, 0},
+    {PH_ENC, 0, 0, 0, 0, 0, PH_ENC | PH_ACC, 0, 0, 0, 0, 0}};
+__constant__ int c_fwd_first[N_PHASES] = {0, 4, 12, 20, 28, 36, 44, 48, 56, 64, 72};
+__constant__ int c_fwd_chunk_phase[N_CHUNKS] = {
+    0, 0, 0, 0,
     1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4,
-    5, 5, 5, 5, 5, 5, 5, 5, 6, 6,
+    5, 5, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6,
     7, 7, 7, 7, 7, 7, 7, 7, 8, 8, 8, 8, 8, 8, 8, 8, 9, 9, 9, 9, 9, 9, 9, 9, 10, 10, 10, 10};
-
-// fp32 side table offsets (floats)
-constexpr int SIDE_BIAS = 0;        // 8 x 256 trunk biases
-constexpr int SIDE_BFEAT = 2048;    // 256
-constexpr int SIDE_BDDIR = 2304;    // 128
-constexpr int SIDE_WSIG = 2432;     // 256
-constexpr int SIDE_WRGB = 2688;     // 3 x 128 ([channel][k])
-constexpr int SIDE_BSIG = 3072;     // 1
-constexpr int SIDE_BRGB = 3073;     // 3
-constexpr int SIDE_FLOATS = 3080;
-
-// shared memory map (bytes, relative to the 1024-aligned base)
-constexpr int SM_ACT = 0;                                  // 2 x 65536
-constexpr int SM_RING = 131072;                            // STAGES x 16384
-constexpr int SM_SIDE = SM_RING + STAGES * CHUNK_BYTES;    // 12320
-constexpr int SM_BAR = SM_SIDE + SIDE_FLOATS * 4;          // mbarriers
-constexpr int SM_FULL = SM_BAR;                            // STAGES
-constexpr int SM_EMPTY = SM_FULL + 8 * STAGES;             // STAGES
-constexpr int SM_ACCF = SM_EMPTY + 8 * STAGES;             // 2
-constexpr int SM_ACTR = SM_ACCF + 16;                      // 2
-constexpr int SM_TMEM = SM_ACTR + 16;                      // u32
-constexpr int SM_TOTAL = SM_TMEM + 16;
-constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
-
-constexpr int NUM_THREADS = 320;  // 8 worker warps (4 per sub-tile) + producer warp + MMA warp
-
-// per-net layer offsets inside the flat fp32 blob (floats), filled by the host
-struct BlobOffsets {
-    int64_t w[12];  // d0..d7, sigma, feature, ddir, rgb
-    int64_t b[12];
-};
 
 struct FwdParams {
     const float* o;
@@ -89,31 +54,25 @@ struct FwdParams {
     const float* side;
     const float* dirbias;  // (rays, 128)
     float4* preds;         // (M) [r,g,b,sigma] raw
-    __nv_bfloat16* act_save;  // optional saved-activation images (training)
+    uint8_t* act_save;     // optional saved-activation images (training)
+    uint32_t* mask_save;   // optional ReLU masks (training)
 };
-
-// saved activation image layout per 128-row tile (bytes): enc 16 KB, h1..h8 8 x 64 KB, feature 64 KB, hd 32 KB
-constexpr int64_t SAVE_ENC = 0;
-constexpr int64_t SAVE_H = 16384;            // + 65536 * i, i = 0..7  (outputs of L0..L7)
-constexpr int64_t SAVE_FEAT = 16384 + 8 * 65536;
-constexpr int64_t SAVE_HD = SAVE_FEAT + 65536;
-constexpr int64_t SAVE_TILE_BYTES = SAVE_HD + 32768;  // 638976
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 // weight packing: fp32 master blob -> bf16 chunk stream (K-major B operand, B[n][k] = W[k][n])
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fwd_weight_at(const float* __restrict__ blob, const BlobOffsets& off, int phase,
                                                int n, int k) {
-    // returns W_phase[k][n] with zero padding
+    // returns W_phase[k][n] with zero padding; k in [64,128) of the encoding phases is the residual block
     switch (phase) {
-        case 0: return (k < ENC_X) ? blob[off.w[0] + (int64_t)k * H + n] : 0.f;
+        case 0:
+            if (k >= 64) k -= 64, k = (k < 3) ? k : 1 << 20;
+            return (k < ENC_X) ? blob[off.w[0] + (int64_t)k * H + n] : 0.f;
         case 1: case 2: case 3: case 4: return blob[off.w[phase] + (int64_t)k * H + n];
         case 5: return blob[off.w[5] + (int64_t)k * H + n];
-        case 6: return (k < ENC_X) ? blob[off.w[5] + (int64_t)(H + k) * H + n] : 0.f;
+        case 6:
+            if (k >= 64) k -= 64, k = (k < 3) ? k : 1 << 20;
+            return (k < ENC_X) ? blob[off.w[5] + (int64_t)(H + k) * H + n] : 0.f;
         case 7: return blob[off.w[6] + (int64_t)k * H + n];
         case 8: return blob[off.w[7] + (int64_t)k * H + n];
         case 9: return blob[off.w[9] + (int64_t)k * H + n];                 // feature
@@ -129,9 +88,9 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
         int g = i / (128 * 8);
         int rem = i - g * 128 * 8;
         int n = rem >> 3, kg = rem & 7;
-        int phase = c_chunk_phase[g];
-        int j = g - c_ph_first[phase];
-        int kbs = c_ph_kb[phase];
+        int phase = c_fwd_chunk_phase[g];
+        int j = g - c_fwd_first[phase];
+        int kbs = c_fwd_prog.kb[phase];
         int h = j / kbs, kb = j - h * kbs;
         uint32_t packed[4];
 #pragma unroll
@@ -184,15 +143,71 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ 
     }
 }
 
+// ---- epilogue building blocks ---------------------------------------------------------------------
+// one 32-column group of a trunk / feature layer: acc + bias (packed fp32x2 adds), fused ReLU + bf16
+// convert, optional sigma head accumulation and ReLU mask, then four 16-byte swizzled stores.
+template <bool RELU, bool SIGMA, bool SAVE>
+__device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float* bias_g, const float* wsig_g,
+                                            uint64_t& sig2, uint32_t& mk, uint32_t act_base, int row, int cg) {
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias_g);
+    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(wsig_g);
+    uint32_t pk[16];
+    mk = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const ulonglong2 bb = b2[q];
+        uint64_t x01 = f2_add(f2_pack(v[4 * q], v[4 * q + 1]), bb.x);
+        uint64_t x23 = f2_add(f2_pack(v[4 * q + 2], v[4 * q + 3]), bb.y);
+        float x0, x1, x2, x3;
+        f2_unpack(x01, x0, x1);
+        f2_unpack(x23, x2, x3);
+        if (SIGMA) {
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+            const ulonglong2 ws = s2[q];
+            sig2 = f2_fma(f2_pack(__float_as_uint(x0), __float_as_uint(x1)), ws.x, sig2);
+            sig2 = f2_fma(f2_pack(__float_as_uint(x2), __float_as_uint(x3)), ws.y, sig2);
+        }
+        if (SAVE && RELU) {
+            mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
+            mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
+            mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
+            mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
+        }
+        pk[2 * q] = cvt_bf16x2<RELU>(x0, x1);
+        pk[2 * q + 1] = cvt_bf16x2<RELU>(x2, x3);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+
+// whole 256-column epilogue with the TMEM loads software-pipelined one group ahead
+template <bool RELU, bool SIGMA, bool SAVE>
+__device__ __forceinline__ void trunk_epilogue(uint32_t t_lane, const float* bias, const float* wsig, float& sig,
+                                               uint32_t (&mask)[8], uint32_t act_base, int row) {
+    uint32_t va[32], vb[32];
+    uint64_t sig2 = 0ull;
+    tmem_ld32(t_lane, va);
+#pragma unroll
+    for (int cg = 0; cg < 8; cg += 2) {
+        tmem_ld_wait();
+        tmem_ld32(t_lane + (cg + 1) * 32, vb);
+        trunk_group<RELU, SIGMA, SAVE>(va, bias + cg * 32, wsig + cg * 32, sig2, mask[cg], act_base, row, cg);
+        tmem_ld_wait();
+        if (cg + 2 < 8) tmem_ld32(t_lane + (cg + 2) * 32, va);
+        trunk_group<RELU, SIGMA, SAVE>(vb, bias + (cg + 1) * 32, wsig + (cg + 1) * 32, sig2, mask[cg + 1], act_base, row,
+                                       cg + 1);
+    }
+    if (SIGMA) {
+        float a, b;
+        f2_unpack(sig2, a, b);
+        sig = a + b;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused forward kernel
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_row_chunk(uint32_t act_base, int kblock, int row, int chunk16, uint32_t a,
-                                                uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t addr = act_base + kblock * (TILE_M * 128) + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
 template <bool SAVE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const FwdParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -201,22 +216,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
     uint8_t* smem = smem_raw + (base - raw_addr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const uint32_t bar_full = base + SM_FULL, bar_empty = base + SM_EMPTY, bar_accf = base + SM_ACCF,
-                   bar_actr = base + SM_ACTR;
+    Barriers B;
+    init_barriers(base, B);
     float* side = reinterpret_cast<float*>(smem + SM_SIDE);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1);
-        }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(bar_accf + 8 * s, 1);
-            mbar_init(bar_actr + 8 * s, TILE_M);
-        }
-        fence_barrier_init();
-    }
     if (warp == 9) tmem_alloc(base + SM_TMEM, 512);
     for (int i = threadIdx.x; i < SIDE_FLOATS; i += NUM_THREADS) side[i] = P.side[i];
     tc_fence_before();
@@ -224,82 +227,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t my_pairs = (P.n_pairs > blockIdx.x) ? (P.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t total_chunks = my_pairs * N_CHUNKS;
+    const int my_pairs = (P.n_pairs > blockIdx.x) ? (int)((P.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int total_chunks = my_pairs * N_CHUNKS;
 
     if (warp == 8) {
-        // ===================== weight producer =====================
-        if (lane == 0) {
-            for (int64_t g = 0; g < total_chunks; ++g) {
-                int slot = (int)(g % STAGES);
-                int64_t k = g / STAGES;
-                if (k > 0) mbar_wait(bar_empty + 8 * slot, (uint32_t)((k - 1) & 1), 1);
-                mbar_arrive_expect_tx(bar_full + 8 * slot, CHUNK_BYTES);
-                bulk_g2s(base + SM_RING + slot * CHUNK_BYTES, P.w_chunks + (size_t)(g % N_CHUNKS) * CHUNK_ELEMS,
-                         CHUNK_BYTES, bar_full + 8 * slot);
-            }
-        }
-    } else if (warp == 9) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
-            int64_t g[2] = {0, 0};       // next chunk (global counter) per sub-tile
-            int64_t nstart[2] = {0, 0};  // number of phase starts consumed per sub-tile
-            long long stall_t0 = 0;
-            bool stalled = false;
-            while (g[0] < total_chunks || g[1] < total_chunks) {
-                int pick = -1;
-                bool can[2];
-                can[0] = g[0] < total_chunks && (g[0] - g[1]) < LAG_MAX;
-                can[1] = g[1] < g[0];
-                int first = ((g[0] - g[1]) < LAG_TARGET) ? 0 : 1;
-                for (int a = 0; a < 2 && pick < 0; ++a) {
-                    int s = a == 0 ? first : 1 - first;
-                    if (!can[s]) continue;
-                    int c = (int)(g[s] % N_CHUNKS);
-                    int ph = c_chunk_phase[c];
-                    bool ready = true;
-                    if (c == c_ph_first[ph]) ready = mbar_probe(bar_actr + 8 * s, (uint32_t)(nstart[s] & 1));
-                    if (ready && s == 0) {
-                        int slot = (int)(g[0] % STAGES);
-                        ready = mbar_probe(bar_full + 8 * slot, (uint32_t)((g[0] / STAGES) & 1));
-                    }
-                    if (ready) pick = s;
-                }
-                if (pick < 0) {
-                    if (!stalled) { stalled = true; stall_t0 = clock64(); }
-                    else if (clock64() - stall_t0 > TC5_TIMEOUT_CYCLES) {
-                        printf("tc5: MMA issuer stalled block=%d gA=%lld gB=%lld\n", blockIdx.x, (long long)g[0],
-                               (long long)g[1]);
-                        __trap();
-                    }
-                    continue;
-                }
-                stalled = false;
-                const int s = pick;
-                const int c = (int)(g[s] % N_CHUNKS);
-                const int ph = c_chunk_phase[c];
-                const int j = c - c_ph_first[ph];
-                const int kbs = c_ph_kb[ph];
-                const int h = j / kbs, kb = j - h * kbs;
-                if (j == 0) ++nstart[s];
-                tc_fence_after();
-                const int slot = (int)(g[s] % STAGES);
-                const uint32_t a_base = base + SM_ACT + s * 65536 + (kbs == 1 ? 0 : kb) * (TILE_M * 128);
-                const uint32_t b_base = base + SM_RING + slot * CHUNK_BYTES;
-                const uint32_t d_tmem = tmem_base + s * 256 + h * 128;
-                const bool acc0 = (kb > 0) || (ph == 6);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint64_t ad = make_sdesc_sw128(a_base + k * 32, 16, 1024);
-                    uint64_t bd = make_sdesc_sw128(b_base + k * 32, 16, 1024);
-                    mma_bf16_ss(d_tmem, ad, bd, idesc, (acc0 || k > 0) ? 1u : 0u);
-                }
-                if (s == 1) mma_commit(bar_empty + 8 * slot);               // both sub-tiles have used this chunk
-                if (j == c_ph_chunks[ph] - 1) mma_commit(bar_accf + 8 * s);  // accumulator of this phase complete
-                ++g[s];
-            }
-        }
+        if (lane == 0) producer_loop(base, B, P.w_chunks, N_CHUNKS, total_chunks);
+    } else if (warp >= 9) {
+        if (lane == 0) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs);
     } else {
         // ===================== workers: PE prologue + epilogues =====================
         const int s = warp >> 2;
@@ -308,16 +242,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
         const uint32_t t_lane = tmem_base + (uint32_t(32 * (warp & 3)) << 16) + s * 256;
         const bool elected = (row == 0);
         uint32_t accf_par = 0;
-        uint32_t E[32];
+        uint32_t E[32];     // bf16(enc), 64 channels packed
+        uint32_t Elo[2];    // bf16 residuals of the raw x, y, z channels
 
-        for (int64_t it = 0; it < my_pairs; ++it) {
-            const int64_t pair = blockIdx.x + it * gridDim.x;
+        for (int it = 0; it < my_pairs; ++it) {
+            const int64_t pair = blockIdx.x + (int64_t)it * gridDim.x;
             const int64_t tile = pair * 2 + s;
             const int64_t g_row = tile * TILE_M + row;
             const bool valid = g_row < P.M;
             const int64_t gr = valid ? g_row : (P.M - 1);
             const int64_t ray = gr / P.N;
-            uint8_t* save_tile = SAVE ? reinterpret_cast<uint8_t*>(P.act_save) + tile * SAVE_TILE_BYTES : nullptr;
+            uint8_t* save_tile = SAVE ? P.act_save + tile * SAVE_TILE_BYTES : nullptr;
+            uint32_t* mask_tile = SAVE ? P.mask_save + tile * (MASK_TILE_BYTES / 4) : nullptr;
 
             // ---- positional encoding of this row's sample point (fp32, accurate sincosf) ----
             {
@@ -341,6 +277,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                 e[63] = 0.f;
 #pragma unroll
                 for (int q = 0; q < 32; ++q) E[q] = pack_bf16x2(e[2 * q], e[2 * q + 1]);
+                float lo[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) lo[c] = p[c] - __bfloat162float(__float2bfloat16_rn(p[c]));
+                Elo[0] = pack_bf16x2(lo[0], lo[1]);
+                Elo[1] = pack_bf16x2(lo[2], 0.f);
             }
             if (SAVE) {  // previous tile's last bulk store must have finished reading act before we overwrite it
                 if (elected) bulk_wait_read0();
@@ -348,17 +289,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
             }
 #pragma unroll
             for (int c = 0; c < 8; ++c) store_row_chunk(act_base, 0, row, c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
+            store_row_chunk(act_base, 1, row, 0, Elo[0], Elo[1], 0u, 0u);
+            store_row_chunk(act_base, 1, row, 1, 0u, 0u, 0u, 0u);
             tc_fence_before();
             fence_proxy_async_smem();
             if (SAVE) {
                 named_bar_sync(1 + s, TILE_M);
                 if (elected) { bulk_s2g(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
             }
-            mbar_arrive(bar_actr + 8 * s);
+            mbar_arrive(B.actr + 8 * s);
 
             float sig = 0.f;
             for (int ph = 0; ph < N_PHASES; ++ph) {
-                mbar_wait(bar_accf + 8 * s, accf_par, 2);
+                mbar_wait(B.accf + 8 * s, accf_par, 2);
                 accf_par ^= 1;
                 tc_fence_after();
                 if (SAVE) {
@@ -366,13 +309,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     named_bar_sync(1 + s, TILE_M);
                 }
                 if (ph == 5) {
-                    // L5a done: stage the skip-connection encoding as K-block 0 for L5b
+                    // L5a done: stage the skip-connection encoding as K-blocks 0 (hi) and 1 (residual) for L5b
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
                         store_row_chunk(act_base, 0, row, c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
+                    store_row_chunk(act_base, 1, row, 0, Elo[0], Elo[1], 0u, 0u);
+                    store_row_chunk(act_base, 1, row, 1, 0u, 0u, 0u, 0u);
                     tc_fence_before();
                     fence_proxy_async_smem();
-                    mbar_arrive(bar_actr + 8 * s);
+                    mbar_arrive(B.actr + 8 * s);
                     continue;
                 }
                 if (ph < 10) {
@@ -380,38 +325,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     const int layer = (ph <= 4) ? ph : (ph == 6 ? 5 : (ph == 7 ? 6 : (ph == 8 ? 7 : 8)));
                     const float* bias = side + (layer < 8 ? SIDE_BIAS + layer * H : SIDE_BFEAT);
                     const bool relu = layer < 8;
-#pragma unroll 1
-                    for (int cg = 0; cg < 8; ++cg) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + cg * 32, v);
-                        tmem_ld_wait();
-                        uint32_t pk[16];
-                        const float4* b4 = reinterpret_cast<const float4*>(bias + cg * 32);
-                        const float4* s4 = reinterpret_cast<const float4*>(side + SIDE_WSIG + cg * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 bb = b4[q];
-                            float x0 = __uint_as_float(v[4 * q]) + bb.x;
-                            float x1 = __uint_as_float(v[4 * q + 1]) + bb.y;
-                            float x2 = __uint_as_float(v[4 * q + 2]) + bb.z;
-                            float x3 = __uint_as_float(v[4 * q + 3]) + bb.w;
-                            if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
-                            if (ph == 8) {
-                                const float4 ws = s4[q];
-                                sig = fmaf(x0, ws.x, sig); sig = fmaf(x1, ws.y, sig);
-                                sig = fmaf(x2, ws.z, sig); sig = fmaf(x3, ws.w, sig);
-                            }
-                            pk[2 * q] = pack_bf16x2(x0, x1);
-                            pk[2 * q + 1] = pack_bf16x2(x2, x3);
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1],
-                                            pk[4 * c + 2], pk[4 * c + 3]);
-                    }
+                    uint32_t mask[8];
+                    const float* wsig = side + SIDE_WSIG;
+                    if (ph == 8) trunk_epilogue<true, true, SAVE>(t_lane, bias, wsig, sig, mask, act_base, row);
+                    else if (relu) trunk_epilogue<true, false, SAVE>(t_lane, bias, wsig, sig, mask, act_base, row);
+                    else trunk_epilogue<false, false, SAVE>(t_lane, bias, wsig, sig, mask, act_base, row);
                     tc_fence_before();
                     fence_proxy_async_smem();
                     if (SAVE) {
+                        if (relu) {
+                            uint4* mp = reinterpret_cast<uint4*>(mask_tile + ((size_t)layer * 128 + row) * 8);
+                            mp[0] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
+                            mp[1] = make_uint4(mask[4], mask[5], mask[6], mask[7]);
+                        }
                         named_bar_sync(1 + s, TILE_M);
                         if (elected) {
                             int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
@@ -419,17 +345,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                             bulk_commit();
                         }
                     }
-                    mbar_arrive(bar_actr + 8 * s);
+                    mbar_arrive(B.actr + 8 * s);
                 } else {
                     // ddir epilogue: + bias + per-ray direction bias, ReLU, rgb head (fp32), write preds
                     float r = 0.f, gch = 0.f, b = 0.f;
                     const float* db = P.dirbias + ray * (H / 2);
+                    uint32_t mask[4];
 #pragma unroll 1
                     for (int cg = 0; cg < 4; ++cg) {
                         uint32_t v[32];
                         tmem_ld32(t_lane + cg * 32, v);
                         tmem_ld_wait();
                         uint32_t pk[16];
+                        uint32_t mk = 0;
                         const float4* bd4 = reinterpret_cast<const float4*>(side + SIDE_BDDIR + cg * 32);
                         const float4* wr4 = reinterpret_cast<const float4*>(side + SIDE_WRGB + cg * 32);
                         const float4* wg4 = reinterpret_cast<const float4*>(side + SIDE_WRGB + 128 + cg * 32);
@@ -445,13 +373,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                             r = fmaf(x0, wr.x, r); r = fmaf(x1, wr.y, r); r = fmaf(x2, wr.z, r); r = fmaf(x3, wr.w, r);
                             gch = fmaf(x0, wg.x, gch); gch = fmaf(x1, wg.y, gch); gch = fmaf(x2, wg.z, gch); gch = fmaf(x3, wg.w, gch);
                             b = fmaf(x0, wb.x, b); b = fmaf(x1, wb.y, b); b = fmaf(x2, wb.z, b); b = fmaf(x3, wb.w, b);
-                            v[4 * q] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
-                            v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
+                            if (SAVE) {
+                                mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
+                                mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
+                                mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
+                                mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
+                                pk[2 * q] = pack_bf16x2(x0, x1);
+                                pk[2 * q + 1] = pack_bf16x2(x2, x3);
+                            }
                         }
                         if (SAVE) {
-#pragma unroll
-                            for (int q = 0; q < 16; ++q)
-                                pk[q] = pack_bf16x2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+                            mask[cg] = mk;
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
                                 store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1],
@@ -463,6 +395,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                                                      b + side[SIDE_BRGB + 2], sig + side[SIDE_BSIG]);
                     tc_fence_before();
                     if (SAVE) {
+                        uint4* mp = reinterpret_cast<uint4*>(mask_tile + ((size_t)8 * 128 + row) * 8);
+                        mp[0] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
+                        mp[1] = make_uint4(0u, 0u, 0u, 0u);
                         fence_proxy_async_smem();
                         named_bar_sync(1 + s, TILE_M);
                         if (elected) { bulk_s2g(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
@@ -564,14 +499,51 @@ __global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const float* __re
     (void)lane;
 }
 
-BlobOffsets make_offsets(const nerf_ctx* ctx) {
-    BlobOffsets off;
-    for (int i = 0; i < 12; ++i) {
-        off.w[i] = ctx->layers[i].w_off;
-        off.b[i] = ctx->layers[i].b_off;
+// MMA issue-rate probe: `reps` back-to-back passes of K=64 (4 MMAs) over fixed smem operands, N columns.
+// Reports elapsed SM cycles from first issue to commit completion.  mode 0: K-major, 1: MN-major.
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int reps, int mode, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t a_bytes = 128 * 64 * 2, b_bytes = N * 64 * 2;
+    for (uint32_t i = threadIdx.x; i < (a_bytes + b_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    const uint32_t bar = base + a_bytes + b_bytes;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + a_bytes + b_bytes + 16);
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(base + a_bytes + b_bytes + 16, 256);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N, mode, mode);
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint64_t ad, bd;
+                if (mode == 0) {
+                    ad = make_sdesc_sw128(base + k * 32, 16, 1024);
+                    bd = make_sdesc_sw128(base + a_bytes + k * 32, 16, 1024);
+                } else {
+                    ad = make_sdesc_sw128(base + k * 2048, 64 * 128, 1024);
+                    bd = make_sdesc_sw128(base + a_bytes + k * 2048, 64 * 128, 1024);
+                }
+                mma_bf16_ss(tmem_base, ad, bd, idesc, 1u);
+            }
+        }
+        mma_commit(bar);
+        mbar_wait(bar, 0, 9);
+        out[0] = clock64() - t0;
     }
-    return off;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
+
 
 }  // namespace
 
@@ -631,7 +603,8 @@ int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, cons
     P.side = ctx->side[net];
     P.dirbias = ctx->fw_dirbias;
     P.preds = reinterpret_cast<float4*>(preds);
-    P.act_save = save_acts ? ctx->act_save[net] : nullptr;
+    P.act_save = save_acts ? reinterpret_cast<uint8_t*>(ctx->act_save[net]) : nullptr;
+    P.mask_save = save_acts ? ctx->mask_save[net] : nullptr;
     int grid = (int)(P.n_pairs < num_sms() ? P.n_pairs : num_sms());
     timing_begin(0, st);
     if (save_acts) {
@@ -646,6 +619,7 @@ int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, cons
 }
 
 int64_t tc_save_bytes_per_tile() { return SAVE_TILE_BYTES; }
+int tc_fwd_chunks() { return N_CHUNKS; }
 
 }  // namespace nerf
 
@@ -659,6 +633,15 @@ extern "C" int nerf_selftest_gemm(const float* a, const float* b, float* c, int 
     size_t smem = (size_t)(128 + n) * k * 2 + 64 + 1024;
     NERF_CUDA(cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     selftest_gemm_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, b, c, n, k, mode);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+
+extern "C" int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycles_dev, void* stream) {
+    NERF_CHECK_ARG(cycles_dev && (n == 64 || n == 128 || n == 256) && reps >= 1, "bad arguments");
+    size_t smem = (size_t)(128 + n) * 64 * 2 + 64 + 1024;
+    NERF_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(n, reps, mode, cycles_dev);
     NERF_LAUNCHED();
     return NERF_OK;
 }

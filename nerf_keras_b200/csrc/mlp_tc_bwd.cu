@@ -1,20 +1,552 @@
-// Backward of the fused tcgen05 MLP (placeholder until the backward kernels land in this file).
+// Backward of the fused tcgen05 MLP (models.py:94-106 via tf.GradientTape in the reference; SURVEY
+// Appendix A is the hand-derived target).  Three kinds of kernels, all sm_100a:
+//
+//  1. nerf_mlp_bwd_tc_kernel -- the dX chain.  Same skeleton as the forward kernel (two 128-row
+//     sub-tiles per CTA, shared weight ring, TMEM accumulators), streaming the TRANSPOSED weights:
+//     rgb head and ddir ReLU on CUDA cores -> dZ_ddir; then dZ_ddir x Wddir^T, x Wfeat^T (+ sigma
+//     head), x W7^T ... x W1^T, each epilogue masking with the forward ReLU sign bits and writing the
+//     bf16 dZ tile both as the next A operand and (bulk store) as an image for the weight-gradient
+//     kernel.
+//  2. nerf_wgrad_tc_kernel -- dW = X^T dZ per layer as a split-K tcgen05 GEMM over the saved activation
+//     and dZ images.  The images are exactly the 128B-swizzled operand tiles, so a [samples x features]
+//     tile is consumed as an MN-major operand (features along M/N, samples along K) without any
+//     transpose.  Accumulators stay in TMEM for a CTA's whole slab of samples; bias gradients (column
+//     sums of dZ) and the tiny sigma / rgb head gradients are CUDA-core side jobs on the same tiles.
+//  3. ddir_dirgrad_kernel -- gradient of the direction rows of Wddir (the per-ray bias hoisted out of
+//     the forward kernel): per-ray sums of dZ_ddir times the ray's direction encoding.
 #include "common.cuh"
 #include "ctx.cuh"
+#include "mlp_tc_common.cuh"
+
+using namespace nerf;
+using namespace tc5;
+using namespace tcmlp;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// 1. dX chain
+// ------------------------------------------------------------------------------------------------
+// phases: P0 dZ_ddir x Wddir[0:256]^T (K=128) ; P1 dFeat x Wfeat^T ; P2..P8 dZ_l x W_l^T for l = 7..1
+constexpr int B_PHASES = 9;
+constexpr int B_CHUNKS = 68;
+__constant__ Program c_bwd_prog = {
+    B_PHASES, B_CHUNKS,
+    {4, 8, 8, 8, 8, 8, 8, 8, 8, 0, 0, 0},
+    {2, 4, 4, 4, 4, 4, 4, 4, 4, 0, 0, 0},
+    {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
+
+// B[n][k] = W_phase[n][k]  (weights in their natural (in, out) layout are K-major for dX = dZ x W^T)
+__device__ __forceinline__ float bwd_weight_at(const float* __restrict__ blob, const BlobOffsets& off, int phase,
+                                               int n, int k) {
+    if (phase == 0) return blob[off.w[10] + (int64_t)n * (H / 2) + k];   // Wddir rows 0..255, 128 cols
+    if (phase == 1) return blob[off.w[9] + (int64_t)n * H + k];          // Wfeature
+    const int l = 9 - phase;                                             // 7..1
+    return blob[off.w[l] + (int64_t)n * H + k];                          // rows 0..255 (h part for l = 5)
+}
+
+__global__ void __launch_bounds__(256) pack_bwd_kernel(const float* __restrict__ blob, BlobOffsets off,
+                                                       __nv_bfloat16* __restrict__ chunks) {
+    const int total = B_CHUNKS * 128 * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int g = i / (128 * 8);
+        int rem = i - g * 128 * 8;
+        int n = rem >> 3, kg = rem & 7;
+        int phase, j;
+        if (g < 4) { phase = 0; j = g; } else { phase = 1 + (g - 4) / 8; j = (g - 4) % 8; }
+        int kbs = c_bwd_prog.kb[phase];
+        int h = j / kbs, kb = j - h * kbs;
+        uint32_t packed[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int k0 = kb * 64 + kg * 8 + 2 * q;
+            packed[q] = pack_bf16x2(bwd_weight_at(blob, off, phase, h * 128 + n, k0),
+                                    bwd_weight_at(blob, off, phase, h * 128 + n, k0 + 1));
+        }
+        uint8_t* dst = reinterpret_cast<uint8_t*>(chunks) + (size_t)g * CHUNK_BYTES + sw128_offset(n, kg * 8);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
+struct BwdParams {
+    const float4* dpreds;   // (M) dL/d[r,g,b,sigma] raw
+    int64_t M;
+    int64_t n_pairs;
+    const __nv_bfloat16* w_chunks;
+    const float* side;
+    const uint32_t* mask_save;
+    uint8_t* dz_save;
+};
+
+// one 32-column group of a chain epilogue: optional sigma-head term, ReLU mask, bf16, swizzled store
+template <bool SIGMA, bool MASK>
+__device__ __forceinline__ void chain_group(const uint32_t (&v)[32], float dsig, const float* wsig_g, uint32_t mk,
+                                            uint32_t act_base, int row, int cg) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        float x0 = __uint_as_float(v[2 * q]), x1 = __uint_as_float(v[2 * q + 1]);
+        if (SIGMA) {
+            x0 = fmaf(dsig, wsig_g[2 * q], x0);
+            x1 = fmaf(dsig, wsig_g[2 * q + 1], x1);
+        }
+        if (MASK) {
+            x0 = ((mk >> (2 * q)) & 1u) ? x0 : 0.f;
+            x1 = ((mk >> (2 * q + 1)) & 1u) ? x1 : 0.f;
+        }
+        pk[q] = cvt_bf16x2<false>(x0, x1);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+
+template <bool SIGMA, bool MASK>
+__device__ __forceinline__ void chain_epilogue(uint32_t t_lane, float dsig, const float* wsig, const uint32_t (&mask)[8],
+                                               uint32_t act_base, int row) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(t_lane, va);
+#pragma unroll
+    for (int cg = 0; cg < 8; cg += 2) {
+        tmem_ld_wait();
+        tmem_ld32(t_lane + (cg + 1) * 32, vb);
+        chain_group<SIGMA, MASK>(va, dsig, wsig + cg * 32, mask[cg], act_base, row, cg);
+        tmem_ld_wait();
+        if (cg + 2 < 8) tmem_ld32(t_lane + (cg + 2) * 32, va);
+        chain_group<SIGMA, MASK>(vb, dsig, wsig + (cg + 1) * 32, mask[cg + 1], act_base, row, cg + 1);
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const BwdParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    Barriers B;
+    init_barriers(base, B);
+    float* side = reinterpret_cast<float*>(smem + SM_SIDE);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+    if (warp == 9) tmem_alloc(base + SM_TMEM, 512);
+    for (int i = threadIdx.x; i < SIDE_FLOATS; i += NUM_THREADS) side[i] = P.side[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int my_pairs = (P.n_pairs > blockIdx.x) ? (int)((P.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int total_chunks = my_pairs * B_CHUNKS;
+
+    if (warp == 8) {
+        if (lane == 0) producer_loop(base, B, P.w_chunks, B_CHUNKS, total_chunks);
+    } else if (warp >= 9) {
+        if (lane == 0) issuer_loop(base, B, tmem_base, c_bwd_prog, warp - 9, my_pairs);
+    } else {
+        const int s = warp >> 2;
+        const int row = threadIdx.x - s * TILE_M;
+        const uint32_t act_base = base + SM_ACT + s * 65536;
+        const uint32_t t_lane = tmem_base + (uint32_t(32 * (warp & 3)) << 16) + s * 256;
+        const bool elected = (row == 0);
+        uint32_t accf_par = 0;
+
+        for (int it = 0; it < my_pairs; ++it) {
+            const int64_t pair = blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t tile = pair * 2 + s;
+            const int64_t g_row = tile * TILE_M + row;
+            const bool valid = g_row < P.M;
+            const uint32_t* mask_tile = P.mask_save + tile * (MASK_TILE_BYTES / 4);
+            uint8_t* dz_tile = P.dz_save + tile * DZ_TILE_BYTES;
+            const float4 dp = valid ? P.dpreds[g_row] : make_float4(0.f, 0.f, 0.f, 0.f);
+
+            // ---- prologue: rgb head backward + ddir ReLU mask -> dZ_ddir (128 wide) ----
+            if (elected) bulk_wait_read0();
+            named_bar_sync(1 + s, TILE_M);
+            {
+                const uint4 mk4 = *reinterpret_cast<const uint4*>(mask_tile + ((size_t)8 * 128 + row) * 8);
+                const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
+#pragma unroll
+                for (int cg = 0; cg < 4; ++cg) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int c0 = cg * 32 + 2 * q;
+                        float x0 = dp.x * side[SIDE_WRGB + c0] + dp.y * side[SIDE_WRGB + 128 + c0] + dp.z * side[SIDE_WRGB + 256 + c0];
+                        float x1 = dp.x * side[SIDE_WRGB + c0 + 1] + dp.y * side[SIDE_WRGB + 128 + c0 + 1] +
+                                   dp.z * side[SIDE_WRGB + 256 + c0 + 1];
+                        x0 = ((mk[cg] >> (2 * q)) & 1u) ? x0 : 0.f;
+                        x1 = ((mk[cg] >> (2 * q + 1)) & 1u) ? x1 : 0.f;
+                        pk[q] = cvt_bf16x2<false>(x0, x1);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2],
+                                        pk[4 * c + 3]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            named_bar_sync(1 + s, TILE_M);
+            if (elected) { bulk_s2g(dz_tile + DZ_DDIR, act_base, 32768); bulk_commit(); }
+            mbar_arrive(B.actr + 8 * s);
+
+            for (int ph = 0; ph < B_PHASES; ++ph) {
+                mbar_wait(B.accf + 8 * s, accf_par, 2);
+                accf_par ^= 1;
+                tc_fence_after();
+                if (elected) bulk_wait_read0();
+                named_bar_sync(1 + s, TILE_M);
+                int64_t dst;
+                uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (ph == 0) {
+                    dst = DZ_FEAT;                                   // feature layer is linear: no mask
+                    chain_epilogue<false, false>(t_lane, 0.f, side + SIDE_WSIG, mask, act_base, row);
+                } else {
+                    const int ml = (ph == 1) ? 7 : (8 - ph);         // mask of the ReLU output feeding this grad: h8 .. h1
+                    const uint4* mp = reinterpret_cast<const uint4*>(mask_tile + ((size_t)ml * 128 + row) * 8);
+                    const uint4 m0 = mp[0], m1 = mp[1];
+                    mask[0] = m0.x; mask[1] = m0.y; mask[2] = m0.z; mask[3] = m0.w;
+                    mask[4] = m1.x; mask[5] = m1.y; mask[6] = m1.z; mask[7] = m1.w;
+                    dst = DZ_Z + (int64_t)65536 * ml;
+                    if (ph == 1) chain_epilogue<true, true>(t_lane, dp.w, side + SIDE_WSIG, mask, act_base, row);
+                    else chain_epilogue<false, true>(t_lane, 0.f, side + SIDE_WSIG, mask, act_base, row);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                named_bar_sync(1 + s, TILE_M);
+                if (elected) { bulk_s2g(dz_tile + dst, act_base, 65536); bulk_commit(); }
+                if (ph < B_PHASES - 1) mbar_arrive(B.actr + 8 * s);
+            }
+        }
+        if (elected) bulk_wait_all0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. weight gradients: dW[k_in][n_out] = sum over samples  X[m][k_in] * dZ[m][n_out]
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 192;            // 4 worker warps + loader warp + MMA warp
+constexpr int WG_STAGES = 3;
+constexpr int WG_SLOT = 65536;             // A half-blocks (4 x 8 KB) + B half-blocks (4 x 8 KB)
+constexpr int WG_SM_BAR = WG_STAGES * WG_SLOT;
+constexpr int WG_SMEM = WG_SM_BAR + 128 + 1024;
+constexpr int WG_NJOBS = 12;
+
+struct WgJob {
+    int64_t a_off;       // byte offset of the X image inside a saved-activation tile
+    int64_t b_off;       // byte offset of the dZ image inside a dZ tile
+    int n_a;             // 64-feature blocks of X: 1, 2 or 4
+    int n_b;             // 64-feature blocks of dZ: 2 or 4   (0: no MMA, CUDA-core job)
+    int64_t w_dst;       // float offset (in the grads blob of this net) of dW row 0
+    int ld;              // fan_out
+    int rows;            // valid rows of dW produced by this job
+    int64_t bias_dst;    // float offset of the bias gradient (column sums of dZ), or -1
+    int extra;           // 0 none, 1 sigma head (X weighted by dpreds.w), 2 rgb head (X weighted by dpreds.xyz)
+    int64_t extra_w, extra_b;
+};
+struct WgParams {
+    WgJob jobs[WG_NJOBS];
+    const uint8_t* act_save;
+    const uint8_t* dz_save;
+    const float4* dpreds;
+    int64_t M;
+    int64_t n_half_tiles;   // 2 * tiles
+    float* grads;           // this net's gradient blob
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WgJob& J = P.jobs[blockIdx.y];
+    const uint32_t bar_full = base + WG_SM_BAR, bar_empty = bar_full + 8 * WG_STAGES, bar_done = bar_empty + 8 * WG_STAGES;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_SM_BAR + 8 * (2 * WG_STAGES + 1));
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1 + 128);   // tcgen05.commit + the 128 side-job threads
+        }
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(base + WG_SM_BAR + 8 * (2 * WG_STAGES + 1), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // this CTA's slab of half-tiles (64 samples each)
+    const int64_t per = (P.n_half_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t ht0 = (int64_t)blockIdx.x * per;
+    const int64_t ht1 = (ht0 + per < P.n_half_tiles) ? ht0 + per : P.n_half_tiles;
+    const int n_ht = (ht1 > ht0) ? (int)(ht1 - ht0) : 0;
+    const int n_a_load = (J.n_a == 1) ? 2 : J.n_a;   // a single 64-feature block is loaded twice (M = 128 MMA)
+    const int n_mh = (J.n_b == 0) ? 0 : ((J.n_a == 4) ? 2 : 1);
+
+    if (warp == 4) {
+        // ===================== loader =====================
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t par = 1;
+            for (int i = 0; i < n_ht; ++i) {
+                const int64_t ht = ht0 + i;
+                const int64_t tile = ht >> 1;
+                const int half = (int)(ht & 1);
+                mbar_wait(bar_empty + 8 * slot, par, 11);
+                const uint32_t dst = base + slot * WG_SLOT;
+                mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)(n_a_load + J.n_b) * 8192u);
+                const uint8_t* a_src = P.act_save + tile * SAVE_TILE_BYTES + J.a_off + half * 8192;
+                for (int b = 0; b < n_a_load; ++b)
+                    bulk_g2s(dst + b * 8192, a_src + (J.n_a == 1 ? 0 : b) * 16384, 8192, bar_full + 8 * slot);
+                const uint8_t* b_src = P.dz_save + tile * DZ_TILE_BYTES + J.b_off + half * 8192;
+                for (int b = 0; b < J.n_b; ++b)
+                    bulk_g2s(dst + 32768 + b * 8192, b_src + b * 16384, 8192, bar_full + 8 * slot);
+                if (++slot == WG_STAGES) { slot = 0; par ^= 1; }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 64 * (J.n_b ? J.n_b : 2), 1, 1);
+            int slot = 0;
+            uint32_t par = 0;
+            for (int i = 0; i < n_ht; ++i) {
+                mbar_wait(bar_full + 8 * slot, par, 12);
+                tc_fence_after();
+                const uint32_t a0 = base + slot * WG_SLOT, b0 = a0 + 32768;
+                for (int mh = 0; mh < n_mh; ++mh) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        const uint64_t ad = make_sdesc_sw128(a0 + mh * 16384 + k4 * 2048, 8192, 1024);
+                        const uint64_t bd = make_sdesc_sw128(b0 + k4 * 2048, 8192, 1024);
+                        mma_bf16_ss(tmem_base + mh * 256, ad, bd, idesc, (i > 0 || k4 > 0) ? 1u : 0u);
+                    }
+                }
+                mma_commit(bar_empty + 8 * slot);
+                if (++slot == WG_STAGES) { slot = 0; par ^= 1; }
+            }
+            mma_commit(bar_done);
+        }
+    } else {
+        // ===================== side jobs + final reduction =====================
+        const int tid = threadIdx.x;                 // 0..127
+        float s0 = 0.f, s1 = 0.f;                    // bias: column sums of dZ (cols 2 tid, 2 tid + 1)
+        float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; // head gradients for features 2 tid, 2 tid + 1
+        float eb[3] = {0.f, 0.f, 0.f};
+        const int blk = tid >> 5, wd = tid & 31;     // 64-feature block and 4-byte word inside the 128 B row
+        int slot = 0;
+        uint32_t par = 0;
+        for (int i = 0; i < n_ht; ++i) {
+            const int64_t ht = ht0 + i;
+            mbar_wait(bar_full + 8 * slot, par, 13);
+            const uint32_t a0 = base + slot * WG_SLOT, b0 = a0 + 32768;
+            if (J.bias_dst >= 0 && blk < J.n_b) {
+#pragma unroll 8
+                for (int r = 0; r < 64; ++r) {
+                    const uint32_t addr = b0 + blk * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
+                    uint32_t w;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
+                    s0 += __uint_as_float(w << 16);
+                    s1 += __uint_as_float(w & 0xFFFF0000u);
+                }
+            }
+            if (J.extra && blk < J.n_a) {
+                const int64_t m0 = ht * 64;
+#pragma unroll 4
+                for (int r = 0; r < 64; ++r) {
+                    const int64_t m = m0 + r;
+                    const float4 dp = (m < P.M) ? __ldg(P.dpreds + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const uint32_t addr = a0 + blk * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
+                    uint32_t w;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
+                    const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xFFFF0000u);
+                    if (J.extra == 1) {
+                        e[0] = fmaf(x0, dp.w, e[0]); e[1] = fmaf(x1, dp.w, e[1]);
+                        if (tid == 0) eb[0] += dp.w;
+                    } else {
+                        e[0] = fmaf(x0, dp.x, e[0]); e[1] = fmaf(x0, dp.y, e[1]); e[2] = fmaf(x0, dp.z, e[2]);
+                        e[3] = fmaf(x1, dp.x, e[3]); e[4] = fmaf(x1, dp.y, e[4]); e[5] = fmaf(x1, dp.z, e[5]);
+                        if (tid == 0) { eb[0] += dp.x; eb[1] += dp.y; eb[2] += dp.z; }
+                    }
+                }
+            }
+            mbar_arrive(bar_empty + 8 * slot);
+            if (++slot == WG_STAGES) { slot = 0; par ^= 1; }
+        }
+        if (n_ht > 0) {
+            if (J.bias_dst >= 0 && blk < J.n_b) {
+                atomicAdd(P.grads + J.bias_dst + 2 * tid, s0);
+                atomicAdd(P.grads + J.bias_dst + 2 * tid + 1, s1);
+            }
+            if (J.extra == 1) {          // sigma head: W (256,1), b (1)
+                atomicAdd(P.grads + J.extra_w + 2 * tid, e[0]);
+                atomicAdd(P.grads + J.extra_w + 2 * tid + 1, e[1]);
+                if (tid == 0) atomicAdd(P.grads + J.extra_b, eb[0]);
+            } else if (J.extra == 2 && blk < J.n_a) {   // rgb head: W (128,3), b (3)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) atomicAdd(P.grads + J.extra_w + (2 * tid) * 3 + q, e[q]);
+                if (tid == 0)
+                    for (int q = 0; q < 3; ++q) atomicAdd(P.grads + J.extra_b + q, eb[q]);
+            }
+            if (n_mh > 0) {
+                mbar_wait(bar_done, 0, 14);
+                tc_fence_after();
+                const int N = 64 * J.n_b;
+                for (int mh = 0; mh < n_mh; ++mh) {
+                    const int r = mh * 128 + 32 * warp + lane;   // dW row = input feature
+                    for (int cg = 0; cg < N / 32; ++cg) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + (uint32_t(32 * warp) << 16) + mh * 256 + cg * 32, v);
+                        tmem_ld_wait();
+                        if (r < J.rows) {
+                            float* dst = P.grads + J.w_dst + (int64_t)r * J.ld + cg * 32;
+                            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                               __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                            } else {   // layers after the 257-float sigma block are not 16-byte aligned in the blob
+#pragma unroll
+                                for (int q = 0; q < 32; ++q) atomicAdd(dst + q, __uint_as_float(v[q]));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. direction rows of Wddir: dW[256+k][c] = sum_rays enc_dir(ray)[k] * sum_{samples of ray} dZ_ddir[m][c]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) ddir_dirgrad_kernel(const float* __restrict__ d, int64_t rays, int N,
+                                                           const uint8_t* __restrict__ dz_save, float* __restrict__ g_wddir) {
+    __shared__ float enc[ENC_D];
+    const int c = threadIdx.x;
+    float acc[ENC_D];
+#pragma unroll
+    for (int k = 0; k < ENC_D; ++k) acc[k] = 0.f;
+    for (int64_t ray = blockIdx.x; ray < rays; ray += gridDim.x) {
+        if (c < ENC_D) {
+            float v;
+            if (c < 3) v = d[ray * 3 + c];
+            else {
+                int q = c - 3, i = q / 6, r = q - i * 6, comp = r % 3;
+                float arg = __fmul_rn(exp2f((float)i), d[ray * 3 + comp]);
+                v = (r >= 3) ? cosf(arg) : sinf(arg);
+            }
+            enc[c] = v;
+        }
+        __syncthreads();
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const int64_t m = ray * N + n;
+            const int64_t tile = m >> 7;
+            const int r = (int)(m & 127);
+            const uint8_t* p = dz_save + tile * DZ_TILE_BYTES + DZ_DDIR + (c >> 6) * 16384 + sw128_offset(r, c & 63);
+            s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+        }
+#pragma unroll
+        for (int k = 0; k < ENC_D; ++k) acc[k] = fmaf(enc[k], s, acc[k]);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < ENC_D; ++k) atomicAdd(g_wddir + (int64_t)(H + k) * (H / 2) + c, acc[k]);
+}
+
+}  // namespace
 
 namespace nerf {
 int64_t tc_save_bytes_per_tile();
 
 int tc_train_alloc(nerf_ctx* ctx) {
     const nerf_config& c = ctx->cfg;
-    const int64_t tiles_c = ceil_div((int64_t)c.max_rays * c.ns_coarse, 256) * 2;
-    const int64_t tiles_f = ceil_div((int64_t)c.max_rays * (c.ns_coarse + c.ns_fine), 256) * 2;
-    NERF_CUDA(cudaMalloc((void**)&ctx->act_save[0], (size_t)(tiles_c * tc_save_bytes_per_tile())));
-    NERF_CUDA(cudaMalloc((void**)&ctx->act_save[1], (size_t)(tiles_f * tc_save_bytes_per_tile())));
+    const int64_t tiles[2] = {ceil_div((int64_t)c.max_rays * c.ns_coarse, 256) * 2,
+                              ceil_div((int64_t)c.max_rays * (c.ns_coarse + c.ns_fine), 256) * 2};
+    for (int net = 0; net < 2; ++net) {
+        NERF_CUDA(cudaMalloc((void**)&ctx->act_save[net], (size_t)(tiles[net] * SAVE_TILE_BYTES)));
+        NERF_CUDA(cudaMalloc((void**)&ctx->dz_save[net], (size_t)(tiles[net] * DZ_TILE_BYTES)));
+        NERF_CUDA(cudaMalloc((void**)&ctx->mask_save[net], (size_t)(tiles[net] * MASK_TILE_BYTES)));
+        NERF_CUDA(cudaMalloc((void**)&ctx->w_bwd[net], (size_t)B_CHUNKS * CHUNK_BYTES));
+    }
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     return NERF_OK;
 }
 
-int tc_backward(nerf_ctx*, int, const float*, const float*, const float*, int64_t, int, const float*, cudaStream_t) {
-    return fail(NERF_ERR_STATE, "tc_backward: not built yet");
+// gradients of one net given dL/dpreds; the forward must have run with save_acts on the same batch
+int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
+                const float* d_preds, cudaStream_t st) {
+    (void)o; (void)t;
+    const int64_t M = B * (int64_t)N;
+    const int64_t n_pairs = ceil_div(M, 2 * TILE_M);
+    BlobOffsets off = make_offsets(ctx);
+    const float* blob = ctx->params + (int64_t)net * ctx->n_params;
+    float* grads = ctx->grads + (int64_t)net * ctx->n_params;
+
+    pack_bwd_kernel<<<num_sms(), 256, 0, st>>>(blob, off, ctx->w_bwd[net]);
+    NERF_LAUNCHED();
+
+    BwdParams P;
+    P.dpreds = reinterpret_cast<const float4*>(d_preds);
+    P.M = M;
+    P.n_pairs = n_pairs;
+    P.w_chunks = ctx->w_bwd[net];
+    P.side = ctx->side[net];
+    P.mask_save = ctx->mask_save[net];
+    P.dz_save = reinterpret_cast<uint8_t*>(ctx->dz_save[net]);
+    int grid = (int)(n_pairs < num_sms() ? n_pairs : num_sms());
+    timing_begin(1, st);
+    nerf_mlp_bwd_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
+    timing_end(1, st);
+    NERF_LAUNCHED();
+
+    WgParams W;
+    W.act_save = reinterpret_cast<const uint8_t*>(ctx->act_save[net]);
+    W.dz_save = reinterpret_cast<const uint8_t*>(ctx->dz_save[net]);
+    W.dpreds = reinterpret_cast<const float4*>(d_preds);
+    W.M = M;
+    W.n_half_tiles = n_pairs * 4;
+    W.grads = grads;
+    auto job = [&](int i, int64_t a_off, int n_a, int64_t b_off, int n_b, int64_t w_dst, int ld, int rows, int64_t bias,
+                   int extra, int64_t ew, int64_t eb) {
+        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, bias, extra, ew, eb};
+    };
+    job(0, SAVE_ENC, 1, DZ_Z, 4, off.w[0], H, ENC_X, off.b[0], 0, 0, 0);
+    for (int l = 1; l <= 4; ++l)
+        job(l, SAVE_H + 65536 * (l - 1), 4, DZ_Z + 65536 * l, 4, off.w[l], H, H, off.b[l], 0, 0, 0);
+    job(5, SAVE_H + 65536 * 4, 4, DZ_Z + 65536 * 5, 4, off.w[5], H, H, off.b[5], 0, 0, 0);
+    job(6, SAVE_ENC, 1, DZ_Z + 65536 * 5, 4, off.w[5] + (int64_t)H * H, H, ENC_X, -1, 0, 0, 0);
+    job(7, SAVE_H + 65536 * 5, 4, DZ_Z + 65536 * 6, 4, off.w[6], H, H, off.b[6], 0, 0, 0);
+    job(8, SAVE_H + 65536 * 6, 4, DZ_Z + 65536 * 7, 4, off.w[7], H, H, off.b[7], 0, 0, 0);
+    job(9, SAVE_H + 65536 * 7, 4, DZ_FEAT, 4, off.w[9], H, H, off.b[9], 1, off.w[8], off.b[8]);
+    job(10, SAVE_FEAT, 4, DZ_DDIR, 2, off.w[10], H / 2, H, off.b[10], 0, 0, 0);
+    job(11, SAVE_HD, 2, 0, 0, 0, 0, 0, -1, 2, off.w[11], off.b[11]);
+    int slabs = num_sms() / WG_NJOBS;
+    if (slabs < 1) slabs = 1;
+    if (slabs > W.n_half_tiles) slabs = (int)W.n_half_tiles;
+    timing_begin(2, st);
+    nerf_wgrad_tc_kernel<<<dim3(slabs, WG_NJOBS), WG_THREADS, WG_SMEM, st>>>(W);
+    timing_end(2, st);
+    NERF_LAUNCHED();
+
+    ddir_dirgrad_kernel<<<(unsigned)(B < 2 * num_sms() ? B : 2 * num_sms()), 128, 0, st>>>(
+        d, B, N, reinterpret_cast<const uint8_t*>(ctx->dz_save[net]), grads + off.w[10]);
+    NERF_LAUNCHED();
+    return NERF_OK;
 }
 }  // namespace nerf

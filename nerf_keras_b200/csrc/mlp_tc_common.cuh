@@ -1,0 +1,187 @@
+// Shared skeleton of the fused tcgen05 MLP kernels (forward chain and backward dX chain):
+// shared-memory map, chunk "programs", the weight producer and the MMA issuer.
+//
+// A kernel instance processes PAIRS of 128-row sub-tiles (A, B).  Each sub-tile owns a 64 KB
+// activation tile in shared memory (the A operand, 4 K-blocks of [128 x 64] bf16, 128B-swizzled)
+// and 256 fp32 accumulator columns in TMEM.  Weights arrive as a stream of 16 KB chunks
+// ([128 n x 64 k] bf16, K-major, 128B-swizzled) through a STAGES-deep ring; both sub-tiles consume
+// every chunk, so L2->SMEM traffic is paid once per 256 rows.  Two MMA issuer threads (one per
+// sub-tile) feed the tensor pipe, so one sub-tile's epilogue (CUDA cores) overlaps the other's MMAs.
+#pragma once
+#include "common.cuh"
+#include "tc5.cuh"
+
+namespace tcmlp {
+
+using namespace tc5;
+
+constexpr int H = 256;
+constexpr int ENC_X = 63;
+constexpr int ENC_D = 27;
+constexpr int TILE_M = 128;
+constexpr int CHUNK_BYTES = 16384;
+constexpr int CHUNK_ELEMS = CHUNK_BYTES / 2;
+constexpr int STAGES = 5;
+constexpr int MAX_PHASES = 12;
+
+// phase flags
+constexpr int PH_ACC = 1;   // first k-block accumulates onto the existing accumulator
+constexpr int PH_ENC = 2;   // k-block 1 of this phase holds only 16 meaningful columns (one K=16 MMA)
+
+struct Program {
+    int n_phases;
+    int n_chunks;
+    int chunks[MAX_PHASES];  // chunks per phase
+    int kb[MAX_PHASES];      // k-blocks per N-half
+    int flags[MAX_PHASES];
+};
+
+// fp32 side table (per net) kept in shared memory by both kernels (floats)
+constexpr int SIDE_BIAS = 0;        // 8 x 256 trunk biases
+constexpr int SIDE_BFEAT = 2048;    // 256
+constexpr int SIDE_BDDIR = 2304;    // 128
+constexpr int SIDE_WSIG = 2432;     // 256
+constexpr int SIDE_WRGB = 2688;     // 3 x 128 ([channel][k])
+constexpr int SIDE_BSIG = 3072;     // 1
+constexpr int SIDE_BRGB = 3073;     // 3
+constexpr int SIDE_FLOATS = 3080;
+
+// shared memory map (bytes, relative to the 1024-aligned base)
+constexpr int SM_ACT = 0;                                  // 2 x 65536
+constexpr int SM_RING = 131072;                            // STAGES x 16384
+constexpr int SM_SIDE = SM_RING + STAGES * CHUNK_BYTES;    // 12320
+constexpr int SM_BAR = SM_SIDE + SIDE_FLOATS * 4;
+constexpr int SM_FULL = SM_BAR;                            // STAGES mbarriers
+constexpr int SM_EMPTY = SM_FULL + 8 * STAGES;             // STAGES
+constexpr int SM_ACCF = SM_EMPTY + 8 * STAGES;             // 2
+constexpr int SM_ACTR = SM_ACCF + 16;                      // 2
+constexpr int SM_TMEM = SM_ACTR + 16;                      // u32
+constexpr int SM_TOTAL = SM_TMEM + 16;
+constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
+
+constexpr int NUM_THREADS = 352;  // 8 worker warps (4 per sub-tile) + producer warp + 2 MMA issuer warps
+
+// saved activation images per 128-row tile (bytes): written by the forward kernel in training mode,
+// read by the weight-gradient kernel.  Every image is the exact shared-memory operand tile.
+constexpr int64_t SAVE_ENC = 0;                         // [128 x 64] bf16(enc), col 63 = 0
+constexpr int64_t SAVE_H = 16384;                       // + 65536 * i : output of trunk layer i (0..7)
+constexpr int64_t SAVE_FEAT = 16384 + 8 * 65536;        // feature (linear) output
+constexpr int64_t SAVE_HD = SAVE_FEAT + 65536;          // ddir output, 128 wide (32 KB)
+constexpr int64_t SAVE_TILE_BYTES = SAVE_HD + 32768;    // 638976
+// ReLU sign masks per tile: [9 layers][128 rows][8 x u32]  (layer 8 = ddir, 4 words used)
+constexpr int64_t MASK_TILE_BYTES = 9 * 128 * 32;       // 36864
+// gradient (dZ) images per tile, written by the backward chain kernel
+constexpr int64_t DZ_Z = 0;                             // + 65536 * l : grad wrt pre-activation of trunk layer l
+constexpr int64_t DZ_FEAT = 8 * 65536;
+constexpr int64_t DZ_DDIR = 9 * 65536;                  // 128 wide (32 KB)
+constexpr int64_t DZ_TILE_BYTES = DZ_DDIR + 32768;      // 622592
+
+// per-net layer offsets inside the flat fp32 blob (floats): d0..d7, sigma, feature, ddir, rgb
+struct BlobOffsets {
+    int64_t w[12];
+    int64_t b[12];
+};
+template <class Ctx>
+inline BlobOffsets make_offsets(const Ctx* ctx) {
+    BlobOffsets off;
+    for (int i = 0; i < 12; ++i) {
+        off.w[i] = ctx->layers[i].w_off;
+        off.b[i] = ctx->layers[i].b_off;
+    }
+    return off;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// one 16-byte chunk (8 bf16) of row `row` into K-block `kblock` of a 128-row activation tile
+__device__ __forceinline__ void store_row_chunk(uint32_t act_base, int kblock, int row, int chunk16, uint32_t a,
+                                                uint32_t b, uint32_t c, uint32_t d) {
+    uint32_t addr = act_base + kblock * (TILE_M * 128) + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct Barriers {
+    uint32_t full, empty, accf, actr;
+};
+
+__device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B) {
+    B.full = base + SM_FULL; B.empty = base + SM_EMPTY; B.accf = base + SM_ACCF; B.actr = base + SM_ACTR;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(B.full + 8 * i, 1);
+            mbar_init(B.empty + 8 * i, 2);   // one tcgen05.commit per sub-tile
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(B.accf + 8 * s, 1);
+            mbar_init(B.actr + 8 * s, TILE_M);
+        }
+        fence_barrier_init();
+    }
+}
+
+// ---- weight producer: one thread streams the chunk program `n_tiles` times through the ring ----
+__device__ __forceinline__ void producer_loop(uint32_t base, const Barriers& B, const __nv_bfloat16* chunks,
+                                              int n_chunks, int total_chunks) {
+    int slot = 0, c = 0;
+    uint32_t par = 1;  // first lap: slots are free (waiting on parity 1 of a fresh barrier returns at once)
+    for (int g = 0; g < total_chunks; ++g) {
+        mbar_wait(B.empty + 8 * slot, par, 1);
+        mbar_arrive_expect_tx(B.full + 8 * slot, CHUNK_BYTES);
+        bulk_g2s(base + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)c * CHUNK_ELEMS, CHUNK_BYTES, B.full + 8 * slot);
+        if (++c == n_chunks) c = 0;
+        if (++slot == STAGES) { slot = 0; par ^= 1; }
+    }
+}
+
+// ---- MMA issuers: one dedicated thread per sub-tile ------------------------------------------------
+// Each issuer walks the chunk program for its own sub-tile: wait for the sub-tile's A tile at a phase
+// start, wait for the weight chunk, issue the K=16 MMAs, release the ring slot with tcgen05.commit
+// (a slot is recycled when BOTH sub-tiles' commits have arrived), and commit the accumulator barrier at
+// the end of a phase.  The tensor pipe executes the two instruction streams in arrival order, so one
+// sub-tile's MMAs fill the gaps left by the other's epilogue.
+__device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, uint32_t tmem_base, const Program& prog,
+                                            int s, int n_tiles) {
+    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+    // descriptor template: LBO = 16 B (unused for swizzled K-major), SBO = 1024 B, version 1, SWIZZLE_128B
+    const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
+    const uint32_t lbo_bits = (16u >> 4) << 16;
+    const uint32_t a_tile = ((base + SM_ACT + s * 65536) & 0x3FFFF) >> 4;
+    const uint32_t ring0 = ((base + SM_RING) & 0x3FFFF) >> 4;
+    const uint32_t d_base = tmem_base + s * 256;
+    const int n_phases = prog.n_phases;
+    int slot = 0;
+    uint32_t ring_par = 0, actr_par = 0;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        for (int ph = 0; ph < n_phases; ++ph) {
+            const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
+            mbar_wait(B.actr + 8 * s, actr_par, 3);
+            actr_par ^= 1;
+            int h = 0, kb = 0;
+            for (int j = 0; j < n_ch; ++j) {
+                mbar_wait(B.full + 8 * slot, ring_par, 4);
+                tc_fence_after();
+                const uint32_t a_lo = (a_tile + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
+                const uint32_t b_lo = (ring0 + slot * (CHUNK_BYTES >> 4)) | lbo_bits;
+                const uint32_t d_tmem = d_base + h * 128;
+                const bool acc0 = (kb > 0) || (flags & PH_ACC);
+                const int n_mma = ((flags & PH_ENC) && kb == 1) ? 1 : 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < n_mma) {
+                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                        mma_bf16_ss(d_tmem, ad, bd, idesc, (acc0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                mma_commit(B.empty + 8 * slot);
+                if (++slot == STAGES) { slot = 0; ring_par ^= 1; }
+                if (++kb == kbs) { kb = 0; ++h; }
+            }
+            mma_commit(B.accf + 8 * s);
+        }
+    }
+}
+
+}  // namespace tcmlp

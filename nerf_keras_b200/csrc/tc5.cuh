@@ -62,14 +62,21 @@ __device__ __forceinline__ bool mbar_probe(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded blocking wait; on timeout prints `code` and traps (the launch fails, the GPU survives).
+// try_wait suspends the thread in hardware until the phase completes or a short time limit expires;
+// the timeout bookkeeping runs only once every 4096 retries to keep the retry loop at two instructions.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code = 0) {
     if (mbar_test(bar, parity)) return;
-    const long long t0 = clock64();
+    long long t0 = 0;
+    uint32_t n = 0;
     while (!mbar_test(bar, parity)) {
-        if (clock64() - t0 > TC5_TIMEOUT_CYCLES) {
-            printf("tc5: mbarrier wait timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x,
-                   threadIdx.x, parity);
-            __trap();
+        if ((++n & 4095u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > TC5_TIMEOUT_CYCLES) {
+                printf("tc5: mbarrier wait timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x,
+                       threadIdx.x, parity);
+                __trap();
+            }
         }
     }
 }
@@ -174,6 +181,37 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t col /*0..63*/) {
     uint32_t chunk = (col >> 3) ^ (row & 7);
     return (row >> 3) * 1024 + (row & 7) * 128 + chunk * 16 + (col & 7) * 2;
+}
+
+// ---- packed fp32x2 arithmetic (sm_100) and fused relu+convert ------------------------------------
+__device__ __forceinline__ uint64_t f2_pack(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a);
+    hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// (lo, hi) fp32 -> packed bf16x2 with lo in bits [0,16); RELU clamps negatives to +0 in the same instruction
+template <bool RELU>
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t r;
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -323,6 +323,19 @@ class NeRFTrainer:
                                                     _ptr(out), _stream()), "mlp_forward_rays")
         return out
 
+    def debug_mlp_grads(self, net, ray_origins, ray_directions, t_vals, d_preds):
+        """Diagnostics: (preds, d(sum(preds*d_preds))/d(weights of `net`)) through the tcgen05 forward
+        (saved activations) and backward kernels.  Needs compile() (training workspace)."""
+        o, d, t, dp = _f32(ray_origins), _f32(ray_directions), _f32(t_vals), _f32(d_preds)
+        B, N = t.shape
+        idx = {"coarse": 0, "fine": 1}[net]
+        preds = torch.empty((B, N, 4), device=o.device, dtype=torch.float32)
+        _lib.check(_lib.lib().nerf_debug_mlp_grads(self._ctx.handle, idx, _ptr(o), _ptr(d), _ptr(t), B, N, _ptr(dp),
+                                                   _ptr(preds), _stream()), "debug_mlp_grads")
+        g = self._ctx.grad_tensor()
+        n = self._ctx.n_params
+        return preds, g[idx * n:(idx + 1) * n].clone()
+
     def forward_pass_with_minibatch(self, ray_origins, ray_directions, t_vals, l_xyz=None, l_dir=None, batch_size=512,
                                     training=False, u_pdf=None, precision=None):
         """models.py:178-225 -- ray-tile loop; tiles are `batch_size` rays (capped by the workspace)."""
