@@ -289,6 +289,12 @@ def main():
     clocks = sampler.stop()
     k_ms, k_n = C.c_double(), C.c_int64()
     L.nerf_timing_read(0, C.byref(k_ms), C.byref(k_n))
+    kernel_ms = {"mlp_fwd": k_ms.value / args.steps}
+    for kind, nm in ((1, "mlp_bwd_chain"), (2, "wgrad")):
+        a_ms, a_n = C.c_double(), C.c_int64()
+        L.nerf_timing_read(kind, C.byref(a_ms), C.byref(a_n))
+        if a_n.value:
+            kernel_ms[nm] = a_ms.value / args.steps
     e2e_ms = timed(step_e2e, args.steps)
 
     ms_per_step = total_ms / args.steps
@@ -317,7 +323,8 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
             "samples_per_sec": value * (Nc + Nc + Nf),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "kernel_ms_per_step": kernel_ms}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_arm(args.mode, conf, 3, 1, CPU_SAMPLE_RAYS)

@@ -232,7 +232,8 @@ constexpr int WG_THREADS = 192;            // 4 worker warps + loader warp + MMA
 constexpr int WG_STAGES = 3;
 constexpr int WG_SLOT = 65536;             // A half-blocks (4 x 8 KB) + B half-blocks (4 x 8 KB)
 constexpr int WG_SM_BAR = WG_STAGES * WG_SLOT;
-constexpr int WG_SMEM = WG_SM_BAR + 128 + 1024;
+constexpr int WG_SM_DP = WG_SM_BAR + 128;       // 64 x float4 staged upstream gradients (head-gradient jobs)
+constexpr int WG_SMEM = WG_SM_DP + 1024 + 1024;
 constexpr int WG_NJOBS = 12;
 
 struct WgJob {
@@ -360,12 +361,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
                     s1 += __uint_as_float(w & 0xFFFF0000u);
                 }
             }
+            if (J.extra) {
+                // stage this half-tile's 64 upstream gradients with one coalesced load
+                float4* dp_s = reinterpret_cast<float4*>(smem + WG_SM_DP);
+                named_bar_sync(1, 128);
+                if (tid < 64) {
+                    const int64_t m = ht * 64 + tid;
+                    dp_s[tid] = (m < P.M) ? __ldg(P.dpreds + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                named_bar_sync(1, 128);
+            }
             if (J.extra && blk < J.n_a) {
-                const int64_t m0 = ht * 64;
-#pragma unroll 4
+                const float4* dp_s = reinterpret_cast<const float4*>(smem + WG_SM_DP);
+#pragma unroll 8
                 for (int r = 0; r < 64; ++r) {
-                    const int64_t m = m0 + r;
-                    const float4 dp = (m < P.M) ? __ldg(P.dpreds + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 dp = dp_s[r];
                     const uint32_t addr = a0 + blk * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
                     uint32_t w;
                     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
