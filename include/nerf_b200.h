@@ -143,6 +143,9 @@ int nerf_timing_read(int kind, double* total_ms, int64_t* launches);
  * ctx gradient buffer (nerf_grad_buffer), the other net's half is zero. */
 int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t batch,
                          int num_samples, const float* d_preds, float* preds, void* stream);
+/* Timing experiments only: bit0 skip the CUDA-core side jobs, bit1 skip the MMAs, bit2 skip the final
+ * reduction of the weight-gradient kernel (results are then wrong by construction). */
+int nerf_debug_flags(int flags);
 /* MMA issue-rate probe (cycles for `reps` x 4 back-to-back 128 x n x 16 MMAs). */
 int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycles_dev, void* stream);
 /* Self-test of the tcgen05 building block: C (M,N) fp32 = A (M,K) bf16-rounded x B^T, B (N,K). */

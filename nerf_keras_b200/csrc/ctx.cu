@@ -103,8 +103,11 @@ extern "C" int nerf_create(const nerf_config* cfg, nerf_ctx** out) {
         cudaMemset(ctx->grads, 0, np2 * 4);
         cudaMemset(ctx->adam_m, 0, np2 * 4);
         cudaMemset(ctx->adam_v, 0, np2 * 4);
-        ALLOC(ctx->tr_dpred_c, R * Nc * 16);
-        ALLOC(ctx->tr_dpred_f, R * Na * 16);
+        // padded to the 256-row tile pairs the kernels read; the pad stays zero (no gradient from padding rows)
+        ALLOC(ctx->tr_dpred_c, (R * Nc + 512) * 16);
+        ALLOC(ctx->tr_dpred_f, (R * Na + 512) * 16);
+        cudaMemset(ctx->tr_dpred_c, 0, (R * Nc + 512) * 16);
+        cudaMemset(ctx->tr_dpred_f, 0, (R * Na + 512) * 16);
         ALLOC(ctx->tr_drgb_c, R * 12);
         ALLOC(ctx->tr_drgb_f, R * 12);
     }
@@ -310,5 +313,7 @@ extern "C" int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, cons
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = tc_forward_rays(ctx, net, o, d, t, batch, num_samples, preds, true, st))) return rc;
     NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * ctx->n_params * 4, st));
-    return tc_backward(ctx, net, o, d, t, batch, num_samples, d_preds, st);
+    float* dp = net == 0 ? ctx->tr_dpred_c : ctx->tr_dpred_f;   // tile-padded staging buffer
+    NERF_CUDA(cudaMemcpyAsync(dp, d_preds, (size_t)batch * num_samples * 16, cudaMemcpyDeviceToDevice, st));
+    return tc_backward(ctx, net, o, d, t, batch, num_samples, dp, st);
 }

@@ -232,23 +232,21 @@ constexpr int WG_THREADS = 192;            // 4 worker warps + loader warp + MMA
 constexpr int WG_STAGES = 3;
 constexpr int WG_SLOT = 65536;             // A half-blocks (4 x 8 KB) + B half-blocks (4 x 8 KB)
 constexpr int WG_SM_BAR = WG_STAGES * WG_SLOT;
-constexpr int WG_SM_DP = WG_SM_BAR + 128;       // 64 x float4 staged upstream gradients (head-gradient jobs)
-constexpr int WG_SMEM = WG_SM_DP + 1024 + 1024;
-constexpr int WG_NJOBS = 12;
+constexpr int WG_SMEM = WG_SM_BAR + 128 + 1024;
+constexpr int WG_NJOBS = 11;
 
 struct WgJob {
     int64_t a_off;       // byte offset of the X image inside a saved-activation tile
     int64_t b_off;       // byte offset of the dZ image inside a dZ tile
     int n_a;             // 64-feature blocks of X: 1, 2 or 4
-    int n_b;             // 64-feature blocks of dZ: 2 or 4   (0: no MMA, CUDA-core job)
+    int n_b;             // 64-feature blocks of dZ: 2 or 4
     int64_t w_dst;       // float offset (in the grads blob of this net) of dW row 0
     int ld;              // fan_out
     int rows;            // valid rows of dW produced by this job
     int64_t bias_dst;    // float offset of the bias gradient (column sums of dZ), or -1
-    int extra;           // 0 none, 1 sigma head (X weighted by dpreds.w), 2 rgb head (X weighted by dpreds.xyz)
-    int64_t extra_w, extra_b;
 };
 struct WgParams {
+    int debug;              // bit0: skip side jobs, bit1: skip MMAs, bit2: skip final reduction (timing experiments)
     WgJob jobs[WG_NJOBS];
     const uint8_t* act_save;
     const uint8_t* dz_save;
@@ -292,7 +290,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     const int64_t ht1 = (ht0 + per < P.n_half_tiles) ? ht0 + per : P.n_half_tiles;
     const int n_ht = (ht1 > ht0) ? (int)(ht1 - ht0) : 0;
     const int n_a_load = (J.n_a == 1) ? 2 : J.n_a;   // a single 64-feature block is loaded twice (M = 128 MMA)
-    const int n_mh = (J.n_b == 0) ? 0 : ((J.n_a == 4) ? 2 : 1);
+    const int n_mh = (J.n_a == 4) ? 2 : 1;
 
     if (warp == 4) {
         // ===================== loader =====================
@@ -318,14 +316,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 64 * (J.n_b ? J.n_b : 2), 1, 1);
+            const uint32_t idesc = make_idesc_bf16(128, 64 * J.n_b, 1, 1);
             int slot = 0;
             uint32_t par = 0;
             for (int i = 0; i < n_ht; ++i) {
                 mbar_wait(bar_full + 8 * slot, par, 12);
                 tc_fence_after();
                 const uint32_t a0 = base + slot * WG_SLOT, b0 = a0 + 32768;
-                for (int mh = 0; mh < n_mh; ++mh) {
+                for (int mh = 0; mh < ((P.debug & 2) ? 0 : n_mh); ++mh) {
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         const uint64_t ad = make_sdesc_sw128(a0 + mh * 16384 + k4 * 2048, 8192, 1024);
@@ -340,53 +338,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
         }
     } else {
         // ===================== side jobs + final reduction =====================
-        const int tid = threadIdx.x;                 // 0..127
-        float s0 = 0.f, s1 = 0.f;                    // bias: column sums of dZ (cols 2 tid, 2 tid + 1)
-        float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; // head gradients for features 2 tid, 2 tid + 1
-        float eb[3] = {0.f, 0.f, 0.f};
-        const int blk = tid >> 5, wd = tid & 31;     // 64-feature block and 4-byte word inside the 128 B row
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias: partial column sums (8 columns per lane)
         int slot = 0;
         uint32_t par = 0;
         for (int i = 0; i < n_ht; ++i) {
-            const int64_t ht = ht0 + i;
             mbar_wait(bar_full + 8 * slot, par, 13);
-            const uint32_t a0 = base + slot * WG_SLOT, b0 = a0 + 32768;
-            if (J.bias_dst >= 0 && blk < J.n_b) {
-#pragma unroll 8
-                for (int r = 0; r < 64; ++r) {
-                    const uint32_t addr = b0 + blk * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
-                    uint32_t w;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
-                    s0 += __uint_as_float(w << 16);
-                    s1 += __uint_as_float(w & 0xFFFF0000u);
-                }
-            }
-            if (J.extra) {
-                // stage this half-tile's 64 upstream gradients with one coalesced load
-                float4* dp_s = reinterpret_cast<float4*>(smem + WG_SM_DP);
-                named_bar_sync(1, 128);
-                if (tid < 64) {
-                    const int64_t m = ht * 64 + tid;
-                    dp_s[tid] = (m < P.M) ? __ldg(P.dpreds + m) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                named_bar_sync(1, 128);
-            }
-            if (J.extra && blk < J.n_a) {
-                const float4* dp_s = reinterpret_cast<const float4*>(smem + WG_SM_DP);
-#pragma unroll 8
-                for (int r = 0; r < 64; ++r) {
-                    const float4 dp = dp_s[r];
-                    const uint32_t addr = a0 + blk * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
-                    uint32_t w;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr));
-                    const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xFFFF0000u);
-                    if (J.extra == 1) {
-                        e[0] = fmaf(x0, dp.w, e[0]); e[1] = fmaf(x1, dp.w, e[1]);
-                        if (tid == 0) eb[0] += dp.w;
-                    } else {
-                        e[0] = fmaf(x0, dp.x, e[0]); e[1] = fmaf(x0, dp.y, e[1]); e[2] = fmaf(x0, dp.z, e[2]);
-                        e[3] = fmaf(x1, dp.x, e[3]); e[4] = fmaf(x1, dp.y, e[4]); e[5] = fmaf(x1, dp.z, e[5]);
-                        if (tid == 0) { eb[0] += dp.x; eb[1] += dp.y; eb[2] += dp.z; }
+            const uint32_t b0 = base + slot * WG_SLOT + 32768;
+            if (J.bias_dst >= 0 && !(P.debug & (1 | 8))) {
+                // column sums of the dZ half-tile: lane <-> (64-col block, 16-byte chunk), each warp takes 16 rows
+                const int cb = lane >> 3, ch = lane & 7;
+                if (cb < J.n_b) {
+#pragma unroll 4
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const int r = warp * 16 + rr;
+                        const uint32_t addr = b0 + cb * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
+                        uint32_t w0, w1, w2, w3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
+                        cs[0] += __uint_as_float(w0 << 16); cs[1] += __uint_as_float(w0 & 0xFFFF0000u);
+                        cs[2] += __uint_as_float(w1 << 16); cs[3] += __uint_as_float(w1 & 0xFFFF0000u);
+                        cs[4] += __uint_as_float(w2 << 16); cs[5] += __uint_as_float(w2 & 0xFFFF0000u);
+                        cs[6] += __uint_as_float(w3 << 16); cs[7] += __uint_as_float(w3 & 0xFFFF0000u);
                     }
                 }
             }
@@ -394,21 +365,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
             if (++slot == WG_STAGES) { slot = 0; par ^= 1; }
         }
         if (n_ht > 0) {
-            if (J.bias_dst >= 0 && blk < J.n_b) {
-                atomicAdd(P.grads + J.bias_dst + 2 * tid, s0);
-                atomicAdd(P.grads + J.bias_dst + 2 * tid + 1, s1);
-            }
-            if (J.extra == 1) {          // sigma head: W (256,1), b (1)
-                atomicAdd(P.grads + J.extra_w + 2 * tid, e[0]);
-                atomicAdd(P.grads + J.extra_w + 2 * tid + 1, e[1]);
-                if (tid == 0) atomicAdd(P.grads + J.extra_b, eb[0]);
-            } else if (J.extra == 2 && blk < J.n_a) {   // rgb head: W (128,3), b (3)
+            if (J.bias_dst >= 0 && (lane >> 3) < J.n_b) {
 #pragma unroll
-                for (int q = 0; q < 6; ++q) atomicAdd(P.grads + J.extra_w + (2 * tid) * 3 + q, e[q]);
-                if (tid == 0)
-                    for (int q = 0; q < 3; ++q) atomicAdd(P.grads + J.extra_b + q, eb[q]);
+                for (int q = 0; q < 8; ++q) atomicAdd(P.grads + J.bias_dst + (lane >> 3) * 64 + (lane & 7) * 8 + q, cs[q]);
             }
-            if (n_mh > 0) {
+            if (n_mh > 0 && !(P.debug & 4)) {
                 mbar_wait(bar_done, 0, 14);
                 tc_fence_after();
                 const int N = 64 * J.n_b;
@@ -441,47 +402,119 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2b. sigma / rgb head gradients (CUDA cores): dW_sigma = h8^T dsigma, dW_rgb = hd^T d_rgb, and their biases.
+// thread <-> (column pair, row half); reads one 4-byte word per row from the saved h8 / hd images.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_grad_kernel(const uint8_t* __restrict__ act_save,
+                                                        const float4* __restrict__ dpreds /* tile padded */, int64_t n_tiles,
+                                                        float* __restrict__ g_wsig, float* __restrict__ g_bsig,
+                                                        float* __restrict__ g_wrgb, float* __restrict__ g_brgb) {
+    const int cp = threadIdx.x & 127, rh = threadIdx.x >> 7;
+    const int blk = cp >> 5, wd = cp & 31;
+    float s0 = 0.f, s1 = 0.f, bs = 0.f;
+    float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, eb[3] = {0.f, 0.f, 0.f};
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint8_t* h8 = act_save + tile * SAVE_TILE_BYTES + SAVE_H + 7 * 65536 + blk * 16384;
+        const uint8_t* hd = act_save + tile * SAVE_TILE_BYTES + SAVE_HD + blk * 16384;
+        const float4* dp = dpreds + tile * TILE_M;
+#pragma unroll 8
+        for (int rr = 0; rr < 64; ++rr) {
+            const int r = rh * 64 + rr;
+            const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
+            const float4 g = __ldg(dp + r);
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(h8 + off));
+            s0 = fmaf(__uint_as_float(w << 16), g.w, s0);
+            s1 = fmaf(__uint_as_float(w & 0xFFFF0000u), g.w, s1);
+            if (cp == 0) { bs += g.w; eb[0] += g.x; eb[1] += g.y; eb[2] += g.z; }
+            if (blk < 2) {
+                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(hd + off));
+                const float x0 = __uint_as_float(v << 16), x1 = __uint_as_float(v & 0xFFFF0000u);
+                e[0] = fmaf(x0, g.x, e[0]); e[1] = fmaf(x0, g.y, e[1]); e[2] = fmaf(x0, g.z, e[2]);
+                e[3] = fmaf(x1, g.x, e[3]); e[4] = fmaf(x1, g.y, e[4]); e[5] = fmaf(x1, g.z, e[5]);
+            }
+        }
+    }
+    atomicAdd(g_wsig + 2 * cp, s0);
+    atomicAdd(g_wsig + 2 * cp + 1, s1);
+    if (blk < 2) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) atomicAdd(g_wrgb + (2 * cp) * 3 + q, e[q]);
+    }
+    if (cp == 0) {
+        atomicAdd(g_bsig, bs);
+        for (int q = 0; q < 3; ++q) atomicAdd(g_brgb + q, eb[q]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. direction rows of Wddir: dW[256+k][c] = sum_rays enc_dir(ray)[k] * sum_{samples of ray} dZ_ddir[m][c]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) ddir_dirgrad_kernel(const float* __restrict__ d, int64_t rays, int N,
-                                                           const uint8_t* __restrict__ dz_save, float* __restrict__ g_wddir) {
-    __shared__ float enc[ENC_D];
-    const int c = threadIdx.x;
-    float acc[ENC_D];
+// thread <-> (column pair, row half) of a 128-row tile; rows of one ray are contiguous, so each thread keeps a running
+// per-ray sum and folds it into its 27 x 2 accumulators when the ray changes.
+constexpr int DG_MAXR = 66;   // rays touched by one 128-row tile (N >= 2)
+__global__ void __launch_bounds__(128) ddir_dirgrad_kernel(const float* __restrict__ d, int N, int64_t M,
+                                                           const uint8_t* __restrict__ dz_save, int64_t n_tiles,
+                                                           float* __restrict__ g_wddir) {
+    __shared__ float enc_s[DG_MAXR][ENC_D];
+    const int cp = threadIdx.x & 63, rh = threadIdx.x >> 6;
+    const int blk = cp >> 5, wd = cp & 31;
+    float acc[ENC_D][2];
 #pragma unroll
-    for (int k = 0; k < ENC_D; ++k) acc[k] = 0.f;
-    for (int64_t ray = blockIdx.x; ray < rays; ray += gridDim.x) {
-        if (c < ENC_D) {
+    for (int k = 0; k < ENC_D; ++k) acc[k][0] = acc[k][1] = 0.f;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t m_first = tile * TILE_M;
+        if (m_first >= M) break;
+        const int64_t m_last = (m_first + TILE_M - 1 < M - 1) ? m_first + TILE_M - 1 : M - 1;
+        const int64_t ray0 = m_first / N;
+        const int nr = (int)(m_last / N - ray0) + 1;
+        for (int i = threadIdx.x; i < nr * ENC_D; i += blockDim.x) {
+            const int rl = i / ENC_D, c = i - rl * ENC_D;
+            const int64_t ray = ray0 + rl;
             float v;
             if (c < 3) v = d[ray * 3 + c];
             else {
-                int q = c - 3, i = q / 6, r = q - i * 6, comp = r % 3;
-                float arg = __fmul_rn(exp2f((float)i), d[ray * 3 + comp]);
-                v = (r >= 3) ? cosf(arg) : sinf(arg);
+                int q = c - 3, oct = q / 6, r6 = q - oct * 6, comp = r6 % 3;
+                float arg = __fmul_rn(exp2f((float)oct), d[ray * 3 + comp]);
+                v = (r6 >= 3) ? cosf(arg) : sinf(arg);
             }
-            enc[c] = v;
+            enc_s[rl][c] = v;
         }
         __syncthreads();
-        float s = 0.f;
-        for (int n = 0; n < N; ++n) {
-            const int64_t m = ray * N + n;
-            const int64_t tile = m >> 7;
-            const int r = (int)(m & 127);
-            const uint8_t* p = dz_save + tile * DZ_TILE_BYTES + DZ_DDIR + (c >> 6) * 16384 + sw128_offset(r, c & 63);
-            s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
-        }
+        const uint8_t* img = dz_save + tile * DZ_TILE_BYTES + DZ_DDIR + blk * 16384;
+        int64_t m = m_first + rh * 64;
+        int rl = (int)(m / N - ray0);
+        int n_in = (int)(m % N);
+        float s0 = 0.f, s1 = 0.f;
+        for (int rr = 0; rr < 64 && m < M; ++rr, ++m) {
+            const int r = rh * 64 + rr;
+            const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
+            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(img + off));
+            s0 += __uint_as_float(w << 16);
+            s1 += __uint_as_float(w & 0xFFFF0000u);
+            if (++n_in == N || rr == 63 || m + 1 >= M) {
 #pragma unroll
-        for (int k = 0; k < ENC_D; ++k) acc[k] = fmaf(enc[k], s, acc[k]);
+                for (int k = 0; k < ENC_D; ++k) {
+                    acc[k][0] = fmaf(enc_s[rl][k], s0, acc[k][0]);
+                    acc[k][1] = fmaf(enc_s[rl][k], s1, acc[k][1]);
+                }
+                s0 = s1 = 0.f;
+                if (n_in == N) { n_in = 0; ++rl; }
+            }
+        }
         __syncthreads();
     }
 #pragma unroll
-    for (int k = 0; k < ENC_D; ++k) atomicAdd(g_wddir + (int64_t)(H + k) * (H / 2) + c, acc[k]);
+    for (int k = 0; k < ENC_D; ++k) {
+        atomicAdd(g_wddir + (int64_t)(H + k) * (H / 2) + 2 * cp, acc[k][0]);
+        atomicAdd(g_wddir + (int64_t)(H + k) * (H / 2) + 2 * cp + 1, acc[k][1]);
+    }
 }
 
 }  // namespace
 
 namespace nerf {
 int64_t tc_save_bytes_per_tile();
+int g_wg_debug = 0;
 
 int tc_train_alloc(nerf_ctx* ctx) {
     const nerf_config& c = ctx->cfg;
@@ -504,6 +537,9 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     (void)o; (void)t;
     const int64_t M = B * (int64_t)N;
     const int64_t n_pairs = ceil_div(M, 2 * TILE_M);
+    // d_preds is the ctx-owned, tile-padded buffer: rows [M, padded) must carry zero gradient
+    if (n_pairs * 2 * TILE_M > M)
+        NERF_CUDA(cudaMemsetAsync(const_cast<float*>(d_preds) + M * 4, 0, (size_t)(n_pairs * 2 * TILE_M - M) * 16, st));
     BlobOffsets off = make_offsets(ctx);
     const float* blob = ctx->params + (int64_t)net * ctx->n_params;
     float* grads = ctx->grads + (int64_t)net * ctx->n_params;
@@ -526,26 +562,24 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     NERF_LAUNCHED();
 
     WgParams W;
+    W.debug = g_wg_debug;
     W.act_save = reinterpret_cast<const uint8_t*>(ctx->act_save[net]);
     W.dz_save = reinterpret_cast<const uint8_t*>(ctx->dz_save[net]);
     W.dpreds = reinterpret_cast<const float4*>(d_preds);
     W.M = M;
     W.n_half_tiles = n_pairs * 4;
     W.grads = grads;
-    auto job = [&](int i, int64_t a_off, int n_a, int64_t b_off, int n_b, int64_t w_dst, int ld, int rows, int64_t bias,
-                   int extra, int64_t ew, int64_t eb) {
-        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, bias, extra, ew, eb};
+    auto job = [&](int i, int64_t a_off, int n_a, int64_t b_off, int n_b, int64_t w_dst, int ld, int rows, int64_t bias) {
+        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, bias};
     };
-    job(0, SAVE_ENC, 1, DZ_Z, 4, off.w[0], H, ENC_X, off.b[0], 0, 0, 0);
-    for (int l = 1; l <= 4; ++l)
-        job(l, SAVE_H + 65536 * (l - 1), 4, DZ_Z + 65536 * l, 4, off.w[l], H, H, off.b[l], 0, 0, 0);
-    job(5, SAVE_H + 65536 * 4, 4, DZ_Z + 65536 * 5, 4, off.w[5], H, H, off.b[5], 0, 0, 0);
-    job(6, SAVE_ENC, 1, DZ_Z + 65536 * 5, 4, off.w[5] + (int64_t)H * H, H, ENC_X, -1, 0, 0, 0);
-    job(7, SAVE_H + 65536 * 5, 4, DZ_Z + 65536 * 6, 4, off.w[6], H, H, off.b[6], 0, 0, 0);
-    job(8, SAVE_H + 65536 * 6, 4, DZ_Z + 65536 * 7, 4, off.w[7], H, H, off.b[7], 0, 0, 0);
-    job(9, SAVE_H + 65536 * 7, 4, DZ_FEAT, 4, off.w[9], H, H, off.b[9], 1, off.w[8], off.b[8]);
-    job(10, SAVE_FEAT, 4, DZ_DDIR, 2, off.w[10], H / 2, H, off.b[10], 0, 0, 0);
-    job(11, SAVE_HD, 2, 0, 0, 0, 0, 0, -1, 2, off.w[11], off.b[11]);
+    job(0, SAVE_ENC, 1, DZ_Z, 4, off.w[0], H, ENC_X, off.b[0]);
+    for (int l = 1; l <= 4; ++l) job(l, SAVE_H + 65536 * (l - 1), 4, DZ_Z + 65536 * l, 4, off.w[l], H, H, off.b[l]);
+    job(5, SAVE_H + 65536 * 4, 4, DZ_Z + 65536 * 5, 4, off.w[5], H, H, off.b[5]);
+    job(6, SAVE_ENC, 1, DZ_Z + 65536 * 5, 4, off.w[5] + (int64_t)H * H, H, ENC_X, -1);
+    job(7, SAVE_H + 65536 * 5, 4, DZ_Z + 65536 * 6, 4, off.w[6], H, H, off.b[6]);
+    job(8, SAVE_H + 65536 * 6, 4, DZ_Z + 65536 * 7, 4, off.w[7], H, H, off.b[7]);
+    job(9, SAVE_H + 65536 * 7, 4, DZ_FEAT, 4, off.w[9], H, H, off.b[9]);
+    job(10, SAVE_FEAT, 4, DZ_DDIR, 2, off.w[10], H / 2, H, off.b[10]);
     int slabs = num_sms() / WG_NJOBS;
     if (slabs < 1) slabs = 1;
     if (slabs > W.n_half_tiles) slabs = (int)W.n_half_tiles;
@@ -554,9 +588,23 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     timing_end(2, st);
     NERF_LAUNCHED();
 
-    ddir_dirgrad_kernel<<<(unsigned)(B < 2 * num_sms() ? B : 2 * num_sms()), 128, 0, st>>>(
-        d, B, N, reinterpret_cast<const uint8_t*>(ctx->dz_save[net]), grads + off.w[10]);
+    {
+        const int64_t n_tiles = n_pairs * 2;
+        const int grid_h = (int)(n_tiles < 4 * num_sms() ? n_tiles : 4 * num_sms());
+        head_grad_kernel<<<grid_h, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(ctx->act_save[net]),
+                                                 reinterpret_cast<const float4*>(d_preds), n_tiles, grads + off.w[8],
+                                                 grads + off.b[8], grads + off.w[11], grads + off.b[11]);
+        NERF_LAUNCHED();
+    }
+    {
+        const int64_t n_tiles = n_pairs * 2;
+        const int grid_d = (int)(n_tiles < 4 * num_sms() ? n_tiles : 4 * num_sms());
+        ddir_dirgrad_kernel<<<grid_d, 128, 0, st>>>(d, N, M, reinterpret_cast<const uint8_t*>(ctx->dz_save[net]), n_tiles,
+                                                    grads + off.w[10]);
+    }
     NERF_LAUNCHED();
     return NERF_OK;
 }
 }  // namespace nerf
+
+extern "C" int nerf_debug_flags(int flags) { nerf::g_wg_debug = flags; return NERF_OK; }
