@@ -8,7 +8,10 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 OBJS=()
 for f in ops mlp_fp32 ctx mlp_tc mlp_tc_bwd; do
   src="$HERE/$f.cu"; obj="$HERE/$f.o"
-  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/tc5.cuh" -nt "$obj" || "$HERE/ctx.cuh" -nt "$obj" || "$HERE/common.cuh" -nt "$obj" || "$HERE/../../include/nerf_b200.h" -nt "$obj" ]]; then
+  stale=0
+  [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/../../include/nerf_b200.h" -nt "$obj" ]] && stale=1
+  for hdr in "$HERE"/*.cuh; do [[ "$hdr" -nt "$obj" ]] && stale=1; done
+  if [[ $stale -eq 1 ]]; then
     "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj" &
   fi
   OBJS+=("$obj")

@@ -12,8 +12,10 @@
 //     tile is consumed as an MN-major operand (features along M/N, samples along K) without any
 //     transpose.  Accumulators stay in TMEM for a CTA's whole slab of samples; bias gradients (column
 //     sums of dZ) and the tiny sigma / rgb head gradients are CUDA-core side jobs on the same tiles.
-//  3. ddir_dirgrad_kernel -- gradient of the direction rows of Wddir (the per-ray bias hoisted out of
-//     the forward kernel): per-ray sums of dZ_ddir times the ray's direction encoding.
+//     The sigma / rgb heads and the direction rows of Wddir are three more jobs of the same kernel: the
+//     chain kernel emits a [d rgb, d sigma] "head" dZ image, and
+//  3. dir_image_kernel writes the per-sample direction-encoding images (the forward kernel hoists that
+//     product into a per-ray bias, so the operand has to be materialised for the backward).
 #include "common.cuh"
 #include "ctx.cuh"
 #include "mlp_tc_common.cuh"
@@ -184,10 +186,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
                                         pk[4 * c + 3]);
                 }
             }
+            // head image (K-block 2 is free until the first epilogue): [d r, d g, d b, d sigma, 0 ...]
+            store_row_chunk(act_base, 2, row, 0, pack_bf16x2(dp.x, dp.y), pack_bf16x2(dp.z, dp.w), 0u, 0u);
+#pragma unroll
+            for (int c = 1; c < 8; ++c) store_row_chunk(act_base, 2, row, c, 0u, 0u, 0u, 0u);
             tc_fence_before();
             fence_proxy_async_smem();
             named_bar_sync(1 + s, TILE_M);
-            if (elected) { bulk_s2g(dz_tile + DZ_DDIR, act_base, 32768); bulk_commit(); }
+            if (elected) {
+                bulk_s2g(dz_tile + DZ_DDIR, act_base, 32768);
+                bulk_s2g(dz_tile + DZ_HEAD, act_base + 2 * 16384, 16384);
+                bulk_commit();
+            }
             mbar_arrive(B.actr + 8 * s);
 
             for (int ph = 0; ph < B_PHASES; ++ph) {
@@ -233,7 +243,7 @@ constexpr int WG_STAGES = 3;
 constexpr int WG_SLOT = 65536;             // A half-blocks (4 x 8 KB) + B half-blocks (4 x 8 KB)
 constexpr int WG_SM_BAR = WG_STAGES * WG_SLOT;
 constexpr int WG_SMEM = WG_SM_BAR + 128 + 1024;
-constexpr int WG_NJOBS = 11;
+constexpr int WG_NJOBS = 14;
 
 struct WgJob {
     int64_t a_off;       // byte offset of the X image inside a saved-activation tile
@@ -243,6 +253,7 @@ struct WgJob {
     int64_t w_dst;       // float offset (in the grads blob of this net) of dW row 0
     int ld;              // fan_out
     int rows;            // valid rows of dW produced by this job
+    int col_lo, col_hi;  // valid columns [col_lo, col_hi) of the accumulator that are written to dW
     int64_t bias_dst;    // float offset of the bias gradient (column sums of dZ), or -1
 };
 struct WgParams {
@@ -381,14 +392,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
                         tmem_ld_wait();
                         if (r < J.rows) {
                             float* dst = P.grads + J.w_dst + (int64_t)r * J.ld + cg * 32;
-                            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                            const bool full = (J.col_lo <= cg * 32) && (J.col_hi >= cg * 32 + 32);
+                            if (full && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
                                 for (int q = 0; q < 8; ++q)
                                     red_add_v4(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                                __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                            } else {   // layers after the 257-float sigma block are not 16-byte aligned in the blob
+                            } else {   // partial column window, or a layer that is not 16-byte aligned in the blob
 #pragma unroll
-                                for (int q = 0; q < 32; ++q) atomicAdd(dst + q, __uint_as_float(v[q]));
+                                for (int q = 0; q < 32; ++q)
+                                    if (cg * 32 + q >= J.col_lo && cg * 32 + q < J.col_hi) atomicAdd(dst + q, __uint_as_float(v[q]));
                             }
                         }
                     }
@@ -402,111 +415,56 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2b. sigma / rgb head gradients (CUDA cores): dW_sigma = h8^T dsigma, dW_rgb = hd^T d_rgb, and their biases.
-// thread <-> (column pair, row half); reads one 4-byte word per row from the saved h8 / hd images.
+// 3. per-sample direction-encoding images for the direction rows of Wddir (models.py:48-54): the forward
+// kernel hoists that product into a per-ray bias, the backward wants it as a GEMM operand again.
+// One warp per ray writes the ray's N rows ([27 values | zeros], 128 bytes each) into the tiles' images.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) head_grad_kernel(const uint8_t* __restrict__ act_save,
-                                                        const float4* __restrict__ dpreds /* tile padded */, int64_t n_tiles,
-                                                        float* __restrict__ g_wsig, float* __restrict__ g_bsig,
-                                                        float* __restrict__ g_wrgb, float* __restrict__ g_brgb) {
-    const int cp = threadIdx.x & 127, rh = threadIdx.x >> 7;
-    const int blk = cp >> 5, wd = cp & 31;
-    float s0 = 0.f, s1 = 0.f, bs = 0.f;
-    float e[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, eb[3] = {0.f, 0.f, 0.f};
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint8_t* h8 = act_save + tile * SAVE_TILE_BYTES + SAVE_H + 7 * 65536 + blk * 16384;
-        const uint8_t* hd = act_save + tile * SAVE_TILE_BYTES + SAVE_HD + blk * 16384;
-        const float4* dp = dpreds + tile * TILE_M;
-#pragma unroll 8
-        for (int rr = 0; rr < 64; ++rr) {
-            const int r = rh * 64 + rr;
-            const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
-            const float4 g = __ldg(dp + r);
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(h8 + off));
-            s0 = fmaf(__uint_as_float(w << 16), g.w, s0);
-            s1 = fmaf(__uint_as_float(w & 0xFFFF0000u), g.w, s1);
-            if (cp == 0) { bs += g.w; eb[0] += g.x; eb[1] += g.y; eb[2] += g.z; }
-            if (blk < 2) {
-                const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(hd + off));
-                const float x0 = __uint_as_float(v << 16), x1 = __uint_as_float(v & 0xFFFF0000u);
-                e[0] = fmaf(x0, g.x, e[0]); e[1] = fmaf(x0, g.y, e[1]); e[2] = fmaf(x0, g.z, e[2]);
-                e[3] = fmaf(x1, g.x, e[3]); e[4] = fmaf(x1, g.y, e[4]); e[5] = fmaf(x1, g.z, e[5]);
-            }
-        }
-    }
-    atomicAdd(g_wsig + 2 * cp, s0);
-    atomicAdd(g_wsig + 2 * cp + 1, s1);
-    if (blk < 2) {
+__global__ void __launch_bounds__(128) dir_image_kernel(const float* __restrict__ d, int64_t rays, int N,
+                                                        uint8_t* __restrict__ act_save) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < rays; ray += warps_total) {
+        // lane <-> channel pair (2 lane, 2 lane + 1) of the 64-wide row
+        float v[2];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) atomicAdd(g_wrgb + (2 * cp) * 3 + q, e[q]);
-    }
-    if (cp == 0) {
-        atomicAdd(g_bsig, bs);
-        for (int q = 0; q < 3; ++q) atomicAdd(g_brgb + q, eb[q]);
+        for (int q = 0; q < 2; ++q) {
+            const int c = 2 * lane + q;
+            float x = 0.f;
+            if (c < 3) x = d[ray * 3 + c];
+            else if (c < ENC_D) {
+                int qq = c - 3, oct = qq / 6, r6 = qq - oct * 6, comp = r6 % 3;
+                float arg = __fmul_rn(exp2f((float)oct), d[ray * 3 + comp]);
+                x = (r6 >= 3) ? cosf(arg) : sinf(arg);
+            }
+            v[q] = x;
+        }
+        const uint32_t w = pack_bf16x2(v[0], v[1]);
+        for (int n = 0; n < N; ++n) {
+            const int64_t m = ray * N + n;
+            const int64_t tile = m >> 7;
+            const int r = (int)(m & 127);
+            uint8_t* p = act_save + tile * SAVE_TILE_BYTES + SAVE_DIR + (r >> 3) * 1024 + (r & 7) * 128 +
+                         ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4;
+            *reinterpret_cast<uint32_t*>(p) = w;
+        }
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// 3. direction rows of Wddir: dW[256+k][c] = sum_rays enc_dir(ray)[k] * sum_{samples of ray} dZ_ddir[m][c]
-// ------------------------------------------------------------------------------------------------
-// thread <-> (column pair, row half) of a 128-row tile; rows of one ray are contiguous, so each thread keeps a running
-// per-ray sum and folds it into its 27 x 2 accumulators when the ray changes.
-constexpr int DG_MAXR = 66;   // rays touched by one 128-row tile (N >= 2)
-__global__ void __launch_bounds__(128) ddir_dirgrad_kernel(const float* __restrict__ d, int N, int64_t M,
-                                                           const uint8_t* __restrict__ dz_save, int64_t n_tiles,
-                                                           float* __restrict__ g_wddir) {
-    __shared__ float enc_s[DG_MAXR][ENC_D];
-    const int cp = threadIdx.x & 63, rh = threadIdx.x >> 6;
-    const int blk = cp >> 5, wd = cp & 31;
-    float acc[ENC_D][2];
-#pragma unroll
-    for (int k = 0; k < ENC_D; ++k) acc[k][0] = acc[k][1] = 0.f;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t m_first = tile * TILE_M;
-        if (m_first >= M) break;
-        const int64_t m_last = (m_first + TILE_M - 1 < M - 1) ? m_first + TILE_M - 1 : M - 1;
-        const int64_t ray0 = m_first / N;
-        const int nr = (int)(m_last / N - ray0) + 1;
-        for (int i = threadIdx.x; i < nr * ENC_D; i += blockDim.x) {
-            const int rl = i / ENC_D, c = i - rl * ENC_D;
-            const int64_t ray = ray0 + rl;
-            float v;
-            if (c < 3) v = d[ray * 3 + c];
-            else {
-                int q = c - 3, oct = q / 6, r6 = q - oct * 6, comp = r6 % 3;
-                float arg = __fmul_rn(exp2f((float)oct), d[ray * 3 + comp]);
-                v = (r6 >= 3) ? cosf(arg) : sinf(arg);
-            }
-            enc_s[rl][c] = v;
-        }
-        __syncthreads();
-        const uint8_t* img = dz_save + tile * DZ_TILE_BYTES + DZ_DDIR + blk * 16384;
-        int64_t m = m_first + rh * 64;
-        int rl = (int)(m / N - ray0);
-        int n_in = (int)(m % N);
-        float s0 = 0.f, s1 = 0.f;
-        for (int rr = 0; rr < 64 && m < M; ++rr, ++m) {
-            const int r = rh * 64 + rr;
-            const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((((wd >> 2) ^ (r & 7))) << 4) + (wd & 3) * 4;
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(img + off));
-            s0 += __uint_as_float(w << 16);
-            s1 += __uint_as_float(w & 0xFFFF0000u);
-            if (++n_in == N || rr == 63 || m + 1 >= M) {
-#pragma unroll
-                for (int k = 0; k < ENC_D; ++k) {
-                    acc[k][0] = fmaf(enc_s[rl][k], s0, acc[k][0]);
-                    acc[k][1] = fmaf(enc_s[rl][k], s1, acc[k][1]);
-                }
-                s0 = s1 = 0.f;
-                if (n_in == N) { n_in = 0; ++rl; }
-            }
-        }
-        __syncthreads();
+// bias gradients of the two heads: b_rgb = sum d rgb_raw, b_sigma = sum d sigma_raw  (float4 grid-stride reduce)
+__global__ void __launch_bounds__(256) head_bias_kernel(const float4* __restrict__ dpreds, int64_t M,
+                                                        float* __restrict__ g_brgb, float* __restrict__ g_bsig) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = dpreds[i];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
     }
 #pragma unroll
-    for (int k = 0; k < ENC_D; ++k) {
-        atomicAdd(g_wddir + (int64_t)(H + k) * (H / 2) + 2 * cp, acc[k][0]);
-        atomicAdd(g_wddir + (int64_t)(H + k) * (H / 2) + 2 * cp + 1, acc[k][1]);
+    for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o); a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, o); a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(g_brgb, a.x); atomicAdd(g_brgb + 1, a.y); atomicAdd(g_brgb + 2, a.z); atomicAdd(g_bsig, a.w);
     }
 }
 
@@ -522,6 +480,8 @@ int tc_train_alloc(nerf_ctx* ctx) {
                               ceil_div((int64_t)c.max_rays * (c.ns_coarse + c.ns_fine), 256) * 2};
     for (int net = 0; net < 2; ++net) {
         NERF_CUDA(cudaMalloc((void**)&ctx->act_save[net], (size_t)(tiles[net] * SAVE_TILE_BYTES)));
+        // rows of a ragged last tile are read by the weight-gradient GEMMs (times zero gradients): keep them finite
+        NERF_CUDA(cudaMemset(ctx->act_save[net], 0, (size_t)(tiles[net] * SAVE_TILE_BYTES)));
         NERF_CUDA(cudaMalloc((void**)&ctx->dz_save[net], (size_t)(tiles[net] * DZ_TILE_BYTES)));
         NERF_CUDA(cudaMalloc((void**)&ctx->mask_save[net], (size_t)(tiles[net] * MASK_TILE_BYTES)));
         NERF_CUDA(cudaMalloc((void**)&ctx->w_bwd[net], (size_t)B_CHUNKS * CHUNK_BYTES));
@@ -569,39 +529,36 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     W.M = M;
     W.n_half_tiles = n_pairs * 4;
     W.grads = grads;
-    auto job = [&](int i, int64_t a_off, int n_a, int64_t b_off, int n_b, int64_t w_dst, int ld, int rows, int64_t bias) {
-        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, bias};
+    auto job = [&](int i, int64_t a_off, int n_a, int64_t b_off, int n_b, int64_t w_dst, int ld, int rows, int col_lo,
+                   int col_hi, int64_t bias) {
+        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, col_lo, col_hi, bias};
     };
-    job(0, SAVE_ENC, 1, DZ_Z, 4, off.w[0], H, ENC_X, off.b[0]);
-    for (int l = 1; l <= 4; ++l) job(l, SAVE_H + 65536 * (l - 1), 4, DZ_Z + 65536 * l, 4, off.w[l], H, H, off.b[l]);
-    job(5, SAVE_H + 65536 * 4, 4, DZ_Z + 65536 * 5, 4, off.w[5], H, H, off.b[5]);
-    job(6, SAVE_ENC, 1, DZ_Z + 65536 * 5, 4, off.w[5] + (int64_t)H * H, H, ENC_X, -1);
-    job(7, SAVE_H + 65536 * 5, 4, DZ_Z + 65536 * 6, 4, off.w[6], H, H, off.b[6]);
-    job(8, SAVE_H + 65536 * 6, 4, DZ_Z + 65536 * 7, 4, off.w[7], H, H, off.b[7]);
-    job(9, SAVE_H + 65536 * 7, 4, DZ_FEAT, 4, off.w[9], H, H, off.b[9]);
-    job(10, SAVE_FEAT, 4, DZ_DDIR, 2, off.w[10], H / 2, H, off.b[10]);
+    job(0, SAVE_ENC, 1, DZ_Z, 4, off.w[0], H, ENC_X, 0, H, off.b[0]);
+    for (int l = 1; l <= 4; ++l)
+        job(l, SAVE_H + 65536 * (l - 1), 4, DZ_Z + 65536 * l, 4, off.w[l], H, H, 0, H, off.b[l]);
+    job(5, SAVE_H + 65536 * 4, 4, DZ_Z + 65536 * 5, 4, off.w[5], H, H, 0, H, off.b[5]);
+    job(6, SAVE_ENC, 1, DZ_Z + 65536 * 5, 4, off.w[5] + (int64_t)H * H, H, ENC_X, 0, H, -1);
+    job(7, SAVE_H + 65536 * 5, 4, DZ_Z + 65536 * 6, 4, off.w[6], H, H, 0, H, off.b[6]);
+    job(8, SAVE_H + 65536 * 6, 4, DZ_Z + 65536 * 7, 4, off.w[7], H, H, 0, H, off.b[7]);
+    job(9, SAVE_H + 65536 * 7, 4, DZ_FEAT, 4, off.w[9], H, H, 0, H, off.b[9]);
+    job(10, SAVE_FEAT, 4, DZ_DDIR, 2, off.w[10], H / 2, H, 0, H / 2, off.b[10]);
+    // sigma head: h8^T [.., d sigma] -> column 3 of the accumulator is dW_sigma (256,1)
+    job(11, SAVE_H + 65536 * 7, 4, DZ_HEAD, 1, off.w[8] - 3, 1, H, 3, 4, -1);
+    // rgb head: hd^T [d rgb, ..] -> columns 0..2 are dW_rgb (128,3)
+    job(12, SAVE_HD, 2, DZ_HEAD, 1, off.w[11], 3, H / 2, 0, 3, -1);
+    // direction rows of Wddir: dirimg^T dZ_ddir -> rows 256..282 of dW_ddir
+    job(13, SAVE_DIR, 1, DZ_DDIR, 2, off.w[10] + (int64_t)H * (H / 2), H / 2, ENC_D, 0, H / 2, -1);
+    head_bias_kernel<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4*>(d_preds), M, grads + off.b[11],
+                                                grads + off.b[8]);
+    NERF_LAUNCHED();
+    dir_image_kernel<<<stream_grid(B * 32, 128), 128, 0, st>>>(d, B, N, reinterpret_cast<uint8_t*>(ctx->act_save[net]));
+    NERF_LAUNCHED();
     int slabs = num_sms() / WG_NJOBS;
     if (slabs < 1) slabs = 1;
     if (slabs > W.n_half_tiles) slabs = (int)W.n_half_tiles;
     timing_begin(2, st);
     nerf_wgrad_tc_kernel<<<dim3(slabs, WG_NJOBS), WG_THREADS, WG_SMEM, st>>>(W);
     timing_end(2, st);
-    NERF_LAUNCHED();
-
-    {
-        const int64_t n_tiles = n_pairs * 2;
-        const int grid_h = (int)(n_tiles < 4 * num_sms() ? n_tiles : 4 * num_sms());
-        head_grad_kernel<<<grid_h, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(ctx->act_save[net]),
-                                                 reinterpret_cast<const float4*>(d_preds), n_tiles, grads + off.w[8],
-                                                 grads + off.b[8], grads + off.w[11], grads + off.b[11]);
-        NERF_LAUNCHED();
-    }
-    {
-        const int64_t n_tiles = n_pairs * 2;
-        const int grid_d = (int)(n_tiles < 4 * num_sms() ? n_tiles : 4 * num_sms());
-        ddir_dirgrad_kernel<<<grid_d, 128, 0, st>>>(d, N, M, reinterpret_cast<const uint8_t*>(ctx->dz_save[net]), n_tiles,
-                                                    grads + off.w[10]);
-    }
     NERF_LAUNCHED();
     return NERF_OK;
 }

@@ -67,14 +67,16 @@ constexpr int64_t SAVE_ENC = 0;                         // [128 x 64] bf16(enc),
 constexpr int64_t SAVE_H = 16384;                       // + 65536 * i : output of trunk layer i (0..7)
 constexpr int64_t SAVE_FEAT = 16384 + 8 * 65536;        // feature (linear) output
 constexpr int64_t SAVE_HD = SAVE_FEAT + 65536;          // ddir output, 128 wide (32 KB)
-constexpr int64_t SAVE_TILE_BYTES = SAVE_HD + 32768;    // 638976
+constexpr int64_t SAVE_DIR = SAVE_HD + 32768;           // [128 x 64] bf16 direction encoding (27 used), backward only
+constexpr int64_t SAVE_TILE_BYTES = SAVE_DIR + 16384;   // 655360
 // ReLU sign masks per tile: [9 layers][128 rows][8 x u32]  (layer 8 = ddir, 4 words used)
 constexpr int64_t MASK_TILE_BYTES = 9 * 128 * 32;       // 36864
 // gradient (dZ) images per tile, written by the backward chain kernel
 constexpr int64_t DZ_Z = 0;                             // + 65536 * l : grad wrt pre-activation of trunk layer l
 constexpr int64_t DZ_FEAT = 8 * 65536;
 constexpr int64_t DZ_DDIR = 9 * 65536;                  // 128 wide (32 KB)
-constexpr int64_t DZ_TILE_BYTES = DZ_DDIR + 32768;      // 622592
+constexpr int64_t DZ_HEAD = DZ_DDIR + 32768;            // [128 x 64]: cols 0..2 = d rgb_raw, col 3 = d sigma_raw
+constexpr int64_t DZ_TILE_BYTES = DZ_HEAD + 16384;      // 638976
 
 // per-net layer offsets inside the flat fp32 blob (floats): d0..d7, sigma, feature, ddir, rgb
 struct BlobOffsets {
