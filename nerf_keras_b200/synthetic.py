@@ -1,0 +1,92 @@
+"""Synthetic Lego-/Fern-shaped data with the return structure of the reference loaders
+(`prepare_lego_data`, lego_data_utils.py:8-51; `prepare_fern_data`, fern_data_utils.py:462-520) and an
+on-device replacement for `create_batched_dataset_pipeline` (data_utils.py:140-170).
+
+The real datasets need a network download / ImageMagick / GCS (out of scope);
+shapes, bounds and camera models follow SURVEY.md section 8(d) and Appendix B."""
+from __future__ import annotations
+
+import math
+from typing import Iterator, Tuple
+
+import numpy as np
+import torch
+
+from . import data_utils as du
+
+
+def _procedural_rgb(o: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
+    """A cheap smooth function of the ray (so that training has something learnable)."""
+    dn = d / d.norm(dim=-1, keepdim=True)
+    p = o + 4.0 * dn
+    return torch.stack([0.5 + 0.5 * torch.sin(3.0 * p[..., 0]), 0.5 + 0.5 * torch.cos(2.0 * p[..., 1] + p[..., 2]),
+                        0.5 + 0.5 * torch.sin(p[..., 0] * p[..., 2])], dim=-1).clamp(0, 1).contiguous()
+
+
+def _views(H, W, focal, poses):
+    imgs, oris, dirs = [], [], []
+    for pose in poses:
+        o, d = du.get_rays(H, W, focal, pose)
+        o, d = o.reshape(-1, 3), d.reshape(-1, 3)
+        imgs.append(_procedural_rgb(o, d)); oris.append(o); dirs.append(d)
+    return torch.cat(imgs), torch.cat(oris), torch.cat(dirs)
+
+
+def prepare_lego_data(H: int, W: int, n_views: int = 20, seed: int = 0):
+    """((imgs_s, oris_s, dirs_s) train, (...) val, (near, far), focal): flattened per-pixel arrays, 80/20 split,
+    near/far = 2/6 (lego_data_utils.py:26,39-49)."""
+    rng = np.random.default_rng(seed)
+    focal = float(np.float32(0.5 * W / math.tan(0.5 * 0.6911112)))
+    poses = [du.pose_spherical(float(t), float(p), 4.0)
+             for t, p in zip(rng.uniform(-180, 180, n_views), rng.uniform(-90, 0, n_views))]
+    k = int(n_views * 0.8)
+    return _views(H, W, focal, poses[:k]), _views(H, W, focal, poses[k:]), (2.0, 6.0), focal
+
+
+def prepare_fern_data(H: int, W: int, n_views: int = 20, seed: int = 2):
+    """Forward-facing poses (identity rotation + small yaw/pitch, xy translation), pinhole rays with near/far from
+    the bounds as the reference does (fern_data_utils.py:489-496); one view held out (:499-500)."""
+    rng = np.random.default_rng(seed)
+    focal = float(np.float32(407.6 * W / 504.0))
+    poses = []
+    for _ in range(n_views):
+        yaw, pitch = np.deg2rad(rng.uniform(-10, 10, 2))
+        cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+        R = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+        pose = np.eye(4, dtype=np.float32)
+        pose[:3, :3] = R.astype(np.float32)
+        pose[:2, 3] = rng.uniform(-0.3, 0.3, 2).astype(np.float32)
+        poses.append(pose)
+    return _views(H, W, focal, poses[1:]), _views(H, W, focal, poses[:1]), (1.2, 12.0), focal
+
+
+class BatchedRayDataset:
+    """On-device stand-in for `create_batched_dataset_pipeline` (data_utils.py:140-170): one shared jitter vector
+    drawn when the dataset is built (:156, quirk Q1), uniformly random ray batches (drop_remainder), yielding
+    (images, (ray_origins, ray_directions, t_vals)).  rank/world shard each global batch for data parallelism."""
+
+    def __init__(self, images_s, ray_oris_s, ray_dirs_s, num_samples, batch_size, near=2.0, far=6.0, shuffle=True,
+                 rand_sampling=True, steps_per_epoch=None, rank=0, world=1, seed=0):
+        self.img, self.o, self.d = images_s, ray_oris_s, ray_dirs_s
+        self.n = self.o.shape[0]
+        self.batch = int(batch_size)
+        self.local = self.batch // world
+        self.rank, self.world, self.shuffle = rank, world, shuffle
+        self.steps = steps_per_epoch or max(1, self.n // self.batch)
+        u = torch.rand(num_samples, device=self.o.device) if rand_sampling else None
+        self.t_row = du.generate_t_vals(near, far, 1, num_samples, rand_sampling, u=u)
+        self.gen = torch.Generator(device=self.o.device)
+        self.gen.manual_seed(seed)
+
+    def __len__(self):
+        return self.steps
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]]:
+        for s in range(self.steps):
+            if self.shuffle:
+                idx = torch.randint(0, self.n, (self.batch,), device=self.o.device, generator=self.gen)
+            else:
+                idx = (torch.arange(self.batch, device=self.o.device) + s * self.batch) % self.n
+            idx = idx[self.rank * self.local:(self.rank + 1) * self.local]
+            t = self.t_row.expand(idx.shape[0], -1).contiguous()
+            yield self.img[idx], (self.o[idx], self.d[idx], t)

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""train_lego.py --config config/*.json : entry point with the reference's CLI (train_lego.py:25-27) on the
+B200 path.  Data are synthetic Lego-shaped views (the tiny-NeRF download is out of scope); launched under
+torchrun it trains data-parallel like train_tpu_lego.py (one process per GPU, NCCL gradient all-reduce)."""
+import argparse
+import json
+import os
+
+import nerf_keras_b200 as nk
+from nerf_keras_b200.config import load_config, model_kwargs
+from nerf_keras_b200.dist import init_from_env
+from nerf_keras_b200.synthetic import BatchedRayDataset, prepare_lego_data, prepare_fern_data
+
+
+def main(dataset="lego"):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=str, default=f"config/{dataset}_batch_debug.json")
+    ap.add_argument("--steps-per-epoch", type=int, default=None)
+    ap.add_argument("--views", type=int, default=10)
+    args = ap.parse_args()
+    conf = load_config(args.config)
+    name = os.path.splitext(os.path.basename(args.config))[0]
+    rank, local, world = init_from_env()
+    nk.set_random_seed(42)
+    prep = prepare_lego_data if dataset == "lego" else prepare_fern_data
+    train, val, (near, far), focal = prep(conf["HEIGHT"], conf["WIDTH"], n_views=args.views)
+    B, Nc, Nf = conf["BATCH_SIZE"], conf["NS_COARSE"], conf["NS_FINE"]
+    train_ds = BatchedRayDataset(*train, Nc, B, near, far, shuffle=True, steps_per_epoch=args.steps_per_epoch,
+                                 rank=rank, world=world)
+    val_ds = BatchedRayDataset(*val, Nc, conf.get("TEST_BATCH_SIZE", B), near, far, shuffle=False,
+                               steps_per_epoch=min(4, max(1, val[0].shape[0] // B)))
+    coarse = nk.create_nerf_complete_model(**model_kwargs(conf))
+    fine = nk.create_nerf_complete_model(**model_kwargs(conf))
+    trainer = nk.NeRFTrainer(coarse, fine, B // world, Nc, Nf, conf["L_XYZ"], conf["L_DIR"])
+    trainer.compile(optimizer=nk.Adam(learning_rate=conf["LEARNING_RATE"]), loss_fn=nk.MeanSquaredError())
+    history = trainer.fit(train_ds, validation_data=val_ds, epochs=conf["EPOCHS"], verbose=int(rank == 0))
+    if rank == 0:
+        os.makedirs("models", exist_ok=True)
+        trainer.save_weights(f"models/nerf_{dataset}_l{conf['NUM_LAYERS']}_d{conf['HIDDEN_DIM']}_n{Nc + Nf}_{name}.npz")
+        with open(f"models/history_{name}.json", "w") as f:
+            json.dump(history, f)
+
+
+if __name__ == "__main__":
+    main("lego")
