@@ -146,6 +146,9 @@ int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, const float* d,
 /* Timing experiments only: bit0 skip the CUDA-core side jobs, bit1 skip the MMAs, bit2 skip the final
  * reduction of the weight-gradient kernel (results are then wrong by construction). */
 int nerf_debug_flags(int flags);
+/* Diagnostics: timeline trace of CTA 0 of the fused forward kernel (device buffer of 768 int64 clock stamps,
+ * NULL disables). */
+int nerf_debug_trace(long long* dev_buf);
 /* MMA issue-rate probe (cycles for `reps` x 4 back-to-back 128 x n x 16 MMAs). */
 int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycles_dev, void* stream);
 /* Self-test of the tcgen05 building block: C (M,N) fp32 = A (M,K) bf16-rounded x B^T, B (N,K). */

@@ -56,6 +56,7 @@ struct FwdParams {
     float4* preds;         // (M) [r,g,b,sigma] raw
     uint8_t* act_save;     // optional saved-activation images (training)
     uint32_t* mask_save;   // optional ReLU masks (training)
+    long long* trace;      // optional timeline trace buffer (diagnostics)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
 // per-ray fp32 bias of the ddir layer: dirbias[ray][j] = sum_k enc_dir(d_ray)[k] * Wddir[256+k][j]
 __global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ d, int64_t rays,
                                                       const float* __restrict__ wddir /* (283,128) */,
+                                                      const float* __restrict__ bddir /* (128) */,
                                                       float* __restrict__ dirbias) {
     __shared__ float enc[ENC_D];
     for (int64_t ray = blockIdx.x; ray < rays; ray += gridDim.x) {
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ 
         float acc = 0.f;
 #pragma unroll
         for (int k = 0; k < ENC_D; ++k) acc = fmaf(enc[k], wddir[(int64_t)(H + k) * (H / 2) + threadIdx.x], acc);
-        dirbias[ray * (H / 2) + threadIdx.x] = acc;
+        dirbias[ray * (H / 2) + threadIdx.x] = acc + bddir[threadIdx.x];
         __syncthreads();
     }
 }
@@ -146,11 +148,11 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ 
 // ---- epilogue building blocks ---------------------------------------------------------------------
 // one 32-column group of a trunk / feature layer: acc + bias (packed fp32x2 adds), fused ReLU + bf16
 // convert, optional sigma head accumulation and ReLU mask, then four 16-byte swizzled stores.
-template <bool RELU, bool SIGMA, bool SAVE>
-__device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float* bias_g, const float* wsig_g,
-                                            uint64_t& sig2, uint32_t& mk, uint32_t act_base, int row, int cg) {
-    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias_g);
-    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(wsig_g);
+template <bool RELU, bool SIGMA, bool SAVE, int CG>
+__device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float* bias, const float* wsig,
+                                            uint64_t& sig2, uint32_t& mk, const RowStore& rs) {
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias + CG * 32);
+    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(wsig + CG * 32);
     uint32_t pk[16];
     mk = 0;
 #pragma unroll
@@ -178,31 +180,95 @@ __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-        store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
 }
 
 // whole 256-column epilogue with the TMEM loads software-pipelined one group ahead
 template <bool RELU, bool SIGMA, bool SAVE>
 __device__ __forceinline__ void trunk_epilogue(uint32_t t_lane, const float* bias, const float* wsig, float& sig,
-                                               uint32_t (&mask)[8], uint32_t act_base, int row) {
+                                               uint32_t (&mask)[8], const RowStore& rs) {
     uint32_t va[32], vb[32];
     uint64_t sig2 = 0ull;
     tmem_ld32(t_lane, va);
-#pragma unroll
-    for (int cg = 0; cg < 8; cg += 2) {
-        tmem_ld_wait();
-        tmem_ld32(t_lane + (cg + 1) * 32, vb);
-        trunk_group<RELU, SIGMA, SAVE>(va, bias + cg * 32, wsig + cg * 32, sig2, mask[cg], act_base, row, cg);
-        tmem_ld_wait();
-        if (cg + 2 < 8) tmem_ld32(t_lane + (cg + 2) * 32, va);
-        trunk_group<RELU, SIGMA, SAVE>(vb, bias + (cg + 1) * 32, wsig + (cg + 1) * 32, sig2, mask[cg + 1], act_base, row,
-                                       cg + 1);
-    }
+#define NERF_TRUNK_PAIR(CG)                                                                        \
+    tmem_ld_wait();                                                                                \
+    tmem_ld32(t_lane + (CG + 1) * 32, vb);                                                         \
+    trunk_group<RELU, SIGMA, SAVE, CG>(va, bias, wsig, sig2, mask[CG], rs);                        \
+    tmem_ld_wait();                                                                                \
+    if (CG + 2 < 8) tmem_ld32(t_lane + (CG + 2) * 32, va);                                         \
+    trunk_group<RELU, SIGMA, SAVE, CG + 1>(vb, bias, wsig, sig2, mask[CG + 1], rs);
+    NERF_TRUNK_PAIR(0)
+    NERF_TRUNK_PAIR(2)
+    NERF_TRUNK_PAIR(4)
+    NERF_TRUNK_PAIR(6)
+#undef NERF_TRUNK_PAIR
     if (SIGMA) {
         float a, b;
         f2_unpack(sig2, a, b);
         sig = a + b;
     }
+}
+
+// one 32-column group of the ddir epilogue: + (bias + per-ray direction bias), ReLU, rgb head dot products
+template <bool SAVE, int CG>
+__device__ __forceinline__ void ddir_group(const uint32_t (&v)[32], const float* dbias /* this ray, 128 floats */,
+                                           const float* side, uint64_t& r2, uint64_t& g2, uint64_t& b2acc, uint32_t& mk,
+                                           const RowStore& rs) {
+    const ulonglong2* d2 = reinterpret_cast<const ulonglong2*>(dbias + CG * 32);
+    const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + CG * 32);
+    const ulonglong2* wg = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 128 + CG * 32);
+    const ulonglong2* wb = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 256 + CG * 32);
+    uint32_t pk[16];
+    mk = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const ulonglong2 dd = d2[q];
+        float x0, x1, x2, x3;
+        f2_unpack(f2_add(f2_pack(v[4 * q], v[4 * q + 1]), dd.x), x0, x1);
+        f2_unpack(f2_add(f2_pack(v[4 * q + 2], v[4 * q + 3]), dd.y), x2, x3);
+        x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+        const uint64_t x01 = f2_pack(__float_as_uint(x0), __float_as_uint(x1));
+        const uint64_t x23 = f2_pack(__float_as_uint(x2), __float_as_uint(x3));
+        const ulonglong2 a = wr[q], b = wg[q], c = wb[q];
+        r2 = f2_fma(x01, a.x, r2); r2 = f2_fma(x23, a.y, r2);
+        g2 = f2_fma(x01, b.x, g2); g2 = f2_fma(x23, b.y, g2);
+        b2acc = f2_fma(x01, c.x, b2acc); b2acc = f2_fma(x23, c.y, b2acc);
+        if (SAVE) {
+            mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
+            mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
+            mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
+            mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
+            pk[2 * q] = cvt_bf16x2<false>(x0, x1);
+            pk[2 * q + 1] = cvt_bf16x2<false>(x2, x3);
+        }
+    }
+    if (SAVE) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    }
+}
+
+// positional encoding of one point: accurate sincosf at octaves 0 and 5, exact angle doubling in between
+// (sin 2a = 2 sin a cos a, cos 2a = 1 - 2 sin^2 a; at most 4 doublings -> error <= ~2e-6, far below a bf16 ulp)
+__device__ __forceinline__ void encode_xyz(const float (&p)[3], float (&e)[64]) {
+    e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float sv, cv;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            if (i == 0 || i == 5) sincosf((float)(1 << i) * p[c], &sv, &cv);
+            else {
+                const float s2 = 2.f * sv * cv;
+                const float c2 = fmaf(-2.f * sv, sv, 1.f);
+                sv = s2; cv = c2;
+            }
+            e[3 + 6 * i + c] = sv;
+            e[3 + 6 * i + 3 + c] = cv;
+        }
+    }
+    e[63] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -233,7 +299,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
     if (warp == 8) {
         if (lane == 0) producer_loop(base, B, P.w_chunks, N_CHUNKS, total_chunks);
     } else if (warp >= 9) {
-        if (lane == 0) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs);
+        if (lane == 0) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace);
     } else {
         // ===================== workers: PE prologue + epilogues =====================
         const int s = warp >> 2;
@@ -241,6 +307,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
         const uint32_t act_base = base + SM_ACT + s * 65536;
         const uint32_t t_lane = tmem_base + (uint32_t(32 * (warp & 3)) << 16) + s * 256;
         const bool elected = (row == 0);
+        float* dbs = reinterpret_cast<float*>(smem + SM_DIRB) + s * (DIRB_ROWS * 128);   // staged per-ray ddir biases
+        RowStore rs;
+        rs.init(act_base, row);
         uint32_t accf_par = 0;
         uint32_t E[32];     // bf16(enc), 64 channels packed
         uint32_t Elo[2];    // bf16 residuals of the raw x, y, z channels
@@ -255,26 +324,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
             uint8_t* save_tile = SAVE ? P.act_save + tile * SAVE_TILE_BYTES : nullptr;
             uint32_t* mask_tile = SAVE ? P.mask_save + tile * (MASK_TILE_BYTES / 4) : nullptr;
 
-            // ---- positional encoding of this row's sample point (fp32, accurate sincosf) ----
+            // ---- stage the ddir biases (bias + direction term) of the rays this sub-tile touches ----
+            const int64_t m_first = tile * TILE_M;
+            const int64_t ray0 = ((m_first < P.M) ? m_first : (P.M - 1)) / P.N;
+            const int64_t m_last = (m_first + TILE_M - 1 < P.M) ? (m_first + TILE_M - 1) : (P.M - 1);
+            const int n_rays = (int)(m_last / P.N - ray0) + 1;
+            const bool staged = n_rays <= DIRB_ROWS;
+            float4 db_pref = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int db_idx = row;                          // thread i prefetches float4 i of the staged block
+            if (staged && db_idx < n_rays * 32)
+                db_pref = __ldg(reinterpret_cast<const float4*>(P.dirbias + ray0 * 128) + db_idx);
+
+            // ---- positional encoding of this row's sample point (fp32) ----
             {
                 const float tv = P.t[gr];
                 float p[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(P.o[ray * 3 + c], __fmul_rn(P.d[ray * 3 + c], tv));
                 float e[64];
-                e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
-#pragma unroll
-                for (int i = 0; i < 10; ++i) {
-                    const float sc = (float)(1 << i);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float sv, cv;
-                        sincosf(sc * p[c], &sv, &cv);
-                        e[3 + 6 * i + c] = sv;
-                        e[3 + 6 * i + 3 + c] = cv;
-                    }
-                }
-                e[63] = 0.f;
+                encode_xyz(p, e);
 #pragma unroll
                 for (int q = 0; q < 32; ++q) E[q] = pack_bf16x2(e[2 * q], e[2 * q + 1]);
                 float lo[3];
@@ -283,14 +351,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                 Elo[0] = pack_bf16x2(lo[0], lo[1]);
                 Elo[1] = pack_bf16x2(lo[2], 0.f);
             }
-            if (SAVE) {  // previous tile's last bulk store must have finished reading act before we overwrite it
-                if (elected) bulk_wait_read0();
-                named_bar_sync(1 + s, TILE_M);
-            }
+            // every thread of the sub-tile is past the previous tile's ddir epilogue (last reader of the staged
+            // biases), and in training mode the previous tile's last bulk store has finished reading the tile
+            if (SAVE && elected) bulk_wait_read0();
+            named_bar_sync(1 + s, TILE_M);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) store_row_chunk(act_base, 0, row, c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
-            store_row_chunk(act_base, 1, row, 0, Elo[0], Elo[1], 0u, 0u);
-            store_row_chunk(act_base, 1, row, 1, 0u, 0u, 0u, 0u);
+            for (int c = 0; c < 8; ++c) rs.store<0>(c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
+            rs.store<1>(0, Elo[0], Elo[1], 0u, 0u);
+            rs.store<1>(1, 0u, 0u, 0u, 0u);
+            if (staged && db_idx < n_rays * 32) reinterpret_cast<float4*>(dbs)[db_idx] = db_pref;
             tc_fence_before();
             fence_proxy_async_smem();
             if (SAVE) {
@@ -301,9 +370,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
 
             float sig = 0.f;
             for (int ph = 0; ph < N_PHASES; ++ph) {
+                if (elected) trace_ev(P.trace, 2 + s, it, ph, 0);      // worker: starts waiting for the accumulator
                 mbar_wait(B.accf + 8 * s, accf_par, 2);
                 accf_par ^= 1;
                 tc_fence_after();
+                if (elected) trace_ev(P.trace, 2 + s, it, ph, 1);      // worker: accumulator ready
                 if (SAVE) {
                     if (elected) bulk_wait_read0();
                     named_bar_sync(1 + s, TILE_M);
@@ -311,10 +382,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                 if (ph == 5) {
                     // L5a done: stage the skip-connection encoding as K-blocks 0 (hi) and 1 (residual) for L5b
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        store_row_chunk(act_base, 0, row, c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
-                    store_row_chunk(act_base, 1, row, 0, Elo[0], Elo[1], 0u, 0u);
-                    store_row_chunk(act_base, 1, row, 1, 0u, 0u, 0u, 0u);
+                    for (int c = 0; c < 8; ++c) rs.store<0>(c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
+                    rs.store<1>(0, Elo[0], Elo[1], 0u, 0u);
+                    rs.store<1>(1, 0u, 0u, 0u, 0u);
                     tc_fence_before();
                     fence_proxy_async_smem();
                     mbar_arrive(B.actr + 8 * s);
@@ -327,9 +397,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     const bool relu = layer < 8;
                     uint32_t mask[8];
                     const float* wsig = side + SIDE_WSIG;
-                    if (ph == 8) trunk_epilogue<true, true, SAVE>(t_lane, bias, wsig, sig, mask, act_base, row);
-                    else if (relu) trunk_epilogue<true, false, SAVE>(t_lane, bias, wsig, sig, mask, act_base, row);
-                    else trunk_epilogue<false, false, SAVE>(t_lane, bias, wsig, sig, mask, act_base, row);
+                    if (ph == 8) trunk_epilogue<true, true, SAVE>(t_lane, bias, wsig, sig, mask, rs);
+                    else if (relu) trunk_epilogue<true, false, SAVE>(t_lane, bias, wsig, sig, mask, rs);
+                    else trunk_epilogue<false, false, SAVE>(t_lane, bias, wsig, sig, mask, rs);
                     tc_fence_before();
                     fence_proxy_async_smem();
                     if (SAVE) {
@@ -345,54 +415,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                             bulk_commit();
                         }
                     }
+                    if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);  // worker: epilogue done
                     mbar_arrive(B.actr + 8 * s);
                 } else {
-                    // ddir epilogue: + bias + per-ray direction bias, ReLU, rgb head (fp32), write preds
-                    float r = 0.f, gch = 0.f, b = 0.f;
-                    const float* db = P.dirbias + ray * (H / 2);
+                    // ddir epilogue: + (bias + per-ray direction bias), ReLU, rgb head (fp32), write preds
+                    uint64_t r2 = 0ull, g2 = 0ull, b2 = 0ull;
                     uint32_t mask[4];
-#pragma unroll 1
-                    for (int cg = 0; cg < 4; ++cg) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + cg * 32, v);
-                        tmem_ld_wait();
-                        uint32_t pk[16];
-                        uint32_t mk = 0;
-                        const float4* bd4 = reinterpret_cast<const float4*>(side + SIDE_BDDIR + cg * 32);
-                        const float4* wr4 = reinterpret_cast<const float4*>(side + SIDE_WRGB + cg * 32);
-                        const float4* wg4 = reinterpret_cast<const float4*>(side + SIDE_WRGB + 128 + cg * 32);
-                        const float4* wb4 = reinterpret_cast<const float4*>(side + SIDE_WRGB + 256 + cg * 32);
-                        const float4* db4 = reinterpret_cast<const float4*>(db + cg * 32);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 bb = bd4[q], dd = __ldg(db4 + q), wr = wr4[q], wg = wg4[q], wb = wb4[q];
-                            float x0 = fmaxf(__uint_as_float(v[4 * q]) + bb.x + dd.x, 0.f);
-                            float x1 = fmaxf(__uint_as_float(v[4 * q + 1]) + bb.y + dd.y, 0.f);
-                            float x2 = fmaxf(__uint_as_float(v[4 * q + 2]) + bb.z + dd.z, 0.f);
-                            float x3 = fmaxf(__uint_as_float(v[4 * q + 3]) + bb.w + dd.w, 0.f);
-                            r = fmaf(x0, wr.x, r); r = fmaf(x1, wr.y, r); r = fmaf(x2, wr.z, r); r = fmaf(x3, wr.w, r);
-                            gch = fmaf(x0, wg.x, gch); gch = fmaf(x1, wg.y, gch); gch = fmaf(x2, wg.z, gch); gch = fmaf(x3, wg.w, gch);
-                            b = fmaf(x0, wb.x, b); b = fmaf(x1, wb.y, b); b = fmaf(x2, wb.z, b); b = fmaf(x3, wb.w, b);
-                            if (SAVE) {
-                                mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
-                                mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
-                                mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
-                                mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
-                                pk[2 * q] = pack_bf16x2(x0, x1);
-                                pk[2 * q + 1] = pack_bf16x2(x2, x3);
-                            }
-                        }
-                        if (SAVE) {
-                            mask[cg] = mk;
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1],
-                                                pk[4 * c + 2], pk[4 * c + 3]);
-                        }
-                    }
+                    // staged copy lives in shared memory; ragged tiles with many short rays fall back to global
+                    const float* db = staged ? (dbs + (int)(ray - ray0) * 128) : (P.dirbias + ray * 128);
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(t_lane, va);
+                    tmem_ld_wait();
+                    tmem_ld32(t_lane + 32, vb);
+                    ddir_group<SAVE, 0>(va, db, side, r2, g2, b2, mask[0], rs);
+                    tmem_ld_wait();
+                    tmem_ld32(t_lane + 64, va);
+                    ddir_group<SAVE, 1>(vb, db, side, r2, g2, b2, mask[1], rs);
+                    tmem_ld_wait();
+                    tmem_ld32(t_lane + 96, vb);
+                    ddir_group<SAVE, 2>(va, db, side, r2, g2, b2, mask[2], rs);
+                    tmem_ld_wait();
+                    ddir_group<SAVE, 3>(vb, db, side, r2, g2, b2, mask[3], rs);
+                    float ra, rb, ga, gb, ba, bb;
+                    f2_unpack(r2, ra, rb); f2_unpack(g2, ga, gb); f2_unpack(b2, ba, bb);
+                    if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);
                     if (valid)
-                        P.preds[g_row] = make_float4(r + side[SIDE_BRGB], gch + side[SIDE_BRGB + 1],
-                                                     b + side[SIDE_BRGB + 2], sig + side[SIDE_BSIG]);
+                        P.preds[g_row] = make_float4(ra + rb + side[SIDE_BRGB], ga + gb + side[SIDE_BRGB + 1],
+                                                     ba + bb + side[SIDE_BRGB + 2], sig + side[SIDE_BSIG]);
                     tc_fence_before();
                     if (SAVE) {
                         uint4* mp = reinterpret_cast<uint4*>(mask_tile + ((size_t)8 * 128 + row) * 8);
@@ -549,6 +598,8 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int reps, int m
 
 namespace nerf {
 
+long long* g_trace_buf = nullptr;
+
 int tc_supported(const nerf_config& c, std::string* why) {
     if (c.num_layers != 8 || c.hidden_dim != 256 || c.skip_layer != 4 || c.l_xyz != 10 || c.l_dir != 4) {
         if (why) *why = "tcgen05 path is specialised to NUM_LAYERS=8, HIDDEN_DIM=256, SKIP_LAYER=4, L_XYZ=10, L_DIR=4";
@@ -593,7 +644,7 @@ int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, cons
     if (B > ctx->cfg.max_rays) return fail(NERF_ERR_INVALID, "tc_forward_rays: batch exceeds cfg.max_rays");
     const float* blob = ctx->params + (int64_t)net * ctx->n_params;
     dirbias_kernel<<<(unsigned)(B < 4 * num_sms() ? B : 4 * num_sms()), 128, 0, st>>>(
-        d, B, blob + ctx->layers[10].w_off, ctx->fw_dirbias);
+        d, B, blob + ctx->layers[10].w_off, blob + ctx->layers[10].b_off, ctx->fw_dirbias);
     NERF_LAUNCHED();
     FwdParams P;
     P.o = o; P.d = d; P.t = t; P.N = N;
@@ -605,6 +656,7 @@ int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, cons
     P.preds = reinterpret_cast<float4*>(preds);
     P.act_save = save_acts ? reinterpret_cast<uint8_t*>(ctx->act_save[net]) : nullptr;
     P.mask_save = save_acts ? ctx->mask_save[net] : nullptr;
+    P.trace = g_trace_buf;
     int grid = (int)(P.n_pairs < num_sms() ? P.n_pairs : num_sms());
     timing_begin(0, st);
     if (save_acts) {
@@ -645,3 +697,6 @@ extern "C" int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycl
     NERF_LAUNCHED();
     return NERF_OK;
 }
+
+// diagnostics: enable (device buffer of 4*3*16*4 int64) / disable the forward-kernel timeline trace
+extern "C" int nerf_debug_trace(long long* dev_buf) { nerf::g_trace_buf = dev_buf; return NERF_OK; }

@@ -81,16 +81,16 @@ struct BwdParams {
 };
 
 // one 32-column group of a chain epilogue: optional sigma-head term, ReLU mask, bf16, swizzled store
-template <bool SIGMA, bool MASK>
-__device__ __forceinline__ void chain_group(const uint32_t (&v)[32], float dsig, const float* wsig_g, uint32_t mk,
-                                            uint32_t act_base, int row, int cg) {
+template <bool SIGMA, bool MASK, int CG>
+__device__ __forceinline__ void chain_group(const uint32_t (&v)[32], float dsig, const float* wsig, uint32_t mk,
+                                            const RowStore& rs) {
     uint32_t pk[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         float x0 = __uint_as_float(v[2 * q]), x1 = __uint_as_float(v[2 * q + 1]);
         if (SIGMA) {
-            x0 = fmaf(dsig, wsig_g[2 * q], x0);
-            x1 = fmaf(dsig, wsig_g[2 * q + 1], x1);
+            x0 = fmaf(dsig, wsig[CG * 32 + 2 * q], x0);
+            x1 = fmaf(dsig, wsig[CG * 32 + 2 * q + 1], x1);
         }
         if (MASK) {
             x0 = ((mk >> (2 * q)) & 1u) ? x0 : 0.f;
@@ -100,23 +100,26 @@ __device__ __forceinline__ void chain_group(const uint32_t (&v)[32], float dsig,
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-        store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
 }
 
 template <bool SIGMA, bool MASK>
 __device__ __forceinline__ void chain_epilogue(uint32_t t_lane, float dsig, const float* wsig, const uint32_t (&mask)[8],
-                                               uint32_t act_base, int row) {
+                                               const RowStore& rs) {
     uint32_t va[32], vb[32];
     tmem_ld32(t_lane, va);
-#pragma unroll
-    for (int cg = 0; cg < 8; cg += 2) {
-        tmem_ld_wait();
-        tmem_ld32(t_lane + (cg + 1) * 32, vb);
-        chain_group<SIGMA, MASK>(va, dsig, wsig + cg * 32, mask[cg], act_base, row, cg);
-        tmem_ld_wait();
-        if (cg + 2 < 8) tmem_ld32(t_lane + (cg + 2) * 32, va);
-        chain_group<SIGMA, MASK>(vb, dsig, wsig + (cg + 1) * 32, mask[cg + 1], act_base, row, cg + 1);
-    }
+#define NERF_CHAIN_PAIR(CG)                                                    \
+    tmem_ld_wait();                                                            \
+    tmem_ld32(t_lane + (CG + 1) * 32, vb);                                     \
+    chain_group<SIGMA, MASK, CG>(va, dsig, wsig, mask[CG], rs);                \
+    tmem_ld_wait();                                                            \
+    if (CG + 2 < 8) tmem_ld32(t_lane + (CG + 2) * 32, va);                     \
+    chain_group<SIGMA, MASK, CG + 1>(vb, dsig, wsig, mask[CG + 1], rs);
+    NERF_CHAIN_PAIR(0)
+    NERF_CHAIN_PAIR(2)
+    NERF_CHAIN_PAIR(4)
+    NERF_CHAIN_PAIR(6)
+#undef NERF_CHAIN_PAIR
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const BwdParams P) {
@@ -150,6 +153,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
         const uint32_t act_base = base + SM_ACT + s * 65536;
         const uint32_t t_lane = tmem_base + (uint32_t(32 * (warp & 3)) << 16) + s * 256;
         const bool elected = (row == 0);
+        RowStore rs;
+        rs.init(act_base, row);
         uint32_t accf_par = 0;
 
         for (int it = 0; it < my_pairs; ++it) {
@@ -167,29 +172,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
             {
                 const uint4 mk4 = *reinterpret_cast<const uint4*>(mask_tile + ((size_t)8 * 128 + row) * 8);
                 const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
-#pragma unroll
-                for (int cg = 0; cg < 4; ++cg) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int c0 = cg * 32 + 2 * q;
-                        float x0 = dp.x * side[SIDE_WRGB + c0] + dp.y * side[SIDE_WRGB + 128 + c0] + dp.z * side[SIDE_WRGB + 256 + c0];
-                        float x1 = dp.x * side[SIDE_WRGB + c0 + 1] + dp.y * side[SIDE_WRGB + 128 + c0 + 1] +
-                                   dp.z * side[SIDE_WRGB + 256 + c0 + 1];
-                        x0 = ((mk[cg] >> (2 * q)) & 1u) ? x0 : 0.f;
-                        x1 = ((mk[cg] >> (2 * q + 1)) & 1u) ? x1 : 0.f;
-                        pk[q] = cvt_bf16x2<false>(x0, x1);
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        store_row_chunk(act_base, cg >> 1, row, (cg & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2],
-                                        pk[4 * c + 3]);
-                }
+#define NERF_DDIR_BWD_GROUP(CG)                                                                                       \
+    {                                                                                                                 \
+        uint32_t pk[16];                                                                                              \
+        _Pragma("unroll") for (int q = 0; q < 16; ++q) {                                                              \
+            const int c0 = CG * 32 + 2 * q;                                                                           \
+            float x0 = dp.x * side[SIDE_WRGB + c0] + dp.y * side[SIDE_WRGB + 128 + c0] + dp.z * side[SIDE_WRGB + 256 + c0]; \
+            float x1 = dp.x * side[SIDE_WRGB + c0 + 1] + dp.y * side[SIDE_WRGB + 128 + c0 + 1] +                      \
+                       dp.z * side[SIDE_WRGB + 256 + c0 + 1];                                                         \
+            x0 = ((mk[CG] >> (2 * q)) & 1u) ? x0 : 0.f;                                                               \
+            x1 = ((mk[CG] >> (2 * q + 1)) & 1u) ? x1 : 0.f;                                                           \
+            pk[q] = cvt_bf16x2<false>(x0, x1);                                                                        \
+        }                                                                                                             \
+        _Pragma("unroll") for (int c = 0; c < 4; ++c)                                                                 \
+            rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);               \
+    }
+                NERF_DDIR_BWD_GROUP(0)
+                NERF_DDIR_BWD_GROUP(1)
+                NERF_DDIR_BWD_GROUP(2)
+                NERF_DDIR_BWD_GROUP(3)
+#undef NERF_DDIR_BWD_GROUP
             }
             // head image (K-block 2 is free until the first epilogue): [d r, d g, d b, d sigma, 0 ...]
-            store_row_chunk(act_base, 2, row, 0, pack_bf16x2(dp.x, dp.y), pack_bf16x2(dp.z, dp.w), 0u, 0u);
+            rs.store<2>(0, pack_bf16x2(dp.x, dp.y), pack_bf16x2(dp.z, dp.w), 0u, 0u);
 #pragma unroll
-            for (int c = 1; c < 8; ++c) store_row_chunk(act_base, 2, row, c, 0u, 0u, 0u, 0u);
+            for (int c = 1; c < 8; ++c) rs.store<2>(c, 0u, 0u, 0u, 0u);
             tc_fence_before();
             fence_proxy_async_smem();
             named_bar_sync(1 + s, TILE_M);
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
                 uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 if (ph == 0) {
                     dst = DZ_FEAT;                                   // feature layer is linear: no mask
-                    chain_epilogue<false, false>(t_lane, 0.f, side + SIDE_WSIG, mask, act_base, row);
+                    chain_epilogue<false, false>(t_lane, 0.f, side + SIDE_WSIG, mask, rs);
                 } else {
                     const int ml = (ph == 1) ? 7 : (8 - ph);         // mask of the ReLU output feeding this grad: h8 .. h1
                     const uint4* mp = reinterpret_cast<const uint4*>(mask_tile + ((size_t)ml * 128 + row) * 8);
@@ -218,8 +225,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
                     mask[0] = m0.x; mask[1] = m0.y; mask[2] = m0.z; mask[3] = m0.w;
                     mask[4] = m1.x; mask[5] = m1.y; mask[6] = m1.z; mask[7] = m1.w;
                     dst = DZ_Z + (int64_t)65536 * ml;
-                    if (ph == 1) chain_epilogue<true, true>(t_lane, dp.w, side + SIDE_WSIG, mask, act_base, row);
-                    else chain_epilogue<false, true>(t_lane, 0.f, side + SIDE_WSIG, mask, act_base, row);
+                    if (ph == 1) chain_epilogue<true, true>(t_lane, dp.w, side + SIDE_WSIG, mask, rs);
+                    else chain_epilogue<false, true>(t_lane, 0.f, side + SIDE_WSIG, mask, rs);
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();

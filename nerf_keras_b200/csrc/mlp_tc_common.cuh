@@ -56,8 +56,11 @@ constexpr int SM_EMPTY = SM_FULL + 8 * STAGES;             // STAGES
 constexpr int SM_ACCF = SM_EMPTY + 8 * STAGES;             // 2
 constexpr int SM_ACTR = SM_ACCF + 16;                      // 2
 constexpr int SM_TMEM = SM_ACTR + 16;                      // u32
-constexpr int SM_TOTAL = SM_TMEM + 16;
+constexpr int DIRB_ROWS = 5;                               // staged per-ray ddir biases per sub-tile (N >= 32 always fits)
+constexpr int SM_DIRB = SM_TMEM + 16;                      // 2 x DIRB_ROWS x 128 floats
+constexpr int SM_TOTAL = SM_DIRB + 2 * DIRB_ROWS * 512;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory limit");
 
 constexpr int NUM_THREADS = 352;  // 8 worker warps (4 per sub-tile) + producer warp + 2 MMA issuer warps
 
@@ -97,12 +100,23 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// one 16-byte chunk (8 bf16) of row `row` into K-block `kblock` of a 128-row activation tile
-__device__ __forceinline__ void store_row_chunk(uint32_t act_base, int kblock, int row, int chunk16, uint32_t a,
-                                                uint32_t b, uint32_t c, uint32_t d) {
-    uint32_t addr = act_base + kblock * (TILE_M * 128) + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
+// Per-thread store addresses of one activation-tile row: off[c] is the shared-memory address of 16-byte chunk c
+// (8 bf16) of this row inside K-block 0, 128B-swizzled (chunk index XOR (row & 7)); K-block kb adds kb * 16 KB,
+// which the compiler folds into the store's immediate offset.  Computed once per thread.
+struct RowStore {
+    uint32_t off[8];
+    __device__ __forceinline__ void init(uint32_t act_base, int row) {
+        const uint32_t rb = act_base + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) off[c] = rb + (uint32_t(c ^ (row & 7)) << 4);
+    }
+    template <int KB>
+    __device__ __forceinline__ void store(int c, uint32_t a, uint32_t b, uint32_t cc, uint32_t d) const {
+        asm volatile("st.shared.v4.b32 [%0+%5], {%1, %2, %3, %4};" ::"r"(off[c]), "r"(a), "r"(b), "r"(cc), "r"(d),
+                     "n"(KB * TILE_M * 128)
+                     : "memory");
+    }
+};
 
 struct Barriers {
     uint32_t full, empty, accf, actr;
@@ -143,8 +157,16 @@ __device__ __forceinline__ void producer_loop(uint32_t base, const Barriers& B, 
 // (a slot is recycled when BOTH sub-tiles' commits have arrived), and commit the accumulator barrier at
 // the end of a phase.  The tensor pipe executes the two instruction streams in arrival order, so one
 // sub-tile's MMAs fill the gaps left by the other's epilogue.
+// optional timeline trace (block 0 only): records (tag, clock) pairs; tag = who * 1000 + tile * 100 + phase * 4 + event
+__device__ __forceinline__ void trace_ev(long long* trace, int who, int tile, int ph, int ev) {
+    if (trace && blockIdx.x == 0 && tile < 3) {
+        const int idx = ((who * 3 + tile) * 16 + ph) * 4 + ev;
+        trace[idx] = clock64();
+    }
+}
+
 __device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, uint32_t tmem_base, const Program& prog,
-                                            int s, int n_tiles) {
+                                            int s, int n_tiles, long long* trace = nullptr) {
     const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
     // descriptor template: LBO = 16 B (unused for swizzled K-major), SBO = 1024 B, version 1, SWIZZLE_128B
     const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
@@ -158,8 +180,10 @@ __device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, ui
     for (int tile = 0; tile < n_tiles; ++tile) {
         for (int ph = 0; ph < n_phases; ++ph) {
             const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
+            trace_ev(trace, s, tile, ph, 0);              // issuer: starts waiting for the A tile
             mbar_wait(B.actr + 8 * s, actr_par, 3);
             actr_par ^= 1;
+            trace_ev(trace, s, tile, ph, 1);              // issuer: A tile ready
             int h = 0, kb = 0;
             for (int j = 0; j < n_ch; ++j) {
                 mbar_wait(B.full + 8 * slot, ring_par, 4);
@@ -182,6 +206,7 @@ __device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, ui
                 if (++kb == kbs) { kb = 0; ++h; }
             }
             mma_commit(B.accf + 8 * s);
+            trace_ev(trace, s, tile, ph, 2);              // issuer: all MMAs of the phase issued
         }
     }
 }

@@ -1,0 +1,29 @@
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nerf_keras_b200 as nk
+from nerf_keras_b200 import _lib
+L = _lib.lib()
+B, Nc, Nf = 4096, 64, 128
+nk.set_random_seed(42)
+c = nk.create_nerf_complete_model(8, 256, 4, 10, 4); f = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+tr = nk.NeRFTrainer(c, f, B, Nc, Nf, 10, 4); tr.build()
+o, d = nk.get_rays(64, 64, 88.0, nk.pose_spherical(20.0, -30.0, 4.0))
+o, d = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
+t = nk.generate_t_vals(2.0, 6.0, B, Nc, False)
+for _ in range(2): tr.mlp_forward_rays("coarse", o, d, t)
+buf = torch.zeros(4 * 3 * 16 * 4, dtype=torch.int64, device="cuda")
+L.nerf_debug_trace(buf.data_ptr())
+tr.mlp_forward_rays("coarse", o, d, t)
+torch.cuda.synchronize()
+L.nerf_debug_trace(None)
+a = buf.cpu().numpy().reshape(4, 3, 16, 4)
+t0 = a[a > 0].min()
+names = ["issA", "issB", "wrkA", "wrkB"]
+for tile in range(2):
+    print(f"tile {tile}: per phase [wait_start, ready, done] relative cycles")
+    for ph in range(11):
+        row = []
+        for who in range(4):
+            e = a[who, tile, ph]
+            row.append(f"{names[who]}: " + " ".join(f"{(x - t0) if x > 0 else -1:7d}" for x in e[:3]))
+        print(f"  ph{ph:2d} | " + " | ".join(row))
