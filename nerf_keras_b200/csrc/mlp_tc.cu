@@ -148,9 +148,9 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ 
 // ---- epilogue building blocks ---------------------------------------------------------------------
 // one 32-column group of a trunk / feature layer: acc + bias (packed fp32x2 adds), fused ReLU + bf16
 // convert, optional sigma head accumulation and ReLU mask, then four 16-byte swizzled stores.
-template <bool RELU, bool SIGMA, bool SAVE, int CG>
+template <bool RELU, bool SIGMA, bool SAVE, int CG, bool STORE>
 __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float* bias, const float* wsig,
-                                            uint64_t& sig2, uint32_t& mk, const RowStore& rs) {
+                                            uint64_t& sig2, uint32_t& mk, const RowStore& rs, uint32_t* held) {
     const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias + CG * 32);
     const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(wsig + CG * 32);
     uint32_t pk[16];
@@ -178,35 +178,55 @@ __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float
         pk[2 * q] = cvt_bf16x2<RELU>(x0, x1);
         pk[2 * q + 1] = cvt_bf16x2<RELU>(x2, x3);
     }
+    if (STORE) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-        rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        for (int c = 0; c < 4; ++c)
+            rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) held[CG * 16 + q] = pk[q];
+    }
 }
 
-// whole 256-column epilogue with the TMEM loads software-pipelined one group ahead
+// First half of a trunk / feature epilogue: columns 0..127 (runs while the MMAs of columns 128..255 are still in
+// flight).  The converted bf16 values are HELD in registers: K-blocks 0,1 of the A tile are still being read.
 template <bool RELU, bool SIGMA, bool SAVE>
-__device__ __forceinline__ void trunk_epilogue(uint32_t t_lane, const float* bias, const float* wsig, float& sig,
-                                               uint32_t (&mask)[8], const RowStore& rs) {
+__device__ __forceinline__ void trunk_part1(uint32_t t_lane, const float* bias, const float* wsig, uint64_t& sig2,
+                                            uint32_t (&mask)[8], const RowStore& rs, uint32_t (&held)[64]) {
+    uint32_t v[32];
+    tmem_ld32(t_lane, v); tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, 0, false>(v, bias, wsig, sig2, mask[0], rs, held);
+    tmem_ld32(t_lane + 32, v); tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, 1, false>(v, bias, wsig, sig2, mask[1], rs, held);
+    tmem_ld32(t_lane + 64, v); tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, 2, false>(v, bias, wsig, sig2, mask[2], rs, held);
+    tmem_ld32(t_lane + 96, v); tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, 3, false>(v, bias, wsig, sig2, mask[3], rs, held);
+}
+// all MMAs of the phase are complete: K-blocks 0,1 may be overwritten with the held first half
+__device__ __forceinline__ void store_held(const RowStore& rs, const uint32_t (&held)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) rs.store<0>(c, held[4 * c], held[4 * c + 1], held[4 * c + 2], held[4 * c + 3]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) rs.store<1>(c, held[32 + 4 * c], held[32 + 4 * c + 1], held[32 + 4 * c + 2], held[32 + 4 * c + 3]);
+}
+// second half: columns 128..255 straight into K-blocks 2,3 (TMEM loads pipelined one group ahead)
+template <bool RELU, bool SIGMA, bool SAVE>
+__device__ __forceinline__ void trunk_part2(uint32_t t_lane, const float* bias, const float* wsig, uint64_t& sig2,
+                                            uint32_t (&mask)[8], const RowStore& rs) {
     uint32_t va[32], vb[32];
-    uint64_t sig2 = 0ull;
-    tmem_ld32(t_lane, va);
-#define NERF_TRUNK_PAIR(CG)                                                                        \
-    tmem_ld_wait();                                                                                \
-    tmem_ld32(t_lane + (CG + 1) * 32, vb);                                                         \
-    trunk_group<RELU, SIGMA, SAVE, CG>(va, bias, wsig, sig2, mask[CG], rs);                        \
-    tmem_ld_wait();                                                                                \
-    if (CG + 2 < 8) tmem_ld32(t_lane + (CG + 2) * 32, va);                                         \
-    trunk_group<RELU, SIGMA, SAVE, CG + 1>(vb, bias, wsig, sig2, mask[CG + 1], rs);
-    NERF_TRUNK_PAIR(0)
-    NERF_TRUNK_PAIR(2)
-    NERF_TRUNK_PAIR(4)
-    NERF_TRUNK_PAIR(6)
-#undef NERF_TRUNK_PAIR
-    if (SIGMA) {
-        float a, b;
-        f2_unpack(sig2, a, b);
-        sig = a + b;
-    }
+    tmem_ld32(t_lane + 128, va);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 160, vb);
+    trunk_group<RELU, SIGMA, SAVE, 4, true>(va, bias, wsig, sig2, mask[4], rs, nullptr);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 192, va);
+    trunk_group<RELU, SIGMA, SAVE, 5, true>(vb, bias, wsig, sig2, mask[5], rs, nullptr);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 224, vb);
+    trunk_group<RELU, SIGMA, SAVE, 6, true>(va, bias, wsig, sig2, mask[6], rs, nullptr);
+    tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, 7, true>(vb, bias, wsig, sig2, mask[7], rs, nullptr);
 }
 
 // one 32-column group of the ddir epilogue: + (bias + per-ray direction bias), ReLU, rgb head dot products
@@ -310,6 +330,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
         float* dbs = reinterpret_cast<float*>(smem + SM_DIRB) + s * (DIRB_ROWS * 128);   // staged per-ray ddir biases
         RowStore rs;
         rs.init(act_base, row);
+        const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;    // A tile hand-off, K-halves
+        const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;    // accumulator hand-off, N-halves
         uint32_t accf_par = 0;
         uint32_t E[32];     // bf16(enc), 64 channels packed
         uint32_t Elo[2];    // bf16 residuals of the raw x, y, z channels
@@ -366,40 +388,65 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                 named_bar_sync(1 + s, TILE_M);
                 if (elected) { bulk_s2g(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
             }
-            mbar_arrive(B.actr + 8 * s);
+            mbar_arrive(bar_lo);
+            mbar_arrive(bar_hi);
 
             float sig = 0.f;
             for (int ph = 0; ph < N_PHASES; ++ph) {
                 if (elected) trace_ev(P.trace, 2 + s, it, ph, 0);      // worker: starts waiting for the accumulator
-                mbar_wait(B.accf + 8 * s, accf_par, 2);
-                accf_par ^= 1;
+                mbar_wait(bar_h0, accf_par, 2);
                 tc_fence_after();
-                if (elected) trace_ev(P.trace, 2 + s, it, ph, 1);      // worker: accumulator ready
-                if (SAVE) {
-                    if (elected) bulk_wait_read0();
-                    named_bar_sync(1 + s, TILE_M);
-                }
+                if (elected) trace_ev(P.trace, 2 + s, it, ph, 1);      // worker: first accumulator half ready
                 if (ph == 5) {
                     // L5a done: stage the skip-connection encoding as K-blocks 0 (hi) and 1 (residual) for L5b
+                    mbar_wait(bar_h1, accf_par, 6);
+                    accf_par ^= 1;
+                    tc_fence_after();
+                    if (SAVE) {
+                        if (elected) bulk_wait_read0();
+                        named_bar_sync(1 + s, TILE_M);
+                    }
 #pragma unroll
                     for (int c = 0; c < 8; ++c) rs.store<0>(c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
                     rs.store<1>(0, Elo[0], Elo[1], 0u, 0u);
                     rs.store<1>(1, 0u, 0u, 0u, 0u);
                     tc_fence_before();
                     fence_proxy_async_smem();
-                    mbar_arrive(B.actr + 8 * s);
+                    mbar_arrive(bar_lo);
+                    mbar_arrive(bar_hi);
                     continue;
                 }
                 if (ph < 10) {
-                    // trunk layer / feature epilogue: bias (+ReLU) -> bf16 -> next A tile
+                    // trunk layer / feature epilogue: bias (+ReLU) -> bf16 -> next A tile, in two column halves
                     const int layer = (ph <= 4) ? ph : (ph == 6 ? 5 : (ph == 7 ? 6 : (ph == 8 ? 7 : 8)));
                     const float* bias = side + (layer < 8 ? SIDE_BIAS + layer * H : SIDE_BFEAT);
                     const bool relu = layer < 8;
-                    uint32_t mask[8];
                     const float* wsig = side + SIDE_WSIG;
-                    if (ph == 8) trunk_epilogue<true, true, SAVE>(t_lane, bias, wsig, sig, mask, rs);
-                    else if (relu) trunk_epilogue<true, false, SAVE>(t_lane, bias, wsig, sig, mask, rs);
-                    else trunk_epilogue<false, false, SAVE>(t_lane, bias, wsig, sig, mask, rs);
+                    uint32_t mask[8];
+                    uint32_t held[64];
+                    uint64_t sig2 = 0ull;
+                    if (ph == 8) trunk_part1<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held);
+                    else if (relu) trunk_part1<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held);
+                    else trunk_part1<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held);
+                    mbar_wait(bar_h1, accf_par, 6);                    // every MMA of the phase is complete
+                    accf_par ^= 1;
+                    tc_fence_after();
+                    if (SAVE) {
+                        if (elected) bulk_wait_read0();
+                        named_bar_sync(1 + s, TILE_M);
+                    }
+                    store_held(rs, held);
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    mbar_arrive(bar_lo);                               // next phase may start on K-blocks 0,1
+                    if (ph == 8) trunk_part2<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
+                    else if (relu) trunk_part2<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
+                    else trunk_part2<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
+                    if (ph == 8) {
+                        float a, b;
+                        f2_unpack(sig2, a, b);
+                        sig = a + b;
+                    }
                     tc_fence_before();
                     fence_proxy_async_smem();
                     if (SAVE) {
@@ -416,9 +463,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                         }
                     }
                     if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);  // worker: epilogue done
-                    mbar_arrive(B.actr + 8 * s);
+                    mbar_arrive(bar_hi);
                 } else {
                     // ddir epilogue: + (bias + per-ray direction bias), ReLU, rgb head (fp32), write preds
+                    mbar_wait(bar_h1, accf_par, 6);
+                    accf_par ^= 1;
+                    if (SAVE) {
+                        if (elected) bulk_wait_read0();
+                        named_bar_sync(1 + s, TILE_M);
+                    }
                     uint64_t r2 = 0ull, g2 = 0ull, b2 = 0ull;
                     uint32_t mask[4];
                     // staged copy lives in shared memory; ragged tiles with many short rays fall back to global

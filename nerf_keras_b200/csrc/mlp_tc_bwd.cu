@@ -80,10 +80,10 @@ struct BwdParams {
     uint8_t* dz_save;
 };
 
-// one 32-column group of a chain epilogue: optional sigma-head term, ReLU mask, bf16, swizzled store
-template <bool SIGMA, bool MASK, int CG>
+// one 32-column group of a chain epilogue: optional sigma-head term, ReLU mask, bf16; stored to the A tile or held
+template <bool SIGMA, bool MASK, int CG, bool STORE>
 __device__ __forceinline__ void chain_group(const uint32_t (&v)[32], float dsig, const float* wsig, uint32_t mk,
-                                            const RowStore& rs) {
+                                            const RowStore& rs, uint32_t* held) {
     uint32_t pk[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -98,28 +98,53 @@ __device__ __forceinline__ void chain_group(const uint32_t (&v)[32], float dsig,
         }
         pk[q] = cvt_bf16x2<false>(x0, x1);
     }
+    if (STORE) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
-        rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        for (int c = 0; c < 4; ++c)
+            rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) held[CG * 16 + q] = pk[q];
+    }
 }
 
+// columns 0..127 while the second N-half's MMAs are in flight: results held in registers
 template <bool SIGMA, bool MASK>
-__device__ __forceinline__ void chain_epilogue(uint32_t t_lane, float dsig, const float* wsig, const uint32_t (&mask)[8],
-                                               const RowStore& rs) {
+__device__ __forceinline__ void chain_part1(uint32_t t_lane, float dsig, const float* wsig, const uint32_t (&mask)[8],
+                                            const RowStore& rs, uint32_t (&held)[64]) {
+    uint32_t v[32];
+    tmem_ld32(t_lane, v); tmem_ld_wait();
+    chain_group<SIGMA, MASK, 0, false>(v, dsig, wsig, mask[0], rs, held);
+    tmem_ld32(t_lane + 32, v); tmem_ld_wait();
+    chain_group<SIGMA, MASK, 1, false>(v, dsig, wsig, mask[1], rs, held);
+    tmem_ld32(t_lane + 64, v); tmem_ld_wait();
+    chain_group<SIGMA, MASK, 2, false>(v, dsig, wsig, mask[2], rs, held);
+    tmem_ld32(t_lane + 96, v); tmem_ld_wait();
+    chain_group<SIGMA, MASK, 3, false>(v, dsig, wsig, mask[3], rs, held);
+}
+__device__ __forceinline__ void store_held(const RowStore& rs, const uint32_t (&held)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) rs.store<0>(c, held[4 * c], held[4 * c + 1], held[4 * c + 2], held[4 * c + 3]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) rs.store<1>(c, held[32 + 4 * c], held[32 + 4 * c + 1], held[32 + 4 * c + 2], held[32 + 4 * c + 3]);
+}
+// columns 128..255 straight into K-blocks 2,3
+template <bool SIGMA, bool MASK>
+__device__ __forceinline__ void chain_part2(uint32_t t_lane, float dsig, const float* wsig, const uint32_t (&mask)[8],
+                                            const RowStore& rs) {
     uint32_t va[32], vb[32];
-    tmem_ld32(t_lane, va);
-#define NERF_CHAIN_PAIR(CG)                                                    \
-    tmem_ld_wait();                                                            \
-    tmem_ld32(t_lane + (CG + 1) * 32, vb);                                     \
-    chain_group<SIGMA, MASK, CG>(va, dsig, wsig, mask[CG], rs);                \
-    tmem_ld_wait();                                                            \
-    if (CG + 2 < 8) tmem_ld32(t_lane + (CG + 2) * 32, va);                     \
-    chain_group<SIGMA, MASK, CG + 1>(vb, dsig, wsig, mask[CG + 1], rs);
-    NERF_CHAIN_PAIR(0)
-    NERF_CHAIN_PAIR(2)
-    NERF_CHAIN_PAIR(4)
-    NERF_CHAIN_PAIR(6)
-#undef NERF_CHAIN_PAIR
+    tmem_ld32(t_lane + 128, va);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 160, vb);
+    chain_group<SIGMA, MASK, 4, true>(va, dsig, wsig, mask[4], rs, nullptr);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 192, va);
+    chain_group<SIGMA, MASK, 5, true>(vb, dsig, wsig, mask[5], rs, nullptr);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 224, vb);
+    chain_group<SIGMA, MASK, 6, true>(va, dsig, wsig, mask[6], rs, nullptr);
+    tmem_ld_wait();
+    chain_group<SIGMA, MASK, 7, true>(vb, dsig, wsig, mask[7], rs, nullptr);
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const BwdParams P) {
@@ -155,6 +180,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
         const bool elected = (row == 0);
         RowStore rs;
         rs.init(act_base, row);
+        const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;    // A tile hand-off, K-halves
+        const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;    // accumulator hand-off, N-halves
         uint32_t accf_par = 0;
 
         for (int it = 0; it < my_pairs; ++it) {
@@ -205,34 +232,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
                 bulk_s2g(dz_tile + DZ_HEAD, act_base + 2 * 16384, 16384);
                 bulk_commit();
             }
-            mbar_arrive(B.actr + 8 * s);
+            mbar_arrive(bar_lo);
+            mbar_arrive(bar_hi);
 
             for (int ph = 0; ph < B_PHASES; ++ph) {
-                mbar_wait(B.accf + 8 * s, accf_par, 2);
-                accf_par ^= 1;
-                tc_fence_after();
-                if (elected) bulk_wait_read0();
-                named_bar_sync(1 + s, TILE_M);
                 int64_t dst;
                 uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (ph == 0) {
-                    dst = DZ_FEAT;                                   // feature layer is linear: no mask
-                    chain_epilogue<false, false>(t_lane, 0.f, side + SIDE_WSIG, mask, rs);
-                } else {
-                    const int ml = (ph == 1) ? 7 : (8 - ph);         // mask of the ReLU output feeding this grad: h8 .. h1
+                int ml = -1;
+                if (ph == 0) dst = DZ_FEAT;                          // feature layer is linear: no mask
+                else {
+                    ml = (ph == 1) ? 7 : (8 - ph);                   // ReLU output feeding this gradient: h8 .. h1
                     const uint4* mp = reinterpret_cast<const uint4*>(mask_tile + ((size_t)ml * 128 + row) * 8);
                     const uint4 m0 = mp[0], m1 = mp[1];
                     mask[0] = m0.x; mask[1] = m0.y; mask[2] = m0.z; mask[3] = m0.w;
                     mask[4] = m1.x; mask[5] = m1.y; mask[6] = m1.z; mask[7] = m1.w;
                     dst = DZ_Z + (int64_t)65536 * ml;
-                    if (ph == 1) chain_epilogue<true, true>(t_lane, dp.w, side + SIDE_WSIG, mask, rs);
-                    else chain_epilogue<false, true>(t_lane, 0.f, side + SIDE_WSIG, mask, rs);
                 }
+                const float* wsig = side + SIDE_WSIG;
+                uint32_t held[64];
+                mbar_wait(bar_h0, accf_par, 2);
+                tc_fence_after();
+                if (ph == 0) chain_part1<false, false>(t_lane, 0.f, wsig, mask, rs, held);
+                else if (ph == 1) chain_part1<true, true>(t_lane, dp.w, wsig, mask, rs, held);
+                else chain_part1<false, true>(t_lane, 0.f, wsig, mask, rs, held);
+                mbar_wait(bar_h1, accf_par, 6);                      // every MMA of the phase is complete
+                accf_par ^= 1;
+                tc_fence_after();
+                if (elected) bulk_wait_read0();                      // previous image store has finished reading the tile
+                named_bar_sync(1 + s, TILE_M);
+                store_held(rs, held);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                if (ph < B_PHASES - 1) mbar_arrive(bar_lo);
+                if (ph == 0) chain_part2<false, false>(t_lane, 0.f, wsig, mask, rs);
+                else if (ph == 1) chain_part2<true, true>(t_lane, dp.w, wsig, mask, rs);
+                else chain_part2<false, true>(t_lane, 0.f, wsig, mask, rs);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 named_bar_sync(1 + s, TILE_M);
                 if (elected) { bulk_s2g(dz_tile + dst, act_base, 65536); bulk_commit(); }
-                if (ph < B_PHASES - 1) mbar_arrive(B.actr + 8 * s);
+                if (ph < B_PHASES - 1) mbar_arrive(bar_hi);
             }
         }
         if (elected) bulk_wait_all0();

@@ -53,9 +53,9 @@ constexpr int SM_SIDE = SM_RING + STAGES * CHUNK_BYTES;    // 12320
 constexpr int SM_BAR = SM_SIDE + SIDE_FLOATS * 4;
 constexpr int SM_FULL = SM_BAR;                            // STAGES mbarriers
 constexpr int SM_EMPTY = SM_FULL + 8 * STAGES;             // STAGES
-constexpr int SM_ACCF = SM_EMPTY + 8 * STAGES;             // 2
-constexpr int SM_ACTR = SM_ACCF + 16;                      // 2
-constexpr int SM_TMEM = SM_ACTR + 16;                      // u32
+constexpr int SM_ACCF = SM_EMPTY + 8 * STAGES;             // 2 sub-tiles x 2 N-halves
+constexpr int SM_ACTR = SM_ACCF + 32;                      // 2 sub-tiles x 2 K-halves
+constexpr int SM_TMEM = SM_ACTR + 32;                      // u32
 constexpr int DIRB_ROWS = 5;                               // staged per-ray ddir biases per sub-tile (N >= 32 always fits)
 constexpr int SM_DIRB = SM_TMEM + 16;                      // 2 x DIRB_ROWS x 128 floats
 constexpr int SM_TOTAL = SM_DIRB + 2 * DIRB_ROWS * 512;
@@ -129,9 +129,9 @@ __device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B) {
             mbar_init(B.full + 8 * i, 1);
             mbar_init(B.empty + 8 * i, 2);   // one tcgen05.commit per sub-tile
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(B.accf + 8 * s, 1);
-            mbar_init(B.actr + 8 * s, TILE_M);
+        for (int i = 0; i < 4; ++i) {                 // index = sub-tile * 2 + half
+            mbar_init(B.accf + 8 * i, 1);
+            mbar_init(B.actr + 8 * i, TILE_M);
         }
         fence_barrier_init();
     }
@@ -151,20 +151,19 @@ __device__ __forceinline__ void producer_loop(uint32_t base, const Barriers& B, 
     }
 }
 
-// ---- MMA issuers: one dedicated thread per sub-tile ------------------------------------------------
-// Each issuer walks the chunk program for its own sub-tile: wait for the sub-tile's A tile at a phase
-// start, wait for the weight chunk, issue the K=16 MMAs, release the ring slot with tcgen05.commit
-// (a slot is recycled when BOTH sub-tiles' commits have arrived), and commit the accumulator barrier at
-// the end of a phase.  The tensor pipe executes the two instruction streams in arrival order, so one
-// sub-tile's MMAs fill the gaps left by the other's epilogue.
-// optional timeline trace (block 0 only): records (tag, clock) pairs; tag = who * 1000 + tile * 100 + phase * 4 + event
+// optional timeline trace (block 0 only): trace[((who * 3 + tile) * 16 + phase) * 4 + event] = clock64()
 __device__ __forceinline__ void trace_ev(long long* trace, int who, int tile, int ph, int ev) {
-    if (trace && blockIdx.x == 0 && tile < 3) {
-        const int idx = ((who * 3 + tile) * 16 + ph) * 4 + ev;
-        trace[idx] = clock64();
-    }
+    if (trace && blockIdx.x == 0 && tile < 3) trace[((who * 3 + tile) * 16 + ph) * 4 + ev] = clock64();
 }
 
+// ---- MMA issuers: one dedicated thread per sub-tile ------------------------------------------------
+// Each issuer walks the chunk program for its own sub-tile: wait for the weight chunk, issue the K=16 MMAs,
+// release the ring slot with tcgen05.commit (a slot is recycled when BOTH sub-tiles' commits have arrived).
+// Hand-offs with the sub-tile's workers are split in halves so that epilogue and MMA overlap:
+//   * the A tile is released in two K-halves: actr[lo] (K-blocks 0,1) gates the first chunk of a phase,
+//     actr[hi] (K-blocks 2,3) gates k-block kbs/2 of the first N-half;
+//   * the accumulator is handed over in two N-halves: accf[h0] after the last chunk of columns 0..127,
+//     accf[h1] at the end of the phase (phases with a single N-half commit both at the end).
 __device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, uint32_t tmem_base, const Program& prog,
                                             int s, int n_tiles, long long* trace = nullptr) {
     const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
@@ -174,18 +173,22 @@ __device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, ui
     const uint32_t a_tile = ((base + SM_ACT + s * 65536) & 0x3FFFF) >> 4;
     const uint32_t ring0 = ((base + SM_RING) & 0x3FFFF) >> 4;
     const uint32_t d_base = tmem_base + s * 256;
+    const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;
+    const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;
     const int n_phases = prog.n_phases;
     int slot = 0;
     uint32_t ring_par = 0, actr_par = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
         for (int ph = 0; ph < n_phases; ++ph) {
             const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
+            const int hi_kb = (kbs >= 4) ? (kbs >> 1) : 0;
             trace_ev(trace, s, tile, ph, 0);              // issuer: starts waiting for the A tile
-            mbar_wait(B.actr + 8 * s, actr_par, 3);
-            actr_par ^= 1;
-            trace_ev(trace, s, tile, ph, 1);              // issuer: A tile ready
+            mbar_wait(bar_lo, actr_par, 3);
+            if (hi_kb == 0) mbar_wait(bar_hi, actr_par, 5);
+            trace_ev(trace, s, tile, ph, 1);              // issuer: A tile (first half) ready
             int h = 0, kb = 0;
             for (int j = 0; j < n_ch; ++j) {
+                if (h == 0 && kb == hi_kb && hi_kb != 0) mbar_wait(bar_hi, actr_par, 5);
                 mbar_wait(B.full + 8 * slot, ring_par, 4);
                 tc_fence_after();
                 const uint32_t a_lo = (a_tile + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
@@ -203,9 +206,15 @@ __device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, ui
                 }
                 mma_commit(B.empty + 8 * slot);
                 if (++slot == STAGES) { slot = 0; ring_par ^= 1; }
-                if (++kb == kbs) { kb = 0; ++h; }
+                if (++kb == kbs) {
+                    kb = 0;
+                    if (h == 0 && j + 1 < n_ch) mma_commit(bar_h0);   // columns 0..127 complete, second half follows
+                    ++h;
+                }
             }
-            mma_commit(B.accf + 8 * s);
+            if (n_ch == kbs) mma_commit(bar_h0);          // single N-half: hand over both barriers at the end
+            mma_commit(bar_h1);
+            actr_par ^= 1;
             trace_ev(trace, s, tile, ph, 2);              // issuer: all MMAs of the phase issued
         }
     }
