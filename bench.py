@@ -243,7 +243,8 @@ def main():
             dst.copy_(src, non_blocking=True)
         img, o, d, t, u = stage
         if args.mode == "train":
-            return trainer.train_step((img, (o, d, t)), u_pdf=u)  # reads the 3 metric floats back (D2H)
+            logs = trainer.train_step((img, (o, d, t)), u_pdf=u)
+            return float(logs["loss"]), float(logs["psnr"]), float(logs["loss_coarse"])  # D2H read of the step's metrics
         rgb = trainer.forward_pass(o, d, t, u_pdf=u)[0][1]
         rgb_host.copy_(rgb, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -22,46 +22,80 @@ struct Pose3x4 {
     float t[3];
 };
 
-__device__ __forceinline__ float ray_dir_component(int64_t pix, int comp, int width, float half_w, float half_h,
-                                                   float focal, const Pose3x4& P) {
-    int h = (int)(pix / width);
-    int w = (int)(pix - (int64_t)h * width);
-    float tu = __fdiv_rn(__fsub_rn((float)w, half_w), focal);   // (u - W*0.5) / focal
-    float tv = __fdiv_rn(__fsub_rn((float)h, half_h), focal);   // (v - H*0.5) / focal
-    float dc0 = tu, dc1 = -tv, dc2 = -1.0f;
-    // camera_dirs = dirs[..., None, :] * R ; reduce over last axis in index order, no FMA
-    float p0 = __fmul_rn(dc0, P.r[comp][0]);
-    float p1 = __fmul_rn(dc1, P.r[comp][1]);
-    float p2 = __fmul_rn(dc2, P.r[comp][2]);
-    return __fadd_rn(__fadd_rn(p0, p1), p2);
+// direction of pixel (h, w): three separately rounded products, reduced left to right (no FMA)
+__device__ __forceinline__ void ray_dir_pixel(int h, int w, float half_w, float half_h, float focal, const Pose3x4& P,
+                                              float (&out)[3]) {
+    const float tu = __fdiv_rn(__fsub_rn((float)w, half_w), focal);   // (u - W*0.5) / focal
+    const float tv = __fdiv_rn(__fsub_rn((float)h, half_h), focal);   // (v - H*0.5) / focal
+    const float dc0 = tu, dc1 = -tv, dc2 = -1.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        out[i] = __fadd_rn(__fadd_rn(__fmul_rn(dc0, P.r[i][0]), __fmul_rn(dc1, P.r[i][1])), __fmul_rn(dc2, P.r[i][2]));
 }
 
+// One thread computes 4 consecutive pixels (12 floats).  The block's 256 x 12 floats are staged in shared memory
+// so that the global stores are fully coalesced float4 writes (thread i writes float4 i, i+256, i+512 of the
+// block's contiguous 12 KB span); origins are a repeating 3-float4 pattern and need no staging.
 __global__ void __launch_bounds__(256) get_rays_kernel(int width, int64_t n_pix, float half_w, float half_h,
                                                        float focal, Pose3x4 P, float* __restrict__ o,
                                                        float* __restrict__ d) {
-    const int64_t n_el = n_pix * 3;
-    const int64_t n_vec = n_el >> 2;
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x) {
-        int64_t e0 = v << 2;
-        int64_t pix = e0 / 3;
-        int comp = (int)(e0 - pix * 3);
-        float od[4], dd[4];
+    __shared__ float4 stage[256 * 3];
+    const int64_t n_grp = n_pix >> 2;
+    const float4 opat[3] = {make_float4(P.t[0], P.t[1], P.t[2], P.t[0]), make_float4(P.t[1], P.t[2], P.t[0], P.t[1]),
+                            make_float4(P.t[2], P.t[0], P.t[1], P.t[2])};
+    float p2[3];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            od[k] = P.t[comp];
-            dd[k] = ray_dir_component(pix, comp, width, half_w, half_h, focal, P);
-            if (++comp == 3) { comp = 0; ++pix; }
+    for (int i = 0; i < 3; ++i) p2[i] = __fmul_rn(-1.0f, P.r[i][2]);
+    for (int64_t g0 = (int64_t)blockIdx.x * 256; g0 < n_grp; g0 += (int64_t)gridDim.x * 256) {
+        const int64_t g = g0 + threadIdx.x;
+        if (g < n_grp) {
+            const int64_t pix0 = g << 2;
+            int h = (int)(pix0 / width);
+            int w = (int)(pix0 - (int64_t)h * width);
+            float v[12];
+            // the row term -tv * R[i][1] and the constant -R[i][2] are shared by the pixels of a row (same roundings
+            // as evaluating them per pixel); only tu = (w - W/2) / focal changes along the row
+            float p1[3];
+            int h_cached = -1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (h != h_cached) {
+                    const float ntv = -__fdiv_rn(__fsub_rn((float)h, half_h), focal);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) p1[i] = __fmul_rn(ntv, P.r[i][1]);
+                    h_cached = h;
+                }
+                const float tu = __fdiv_rn(__fsub_rn((float)w, half_w), focal);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) v[3 * k + i] = __fadd_rn(__fadd_rn(__fmul_rn(tu, P.r[i][0]), p1[i]), p2[i]);
+                if (++w == width) { w = 0; ++h; }
+            }
+            stage[threadIdx.x * 3] = make_float4(v[0], v[1], v[2], v[3]);
+            stage[threadIdx.x * 3 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+            stage[threadIdx.x * 3 + 2] = make_float4(v[8], v[9], v[10], v[11]);
         }
-        reinterpret_cast<float4*>(o)[v] = make_float4(od[0], od[1], od[2], od[3]);
-        reinterpret_cast<float4*>(d)[v] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        __syncthreads();
+        const int64_t n_valid = ((n_grp - g0) < 256 ? (n_grp - g0) : 256) * 3;   // float4s produced by this block
+        float4* dp = reinterpret_cast<float4*>(d) + g0 * 3;
+        float4* op = reinterpret_cast<float4*>(o) + g0 * 3;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int j = threadIdx.x + 256 * k;
+            if (j < n_valid) {
+                dp[j] = stage[j];
+                op[j] = opat[j % 3];
+            }
+        }
+        __syncthreads();
     }
-    // tail (n_el % 4 elements)
-    if (blockIdx.x == 0 && threadIdx.x < (n_el & 3)) {
-        int64_t e = (n_vec << 2) + threadIdx.x;
-        int64_t pix = e / 3;
-        int comp = (int)(e - pix * 3);
-        o[e] = P.t[comp];
-        d[e] = ray_dir_component(pix, comp, width, half_w, half_h, focal, P);
+    // tail (n_pix % 4 pixels)
+    if (blockIdx.x == 0 && threadIdx.x < (n_pix & 3)) {
+        const int64_t pix = (n_grp << 2) + threadIdx.x;
+        const int h = (int)(pix / width), w = (int)(pix - (int64_t)h * width);
+        float dd[3];
+        ray_dir_pixel(h, w, half_w, half_h, focal, P, dd);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { d[pix * 3 + i] = dd[i]; o[pix * 3 + i] = P.t[i]; }
     }
 }
 
@@ -77,7 +111,7 @@ extern "C" int nerf_get_rays(int height, int width, float focal, const float* po
     // `width * 0.5` is a Python float (double) that TF converts to float32 when it meets the f32 tensor
     float half_w = (float)((double)width * 0.5), half_h = (float)((double)height * 0.5);
     int threads = 256;
-    int grid = stream_grid(ceil_div(n_pix * 3, 4), threads);
+    int grid = stream_grid(ceil_div(n_pix, 4), threads);
     get_rays_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(width, n_pix, half_w, half_h, focal, P, o, d);
     NERF_LAUNCHED();
     return NERF_OK;
@@ -135,7 +169,23 @@ __global__ void __launch_bounds__(256) t_vals_kernel(float near_f, float far_f, 
     const float delta = (N > 1) ? __fdiv_rn(__fsub_rn(far_f, near_f), (float)(N - 1)) : 0.0f;
     const float fN = (float)N;
     const int64_t n_el = B * N;
-    if ((N & 3) == 0) {
+    if ((N & 3) == 0 && !u_per_ray && (blockDim.x % (N >> 2)) == 0) {
+        // every ray gets the same row (the reference's single shared jitter vector, Q1): a thread always writes the
+        // same column group, so its float4 is computed once and the kernel is a pure streaming store
+        const int gpr = N >> 2;                          // float4 groups per row
+        const int cg = threadIdx.x % gpr;
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float x = tval_at(cg * 4 + k, N, near_f, far_f, delta);
+            if (u) x = __fadd_rn(x, __fdiv_rn(__fmul_rn(u[cg * 4 + k], range_f), fN));
+            r[k] = x;
+        }
+        const float4 val = make_float4(r[0], r[1], r[2], r[3]);
+        const int64_t n_vec = n_el >> 2;
+        for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * blockDim.x)
+            reinterpret_cast<float4*>(t)[v] = val;       // (grid stride is a multiple of gpr: column group is invariant)
+    } else if ((N & 3) == 0) {
         const int64_t n_vec = n_el >> 2;
         for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_vec;
              v += (int64_t)gridDim.x * blockDim.x) {
@@ -262,6 +312,8 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// forward compositing only needs sigmoid to ~1e-6 absolute (rgb tolerance 1e-5): ex2.approx based exp + fast divide
+__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __global__ void __launch_bounds__(256) volume_render_kernel(const float4* __restrict__ preds,
                                                             const float* __restrict__ t, int64_t B, int N,
@@ -274,30 +326,39 @@ __global__ void __launch_bounds__(256) volume_render_kernel(const float4* __rest
         const float* tt = t + ray * N;
         float carry = 1.0f;  // exclusive transmittance entering this chunk
         float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+        // software prefetch of the next chunk keeps two 512-byte pred loads in flight per warp
+        float4 pr = (lane < N) ? p[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float tn = (lane < N) ? tt[lane] : 0.f;
         for (int base = 0; base < N; base += 32) {
-            int n = base + lane;
-            bool ok = n < N;
-            float4 pr = ok ? p[n] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float tn = ok ? tt[n] : 0.f;
-            float tn1 = (n + 1 < N) ? tt[n + 1] : 0.f;
-            float delta = (n == N - 1) ? 1e10f : (tn1 - tn);
-            float sigma = fmaxf(pr.w, 0.0f);
-            float alpha = 1.0f - expf(-sigma * delta);
-            float x = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
-            float incl = warp_incl_scan_mul(x, lane);
+            const int n = base + lane;
+            const bool ok = n < N;
+            const int nn = n + 32;
+            const float4 pr_next = (nn < N) ? p[nn] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float tn_next = (nn < N) ? tt[nn] : 0.f;
+            // t[n+1]: neighbour lane, or lane 0 of the next chunk for lane 31
+            float tn1 = __shfl_down_sync(0xffffffffu, tn, 1);
+            const float t_first_next = __shfl_sync(0xffffffffu, tn_next, 0);
+            if (lane == 31) tn1 = t_first_next;
+            const float delta = (n == N - 1) ? 1e10f : (tn1 - tn);
+            const float sigma = fmaxf(pr.w, 0.0f);
+            const float alpha = 1.0f - expf(-sigma * delta);
+            const float x = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
+            const float incl = warp_incl_scan_mul(x, lane);
             float excl = __shfl_up_sync(0xffffffffu, incl, 1);
             if (lane == 0) excl = 1.0f;
-            float T = carry * excl;
-            float w = ok ? alpha * T : 0.f;
+            const float T = carry * excl;
+            const float w = ok ? alpha * T : 0.f;
             carry *= __shfl_sync(0xffffffffu, incl, 31);
             if (ok) {
                 if (weights) weights[ray * N + n] = w;
-                sr += w * sigmoidf_acc(pr.x);
-                sg += w * sigmoidf_acc(pr.y);
-                sb += w * sigmoidf_acc(pr.z);
-                sd += w * tn;
+                sr = fmaf(w, sigmoidf_fast(pr.x), sr);
+                sg = fmaf(w, sigmoidf_fast(pr.y), sg);
+                sb = fmaf(w, sigmoidf_fast(pr.z), sb);
+                sd = fmaf(w, tn, sd);
                 sa += w;
             }
+            pr = pr_next;
+            tn = tn_next;
         }
         sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
         if (lane == 0) {

@@ -67,11 +67,14 @@ class MeanSquaredError:
 
 
 class _Mean:
+    """keras.metrics.Mean stand-in.  Values may be 0-d CUDA tensors: they are accumulated on the device and only
+    read back (one synchronisation) when `result()` is converted to a Python number."""
+
     def __init__(self, name):
         self.name, self.total, self.count = name, 0.0, 0
 
     def update_state(self, v):
-        self.total += float(v)
+        self.total = self.total + v
         self.count += 1
 
     def result(self):
@@ -370,8 +373,7 @@ class NeRFTrainer:
             world = allreduce_sum_(self._ctx.grad_tensor(), self.process_group)
             scale = 1.0 / world
         _lib.check(L.nerf_adam_step(self._ctx.handle, scale, _stream()), "adam_step")
-        m = metrics.cpu().numpy()
-        return self._update_metrics(m)
+        return self._update_metrics(metrics)     # stays on the device: no host synchronisation inside the step
 
     def test_step(self, inputs, u_pdf=None):
         """models.py:122-145."""
@@ -381,7 +383,7 @@ class NeRFTrainer:
         metrics = torch.empty((3,), device=images.device, dtype=torch.float32)
         _lib.check(_lib.lib().nerf_metrics(_ptr(images), _ptr(rgbs[0]), _ptr(rgbs[1]), images.shape[0], _ptr(metrics),
                                            _stream()), "test_step")
-        return self._update_metrics(metrics.cpu().numpy())
+        return self._update_metrics(metrics)
 
     def _update_metrics(self, m):
         self.loss_coarse_tracker.update_state(m[0])
@@ -399,17 +401,17 @@ class NeRFTrainer:
             for batch in train_ds:
                 logs = self.train_step(batch)
             for k in ("loss", "psnr", "loss_coarse"):
-                history[k].append(logs.get(k))
+                history[k].append(float(logs[k]) if k in logs else None)
             if validation_data is not None:
                 self.reset_metrics()
                 vlogs = {}
                 for batch in validation_data:
                     vlogs = self.test_step(batch)
-                history["val_loss"].append(vlogs.get("loss"))
-                history["val_psnr"].append(vlogs.get("psnr"))
+                history["val_loss"].append(float(vlogs["loss"]) if "loss" in vlogs else None)
+                history["val_psnr"].append(float(vlogs["psnr"]) if "psnr" in vlogs else None)
                 logs = dict(logs, val_loss=vlogs.get("loss"), val_psnr=vlogs.get("psnr"))
             if verbose:
-                print(f"Epoch {epoch + 1}/{epochs} " + " ".join(f"{k}: {v:.5f}" for k, v in logs.items() if v is not None))
+                print(f"Epoch {epoch + 1}/{epochs} " + " ".join(f"{k}: {float(v):.5f}" for k, v in logs.items() if v is not None))
             for cb in callbacks or []:
                 cb.on_epoch_end(epoch, logs)
         return history

@@ -121,7 +121,7 @@ def test_train_step_metrics_and_coarse_grads(nk):
     g = load_golden("lego_small")
     wc, wf = golden_weights(g)
     tr = _trainer(nk, g, wc, wf)
-    m = tr.train_step((g["img"], (g["o"], g["d"], g["t"])), u_pdf=g["u_pdf"])
+    m = {k: float(v) for k, v in tr.train_step((g["img"], (g["o"], g["d"], g["t"])), u_pdf=g["u_pdf"]).items()}
     # the coarse net sees identical inputs; the fine net's sample positions are re-drawn through the
     # ill-conditioned inverse CDF from bf16 coarse weights, so its loss is compared loosely
     assert abs(m["loss_coarse"] - float(g["metrics"][0])) <= 2e-3 * max(1.0, float(g["metrics"][0]))
@@ -155,10 +155,11 @@ def test_training_reduces_loss_like_the_oracle(nk):
     wc, wf = golden_weights(g)
     tr = _trainer(nk, g, wc, wf)
     batch = (g["img"], (g["o"], g["d"], g["t"]))
-    first = tr.train_step(batch, u_pdf=g["u_pdf"])
+    fl = lambda logs: {k: float(v) for k, v in logs.items()}
+    first = fl(tr.train_step(batch, u_pdf=g["u_pdf"]))
     tr.reset_metrics()
     for _ in range(40):
-        last = tr.train_step(batch, u_pdf=g["u_pdf"])
+        last = fl(tr.train_step(batch, u_pdf=g["u_pdf"]))
         tr.reset_metrics()
     assert last["loss_coarse"] < 0.6 * first["loss_coarse"], (first, last)
     assert last["loss"] < 0.8 * first["loss"], (first, last)
