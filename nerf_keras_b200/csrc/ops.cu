@@ -315,29 +315,42 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + e
 // forward compositing only needs sigmoid to ~1e-6 absolute (rgb tolerance 1e-5): ex2.approx based exp + fast divide
 __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
+// NCH = number of 32-sample chunks per ray, held entirely in registers; the NEXT ray's chunks are loaded before the
+// current ray is processed, so each warp keeps two rays (2 * N * 20 bytes) in flight -- compositing is latency-
+// bound on HBM otherwise (one 640-byte chunk in flight per warp caps the kernel near 3.5 TB/s).
+template <int NCH>
 __global__ void __launch_bounds__(256) volume_render_kernel(const float4* __restrict__ preds,
                                                             const float* __restrict__ t, int64_t B, int N,
                                                             float* __restrict__ rgb, float* __restrict__ depth,
                                                             float* __restrict__ weights, float* __restrict__ acc) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < B; ray += warps_total) {
-        const float4* p = preds + ray * N;
-        const float* tt = t + ray * N;
+    int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float4 cp[NCH], np_[NCH];
+    float ct[NCH], nt[NCH];
+    auto load = [&](int64_t r, float4 (&p)[NCH], float (&tt)[NCH]) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int n = c * 32 + lane;
+            const bool ok = (r < B) && (n < N);
+            p[c] = ok ? __ldg(preds + r * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tt[c] = ok ? __ldg(t + r * N + n) : 0.f;
+        }
+    };
+    load(ray, cp, ct);
+    for (; ray < B; ray += warps_total) {
+        load(ray + warps_total, np_, nt);
         float carry = 1.0f;  // exclusive transmittance entering this chunk
         float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
-        // software prefetch of the next chunk keeps two 512-byte pred loads in flight per warp
-        float4 pr = (lane < N) ? p[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float tn = (lane < N) ? tt[lane] : 0.f;
-        for (int base = 0; base < N; base += 32) {
-            const int n = base + lane;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int n = c * 32 + lane;
             const bool ok = n < N;
-            const int nn = n + 32;
-            const float4 pr_next = (nn < N) ? p[nn] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float tn_next = (nn < N) ? tt[nn] : 0.f;
+            const float4 pr = cp[c];
+            const float tn = ct[c];
             // t[n+1]: neighbour lane, or lane 0 of the next chunk for lane 31
             float tn1 = __shfl_down_sync(0xffffffffu, tn, 1);
-            const float t_first_next = __shfl_sync(0xffffffffu, tn_next, 0);
+            const float t_first_next = __shfl_sync(0xffffffffu, ct[(c + 1 < NCH) ? c + 1 : c], 0);
             if (lane == 31) tn1 = t_first_next;
             const float delta = (n == N - 1) ? 1e10f : (tn1 - tn);
             const float sigma = fmaxf(pr.w, 0.0f);
@@ -357,8 +370,6 @@ __global__ void __launch_bounds__(256) volume_render_kernel(const float4* __rest
                 sd = fmaf(w, tn, sd);
                 sa += w;
             }
-            pr = pr_next;
-            tn = tn_next;
         }
         sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
         if (lane == 0) {
@@ -366,17 +377,30 @@ __global__ void __launch_bounds__(256) volume_render_kernel(const float4* __rest
             if (depth) depth[ray] = sd;
             if (acc) acc[ray] = sa;
         }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) { cp[c] = np_[c]; ct[c] = nt[c]; }
     }
 }
 
 extern "C" int nerf_volume_render(const float* preds, const float* t, int64_t batch, int num_samples, float* rgb,
                                   float* depth, float* weights, float* acc, void* stream) {
     NERF_CHECK_ARG(preds && t && batch >= 0 && num_samples >= 1, "bad arguments");
+    NERF_CHECK_ARG(num_samples <= 512, "num_samples > 512 is not supported by the compositing kernel");
     if (batch == 0) return NERF_OK;
-    int threads = 256;
-    int grid = stream_grid(batch * 32, threads);
-    volume_render_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(preds), t, batch,
-                                                                     num_samples, rgb, depth, weights, acc);
+    const int threads = 256;
+    const int grid = stream_grid(batch * 32, threads);
+    const float4* p4 = reinterpret_cast<const float4*>(preds);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nch = (num_samples + 31) / 32;
+#define NERF_VR(K) volume_render_kernel<K><<<grid, threads, 0, st>>>(p4, t, batch, num_samples, rgb, depth, weights, acc)
+    if (nch <= 1) NERF_VR(1);
+    else if (nch == 2) NERF_VR(2);
+    else if (nch == 3) NERF_VR(3);
+    else if (nch == 4) NERF_VR(4);
+    else if (nch <= 6) NERF_VR(6);
+    else if (nch <= 8) NERF_VR(8);
+    else NERF_VR(16);
+#undef NERF_VR
     NERF_LAUNCHED();
     return NERF_OK;
 }
@@ -387,83 +411,94 @@ extern "C" int nerf_volume_render(const float* preds, const float* t, int64_t ba
 // and optionally d_delta (B,N) = dL/d(delta_n) (needed only for the Q5 path of the fine net).
 // Division-free reverse affine scan: R_n = g_{n+1} a_{n+1} + x_{n+1} R_{n+1}; dL/dx_n = T_n R_n.
 // ------------------------------------------------------------------------------------------------
+// Same register-resident / next-ray-prefetch structure as the forward kernel; the transmittances of the forward
+// sweep stay in registers for the reverse sweep.
+template <int NCH>
 __global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __restrict__ preds,
                                                                 const float* __restrict__ t,
                                                                 const float* __restrict__ d_rgb,
                                                                 const float* __restrict__ d_w_extra, int64_t B,
                                                                 int N, float4* __restrict__ d_preds,
                                                                 float* __restrict__ d_delta) {
-    extern __shared__ float smem_vr[];
     const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int chunks = (N + 31) >> 5;
-    // per warp: T[n] (chunks*32 floats)
-    float* Tbuf = smem_vr + (size_t)wib * chunks * 32;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < B; ray += warps_total) {
-        const float4* p = preds + ray * N;
-        const float* tt = t + ray * N;
-        const float dr = d_rgb[ray * 3], dg = d_rgb[ray * 3 + 1], db = d_rgb[ray * 3 + 2];
+    int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float4 cp[NCH], np_[NCH];
+    float ct[NCH], nt[NCH];
+    auto load = [&](int64_t r, float4 (&p)[NCH], float (&tt)[NCH]) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int n = c * 32 + lane;
+            const bool ok = (r < B) && (n < N);
+            p[c] = ok ? __ldg(preds + r * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tt[c] = ok ? __ldg(t + r * N + n) : 0.f;
+        }
+    };
+    load(ray, cp, ct);
+    for (; ray < B; ray += warps_total) {
+        load(ray + warps_total, np_, nt);
+        const float dr = __ldg(d_rgb + ray * 3), dg = __ldg(d_rgb + ray * 3 + 1), db = __ldg(d_rgb + ray * 3 + 2);
+        float Tc[NCH], dl[NCH];
         // forward sweep: transmittance
         float carry = 1.0f;
-        for (int c = 0; c < chunks; ++c) {
-            int n = c * 32 + lane;
-            bool ok = n < N;
-            float4 pr = ok ? p[n] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float tn = ok ? tt[n] : 0.f;
-            float tn1 = (n + 1 < N) ? tt[n + 1] : 0.f;
-            float delta = (n == N - 1) ? 1e10f : (tn1 - tn);
-            float sigma = fmaxf(pr.w, 0.0f);
-            float alpha = 1.0f - expf(-sigma * delta);
-            float x = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
-            float incl = warp_incl_scan_mul(x, lane);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int n = c * 32 + lane;
+            const bool ok = n < N;
+            const float tn = ct[c];
+            float tn1 = __shfl_down_sync(0xffffffffu, tn, 1);
+            const float t_first_next = __shfl_sync(0xffffffffu, ct[(c + 1 < NCH) ? c + 1 : c], 0);
+            if (lane == 31) tn1 = t_first_next;
+            const float delta = (n == N - 1) ? 1e10f : (tn1 - tn);
+            dl[c] = delta;
+            const float sigma = fmaxf(cp[c].w, 0.0f);
+            const float alpha = 1.0f - expf(-sigma * delta);
+            const float x = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
+            const float incl = warp_incl_scan_mul(x, lane);
             float excl = __shfl_up_sync(0xffffffffu, incl, 1);
             if (lane == 0) excl = 1.0f;
-            Tbuf[n] = carry * excl;
+            Tc[c] = carry * excl;
             carry *= __shfl_sync(0xffffffffu, incl, 31);
         }
-        __syncwarp();
         // reverse sweep: R_n = b_n + a_n R_{n+1}, with a_n = x_{n+1}, b_n = g_{n+1} alpha_{n+1}
-        float Rcarry = 0.0f;  // R entering from the right of this chunk (R of the first element of next chunk's left)
-        for (int c = chunks - 1; c >= 0; --c) {
-            int n = c * 32 + lane;
-            bool ok = n < N;
-            float4 pr = ok ? p[n] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float tn = ok ? tt[n] : 0.f;
-            float tn1 = (n + 1 < N) ? tt[n + 1] : 0.f;
-            float delta = (n == N - 1) ? 1e10f : (tn1 - tn);
-            float sigma = fmaxf(pr.w, 0.0f);
-            float e = expf(-sigma * delta);
-            float alpha = 1.0f - e;
-            float x = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
-            float cr = sigmoidf_acc(pr.x), cg = sigmoidf_acc(pr.y), cb = sigmoidf_acc(pr.z);
+        float Rcarry = 0.0f;
+#pragma unroll
+        for (int c = NCH - 1; c >= 0; --c) {
+            const int n = c * 32 + lane;
+            const bool ok = n < N;
+            const float4 pr = cp[c];
+            const float delta = dl[c];
+            const float sigma = fmaxf(pr.w, 0.0f);
+            const float e = expf(-sigma * delta);
+            const float alpha = 1.0f - e;
+            const float x = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
+            const float cr = sigmoidf_acc(pr.x), cg = sigmoidf_acc(pr.y), cb = sigmoidf_acc(pr.z);
             float g = dr * cr + dg * cg + db * cb;
             if (d_w_extra && ok) g += d_w_extra[ray * N + n];
             if (!ok) g = 0.f;
-            float galpha = ok ? g * alpha : 0.f;
-            // element n contributes the affine map f_n(R) = galpha_n + x_n * R  (maps R_n -> R_{n-1})
+            const float galpha = ok ? g * alpha : 0.f;
+            // element n contributes the affine map f_n(R) = galpha_n + x_n * R  (maps R_n -> R_{n-1});
             // suffix composition within the chunk (lanes to the right applied first)
-            float a = x, b = galpha;  // map for this lane
+            float a = x, b = galpha;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                float a2 = __shfl_down_sync(0xffffffffu, a, o);
-                float b2 = __shfl_down_sync(0xffffffffu, b, o);
-                if (lane + o < 32) {  // compose: this(.) after right(.)  => f(R) = b + a*(b2 + a2 R)
+                const float a2 = __shfl_down_sync(0xffffffffu, a, o);
+                const float b2 = __shfl_down_sync(0xffffffffu, b, o);
+                if (lane + o < 32) {  // f(R) = b + a * (b2 + a2 R)
                     b = b + a * b2;
                     a = a * a2;
                 }
             }
-            // inclusive suffix map of lanes [lane..31]; R_{n-1} = b + a * Rcarry.  We need R_n (exclusive):
-            float a_ex = __shfl_down_sync(0xffffffffu, a, 1);
-            float b_ex = __shfl_down_sync(0xffffffffu, b, 1);
-            float Rn = (lane == 31) ? Rcarry : (b_ex + a_ex * Rcarry);
-            float a0 = __shfl_sync(0xffffffffu, a, 0), b0 = __shfl_sync(0xffffffffu, b, 0);
-            float T = ok ? Tbuf[n] : 0.f;
-            float w = alpha * T;
-            float dLdx = T * Rn;
-            float dLdalpha = g * T - dLdx;
-            float dsig = dLdalpha * delta * e;
-            float ds_raw = (pr.w > 0.0f) ? dsig : 0.0f;
+            const float a_ex = __shfl_down_sync(0xffffffffu, a, 1);
+            const float b_ex = __shfl_down_sync(0xffffffffu, b, 1);
+            const float Rn = (lane == 31) ? Rcarry : (b_ex + a_ex * Rcarry);
+            const float a0 = __shfl_sync(0xffffffffu, a, 0), b0 = __shfl_sync(0xffffffffu, b, 0);
+            const float T = ok ? Tc[c] : 0.f;
+            const float w = alpha * T;
+            const float dLdx = T * Rn;
+            const float dLdalpha = g * T - dLdx;
+            const float dsig = dLdalpha * delta * e;
+            const float ds_raw = (pr.w > 0.0f) ? dsig : 0.0f;
             if (ok) {
                 d_preds[ray * N + n] =
                     make_float4(w * dr * cr * (1.0f - cr), w * dg * cg * (1.0f - cg), w * db * cb * (1.0f - cb), ds_raw);
@@ -471,22 +506,32 @@ __global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __
             }
             Rcarry = b0 + a0 * Rcarry;
         }
-        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) { cp[c] = np_[c]; ct[c] = nt[c]; }
     }
 }
 
 extern "C" int nerf_volume_render_bwd(const float* preds, const float* t, const float* d_rgb, const float* d_w_extra,
                                       int64_t batch, int num_samples, float* d_preds, float* d_delta, void* stream) {
     NERF_CHECK_ARG(preds && t && d_rgb && d_preds && batch >= 0 && num_samples >= 1, "bad arguments");
+    NERF_CHECK_ARG(num_samples <= 512, "num_samples > 512 is not supported by the compositing kernel");
     if (batch == 0) return NERF_OK;
-    int threads = 256;
-    int chunks = (num_samples + 31) / 32;
-    size_t smem = (size_t)(threads / 32) * chunks * 32 * sizeof(float);
-    NERF_CHECK_ARG(smem <= 48 * 1024, "num_samples too large");
-    int grid = stream_grid(batch * 32, threads);
-    volume_render_bwd_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(preds), t, d_rgb, d_w_extra, batch, num_samples,
-        reinterpret_cast<float4*>(d_preds), d_delta);
+    const int threads = 256;
+    const int grid = stream_grid(batch * 32, threads);
+    const float4* p4 = reinterpret_cast<const float4*>(preds);
+    float4* dp4 = reinterpret_cast<float4*>(d_preds);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nch = (num_samples + 31) / 32;
+#define NERF_VRB(K) \
+    volume_render_bwd_kernel<K><<<grid, threads, 0, st>>>(p4, t, d_rgb, d_w_extra, batch, num_samples, dp4, d_delta)
+    if (nch <= 1) NERF_VRB(1);
+    else if (nch == 2) NERF_VRB(2);
+    else if (nch == 3) NERF_VRB(3);
+    else if (nch == 4) NERF_VRB(4);
+    else if (nch <= 6) NERF_VRB(6);
+    else if (nch <= 8) NERF_VRB(8);
+    else NERF_VRB(16);
+#undef NERF_VRB
     NERF_LAUNCHED();
     return NERF_OK;
 }
