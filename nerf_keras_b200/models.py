@@ -277,21 +277,23 @@ class NeRFTrainer:
             m.reset_state()
 
     # -- forward ----------------------------------------------------------------------------------
-    def _forward_tile(self, o, d, t, u_pdf, precision):
+    def _forward_tile(self, o, d, t, u_pdf, precision, maps_only=False):
         B = o.shape[0]
         Nc, Na = self.ns_coarse, self.ns_coarse + self.ns_fine
         dev = o.device
         e = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
-        out = dict(rgb_c=e(B, 3), rgb_f=e(B, 3), depth_c=e(B), depth_f=e(B), w_c=e(B, Nc), w_f=e(B, Na),
-                   pred_c=e(B, Nc, 4), pred_f=e(B, Na, 4), t_all=e(B, Na))
+        out = dict(rgb_c=e(B, 3), rgb_f=e(B, 3), depth_c=e(B), depth_f=e(B))
+        if not maps_only:   # per-sample outputs (weights, raw predictions, sample positions): 4.6 KB per ray
+            out.update(w_c=e(B, Nc), w_f=e(B, Na), pred_c=e(B, Nc, 4), pred_f=e(B, Na, 4), t_all=e(B, Na))
         fo = _lib.ForwardOut(*[_ptr(out.get(k)) for k, _ in _lib.ForwardOut._fields_])
         _lib.check(_lib.lib().nerf_forward_pass(self._ctx.handle, _ptr(o), _ptr(d), _ptr(t), _ptr(u_pdf), B, precision,
                                                 C.byref(fo), _stream()), "forward_pass")
         return out
 
     def forward_pass(self, ray_origins, ray_directions, t_vals, l_xyz=None, l_dir=None, training=False,
-                     batch_size=None, u_pdf=None, precision=None, return_t_all=False):
-        """models.py:151-176.  Returns ((rgb_c,rgb_f),(depth_c,depth_f),(w_c,w_f),(pred_c,pred_f))."""
+                     batch_size=None, u_pdf=None, precision=None, return_t_all=False, maps_only=False):
+        """models.py:151-176.  Returns ((rgb_c,rgb_f),(depth_c,depth_f),(w_c,w_f),(pred_c,pred_f)).
+        maps_only=True skips the per-sample outputs (their pairs are (None, None)): what a renderer needs."""
         if (l_xyz not in (None, self.l_xyz)) or (l_dir not in (None, self.l_dir)):
             raise ValueError("l_xyz / l_dir differ from the trainer's configuration")
         if self._ctx is None:
@@ -303,8 +305,12 @@ class NeRFTrainer:
         u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
         precision = self.precision if precision is None else precision
         tile = self._ctx.max_rays
-        outs = [self._forward_tile(o[s:s + tile], d[s:s + tile], t[s:s + tile], u[s:s + tile], precision)
+        outs = [self._forward_tile(o[s:s + tile], d[s:s + tile], t[s:s + tile], u[s:s + tile], precision, maps_only)
                 for s in range(0, B, tile)]
+        if maps_only:
+            cat = (lambda k: None if k not in outs[0] else
+                   (outs[0][k] if len(outs) == 1 else torch.cat([x[k] for x in outs], dim=0)))
+            return ((cat("rgb_c"), cat("rgb_f")), (cat("depth_c"), cat("depth_f")), (None, None), (None, None))
         cat = (lambda k: outs[0][k]) if len(outs) == 1 else (lambda k: torch.cat([x[k] for x in outs], dim=0))
         res = ((cat("rgb_c"), cat("rgb_f")), (cat("depth_c"), cat("depth_f")), (cat("w_c"), cat("w_f")),
                (cat("pred_c"), cat("pred_f")))
@@ -340,15 +346,15 @@ class NeRFTrainer:
         return preds, g[idx * n:(idx + 1) * n].clone()
 
     def forward_pass_with_minibatch(self, ray_origins, ray_directions, t_vals, l_xyz=None, l_dir=None, batch_size=512,
-                                    training=False, u_pdf=None, precision=None):
+                                    training=False, u_pdf=None, precision=None, maps_only=False):
         """models.py:178-225 -- ray-tile loop; tiles are `batch_size` rays (capped by the workspace)."""
         o, d, t = _f32(ray_origins), _f32(ray_directions), _f32(t_vals)
         B = o.shape[0]
         u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
         outs = [self.forward_pass(o[s:s + batch_size], d[s:s + batch_size], t[s:s + batch_size], l_xyz, l_dir,
-                                  training=training, u_pdf=u[s:s + batch_size], precision=precision)
+                                  training=training, u_pdf=u[s:s + batch_size], precision=precision, maps_only=maps_only)
                 for s in range(0, B, batch_size)]
-        cat = lambda i, j: torch.cat([x[i][j] for x in outs], dim=0)
+        cat = lambda i, j: None if outs[0][i][j] is None else torch.cat([x[i][j] for x in outs], dim=0)
         return tuple((cat(i, 0), cat(i, 1)) for i in range(4))
 
     # -- steps ------------------------------------------------------------------------------------

@@ -297,3 +297,19 @@ def test_tcgen05_mlp_vs_fp32_kernel_large(nk):
     # tiling invariance: forward_pass_with_minibatch == forward_pass
     c = tr_tc.forward_pass_with_minibatch(o, d, t, batch_size=1000, u_pdf=u)
     assert (c[0][1] - a[0][1]).abs().max().item() <= 1e-6
+
+
+def test_ndc_rays_extension_matches_oracle(nk):
+    """EXTENSION (not in the reference): original-NeRF NDC transform, same op order as oracle.ndc_rays."""
+    H, W, focal, near = 378, 504, 407.6, 1.0
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, 3] = [0.1, -0.2, 0.3]
+    o, d = O.get_rays(H, W, focal, pose)
+    o, d = o.reshape(-1, 3)[::37].contiguous(), d.reshape(-1, 3)[::37].contiguous()
+    ro, rd = O.ndc_rays(H, W, focal, near, o, d)
+    go, gd = nk.ndc_rays(H, W, focal, near, o.numpy(), d.numpy())
+    assert np.array_equal(go.cpu().numpy().view(np.uint32), ro.numpy().view(np.uint32))
+    assert np.array_equal(gd.cpu().numpy().view(np.uint32), rd.numpy().view(np.uint32))
+    # rays start on the near plane (z = -1 in NDC) and end at z = +1 as t -> 1
+    np.testing.assert_allclose(go.cpu().numpy()[:, 2], -1.0, atol=1e-5)
+    np.testing.assert_allclose((go + gd).cpu().numpy()[:, 2], 1.0, atol=1e-5)
