@@ -149,6 +149,10 @@ int nerf_debug_flags(int flags);
 /* Diagnostics: timeline trace of CTA 0 of the fused forward kernel (device buffer of 768 int64 clock stamps,
  * NULL disables). */
 int nerf_debug_trace(long long* dev_buf);
+/* Self-test of the CTA-pair (cta_group::2) path: C (256,n) = A (256,k) x B (n,k)^T. */
+int nerf_selftest_gemm_2cta(const float* a, const float* b, float* c, int n, int k, void* stream);
+/* Selects the CTA-pair (cta_group::2, M = 256 MMAs over an SM pair) variant of the fused forward kernel. */
+int nerf_debug_pair_mode(int on);
 /* MMA issue-rate probe (cycles for `reps` x 4 back-to-back 128 x n x 16 MMAs). */
 int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycles_dev, void* stream);
 /* Self-test of the tcgen05 building block: C (M,N) fp32 = A (M,K) bf16-rounded x B^T, B (N,K). */

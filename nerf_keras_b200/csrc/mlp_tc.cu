@@ -57,6 +57,7 @@ struct FwdParams {
     uint8_t* act_save;     // optional saved-activation images (training)
     uint32_t* mask_save;   // optional ReLU masks (training)
     long long* trace;      // optional timeline trace buffer (diagnostics)
+    int dbg;               // experiments: bit0 = no K-half early start in pair mode
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -294,7 +295,9 @@ __device__ __forceinline__ void encode_xyz(const float (&p)[3], float (&e)[64]) 
 // ------------------------------------------------------------------------------------------------
 // the fused forward kernel
 // ------------------------------------------------------------------------------------------------
-template <bool SAVE>
+// PAIR = false: one CTA per SM, independent.  PAIR = true: clusters of two CTAs (an SM pair) sharing M = 256 MMAs
+// (cta_group::2): grid = 2 x clusters, launched with cudaLaunchAttributeClusterDimension {2,1,1}.
+template <bool SAVE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const FwdParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -302,24 +305,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
     uint8_t* smem = smem_raw + (base - raw_addr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;              // 0 = leader of the CTA pair
+    // work units: 256-row tile pairs (one per CTA) or 512-row quads (one per cluster)
+    const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units_grid = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int64_t n_units = PAIR ? (P.n_pairs + 1) / 2 : P.n_pairs;
     Barriers B;
-    init_barriers(base, B);
+    init_barriers(base, B, PAIR);
     float* side = reinterpret_cast<float*>(smem + SM_SIDE);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
-    if (warp == 9) tmem_alloc(base + SM_TMEM, 512);
+    if (warp == 9) {
+        if (PAIR) tmem_alloc_2cta(base + SM_TMEM, 512); else tmem_alloc(base + SM_TMEM, 512);
+    }
     for (int i = threadIdx.x; i < SIDE_FLOATS; i += NUM_THREADS) side[i] = P.side[i];
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync();                                         // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int my_pairs = (P.n_pairs > blockIdx.x) ? (int)((P.n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int my_pairs = (n_units > unit) ? (int)((n_units - unit + n_units_grid - 1) / n_units_grid) : 0;
     const int total_chunks = my_pairs * N_CHUNKS;
+    int steps_per_tile = 0;
+    for (int ph = 0; ph < N_PHASES; ++ph) steps_per_tile += c_fwd_prog.kb[ph];
 
     if (warp == 8) {
-        if (lane == 0) producer_loop(base, B, P.w_chunks, N_CHUNKS, total_chunks);
+        if (lane == 0) {
+            if (PAIR) producer_loop_pair(base, B, P.w_chunks, c_fwd_prog, rank, my_pairs);
+            else producer_loop(base, B, P.w_chunks, N_CHUNKS, total_chunks);
+        }
     } else if (warp >= 9) {
-        if (lane == 0) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace);
+        if (lane == 0) {
+            if (!PAIR) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace);
+            else if (rank == 0) issuer_loop_pair(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace, P.dbg);
+            else if (warp == 9) forwarder_loop_pair(B, my_pairs * steps_per_tile * 2);
+        }
     } else {
         // ===================== workers: PE prologue + epilogues =====================
         const int s = warp >> 2;
@@ -330,15 +350,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
         float* dbs = reinterpret_cast<float*>(smem + SM_DIRB) + s * (DIRB_ROWS * 128);   // staged per-ray ddir biases
         RowStore rs;
         rs.init(act_base, row);
-        const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;    // A tile hand-off, K-halves
+        const uint32_t bar_lo_l = B.actr + 16 * s;                       // A tile hand-off, K-halves (leader's barriers)
+        const uint32_t bar_lo = (PAIR && rank != 0) ? map_to_cta(bar_lo_l, 0) : bar_lo_l;
+        const uint32_t bar_hi = (PAIR && rank != 0) ? map_to_cta(bar_lo_l + 8, 0) : bar_lo_l + 8;
         const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;    // accumulator hand-off, N-halves
         uint32_t accf_par = 0;
         uint32_t E[32];     // bf16(enc), 64 channels packed
         uint32_t Elo[2];    // bf16 residuals of the raw x, y, z channels
+        auto fence_async = [&]() { if (PAIR) fence_proxy_async_all(); else fence_proxy_async_smem(); };
+        auto arrive = [&](uint32_t bar) {                                // the peer's workers arrive on the leader's barrier
+            if (PAIR && rank != 0) mbar_arrive_cluster(bar); else mbar_arrive(bar);
+        };
 
         for (int it = 0; it < my_pairs; ++it) {
-            const int64_t pair = blockIdx.x + (int64_t)it * gridDim.x;
-            const int64_t tile = pair * 2 + s;
+            const int64_t wu = unit + (int64_t)it * n_units_grid;
+            const int64_t tile = PAIR ? (wu * 4 + s * 2 + rank) : (wu * 2 + s);
             const int64_t g_row = tile * TILE_M + row;
             const bool valid = g_row < P.M;
             const int64_t gr = valid ? g_row : (P.M - 1);
@@ -383,13 +409,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
             rs.store<1>(1, 0u, 0u, 0u, 0u);
             if (staged && db_idx < n_rays * 32) reinterpret_cast<float4*>(dbs)[db_idx] = db_pref;
             tc_fence_before();
-            fence_proxy_async_smem();
+            fence_async();
             if (SAVE) {
                 named_bar_sync(1 + s, TILE_M);
                 if (elected) { bulk_s2g(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
             }
-            mbar_arrive(bar_lo);
-            mbar_arrive(bar_hi);
+            arrive(bar_lo);
+            arrive(bar_hi);
 
             float sig = 0.f;
             for (int ph = 0; ph < N_PHASES; ++ph) {
@@ -411,9 +437,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     rs.store<1>(0, Elo[0], Elo[1], 0u, 0u);
                     rs.store<1>(1, 0u, 0u, 0u, 0u);
                     tc_fence_before();
-                    fence_proxy_async_smem();
-                    mbar_arrive(bar_lo);
-                    mbar_arrive(bar_hi);
+                    fence_async();
+                    arrive(bar_lo);
+                    arrive(bar_hi);
                     continue;
                 }
                 if (ph < 10) {
@@ -437,8 +463,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     }
                     store_held(rs, held);
                     tc_fence_before();
-                    fence_proxy_async_smem();
-                    mbar_arrive(bar_lo);                               // next phase may start on K-blocks 0,1
+                    fence_async();
+                    arrive(bar_lo);                                    // next phase may start on K-blocks 0,1
                     if (ph == 8) trunk_part2<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
                     else if (relu) trunk_part2<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
                     else trunk_part2<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
@@ -448,7 +474,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                         sig = a + b;
                     }
                     tc_fence_before();
-                    fence_proxy_async_smem();
+                    fence_async();
                     if (SAVE) {
                         if (relu) {
                             uint4* mp = reinterpret_cast<uint4*>(mask_tile + ((size_t)layer * 128 + row) * 8);
@@ -463,7 +489,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                         }
                     }
                     if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);  // worker: epilogue done
-                    mbar_arrive(bar_hi);
+                    arrive(bar_hi);
                 } else {
                     // ddir epilogue: + (bias + per-ray direction bias), ReLU, rgb head (fp32), write preds
                     mbar_wait(bar_h1, accf_par, 6);
@@ -500,7 +526,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                         uint4* mp = reinterpret_cast<uint4*>(mask_tile + ((size_t)8 * 128 + row) * 8);
                         mp[0] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
                         mp[1] = make_uint4(0u, 0u, 0u, 0u);
-                        fence_proxy_async_smem();
+                        fence_async();
                         named_bar_sync(1 + s, TILE_M);
                         if (elected) { bulk_s2g(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
                     }
@@ -512,7 +538,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (PAIR) cluster_sync();            // the leader's MMAs read the peer's shared memory: leave together
+    if (warp == 9) {
+        if (PAIR) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -601,6 +630,69 @@ __global__ void __launch_bounds__(128, 1) selftest_gemm_kernel(const float* __re
     (void)lane;
 }
 
+// self-test of the CTA-pair path: C (256, N) = A (256, K) x B (N, K)^T, K-major operands, N = 128 or 256.
+// Each CTA of the pair stages its 128 rows of A and its N/2 rows of B; the leader issues M = 256 MMAs.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+selftest_gemm_2cta_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = cluster_ctarank();
+    const int NB = N / 2;                                   // B rows held by this CTA
+    const uint32_t a_bytes = 128 * K * 2, b_bytes = NB * K * 2;
+    uint8_t* a_img = smem;
+    uint8_t* b_img = smem + a_bytes;
+    const uint32_t bar = base + a_bytes + b_bytes;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + a_bytes + b_bytes + 16);
+    for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+        int r = i / K, k = i - r * K;
+        uint32_t off = (k >> 6) * (128 * 128) + sw128_offset(r, k & 63);
+        *reinterpret_cast<__nv_bfloat16*>(a_img + off) = __float2bfloat16(A[(size_t)(rank * 128 + r) * K + k]);
+    }
+    for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
+        int r = i / K, k = i - r * K;
+        uint32_t off = (k >> 6) * (NB * 128) + sw128_offset(r, k & 63);
+        *reinterpret_cast<__nv_bfloat16*>(b_img + off) = __float2bfloat16(B[(size_t)(rank * NB + r) * K + k]);
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc_2cta(base + a_bytes + b_bytes + 16, 256);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();                                          // both CTAs' operands and barriers are ready
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (rank == 0 && threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(256, N, 0, 0);
+        for (int k16 = 0; k16 < K / 16; ++k16) {
+            int kb = k16 >> 2, kk = k16 & 3;
+            uint64_t ad = make_sdesc_sw128(base + kb * (128 * 128) + kk * 32, 16, 1024);
+            uint64_t bd = make_sdesc_sw128(base + a_bytes + kb * (NB * 128) + kk * 32, 16, 1024);
+            mma_bf16_ss_2cta(tmem_base, ad, bd, idesc, k16 > 0 ? 1u : 0u);
+        }
+        mma_commit_2cta(bar, 0x3);
+    }
+    mbar_wait(bar, 0, 9);
+    tc_fence_after();
+    const int row = rank * 128 + threadIdx.x;
+    for (int cg = 0; cg < N / 32; ++cg) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(32 * warp) << 16) + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) C[(int64_t)row * N + cg * 32 + q] = __uint_as_float(v[q]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 0) tmem_dealloc_2cta(tmem_base, 256);
+}
+
 // MMA issue-rate probe: `reps` back-to-back passes of K=64 (4 MMAs) over fixed smem operands, N columns.
 // Reports elapsed SM cycles from first issue to commit completion.  mode 0: K-major, 1: MN-major.
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int reps, int mode, long long* out) {
@@ -652,6 +744,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int reps, int m
 namespace nerf {
 
 long long* g_trace_buf = nullptr;
+int g_pair_mode = 0;   // 1: cta_group::2 forward kernel (nerf_debug_pair_mode)
 
 int tc_supported(const nerf_config& c, std::string* why) {
     if (c.num_layers != 8 || c.hidden_dim != 256 || c.skip_layer != 4 || c.l_xyz != 10 || c.l_dir != 4) {
@@ -666,8 +759,10 @@ int tc_alloc(nerf_ctx* ctx) {
         NERF_CUDA(cudaMalloc(&ctx->w_fwd[net], (size_t)N_CHUNKS * CHUNK_BYTES));
         NERF_CUDA(cudaMalloc(&ctx->side[net], SIDE_FLOATS * sizeof(float)));
     }
-    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     return NERF_OK;
 }
 
@@ -710,13 +805,28 @@ int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, cons
     P.act_save = save_acts ? reinterpret_cast<uint8_t*>(ctx->act_save[net]) : nullptr;
     P.mask_save = save_acts ? ctx->mask_save[net] : nullptr;
     P.trace = g_trace_buf;
-    int grid = (int)(P.n_pairs < num_sms() ? P.n_pairs : num_sms());
+    P.dbg = g_pair_mode >> 1;
+    if (save_acts && !ctx->act_save[net]) return fail(NERF_ERR_STATE, "tc_forward_rays: ctx was not created with training=1");
     timing_begin(0, st);
-    if (save_acts) {
-        if (!ctx->act_save[net]) return fail(NERF_ERR_STATE, "tc_forward_rays: ctx was not created with training=1");
-        nerf_mlp_fwd_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
+    if (g_pair_mode & 1) {
+        // CTA pairs: clusters of 2 over 512-row quads
+        const int64_t n_quads = (P.n_pairs + 1) / 2;
+        const int clusters = (int)(n_quads < num_sms() / 2 ? n_quads : num_sms() / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (save_acts) NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc_kernel<true, true>, P));
+        else NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc_kernel<false, true>, P));
     } else {
-        nerf_mlp_fwd_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
+        int grid = (int)(P.n_pairs < num_sms() ? P.n_pairs : num_sms());
+        if (save_acts) nerf_mlp_fwd_tc_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
+        else nerf_mlp_fwd_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
     }
     timing_end(0, st);
     NERF_LAUNCHED();
@@ -753,3 +863,15 @@ extern "C" int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycl
 
 // diagnostics: enable (device buffer of 4*3*16*4 int64) / disable the forward-kernel timeline trace
 extern "C" int nerf_debug_trace(long long* dev_buf) { nerf::g_trace_buf = dev_buf; return NERF_OK; }
+
+extern "C" int nerf_selftest_gemm_2cta(const float* a, const float* b, float* c, int n, int k, void* stream) {
+    NERF_CHECK_ARG(a && b && c && (n == 128 || n == 256) && k >= 64 && k <= 256 && (k % 64) == 0, "bad arguments");
+    size_t smem = (size_t)(128 + n / 2) * k * 2 + 64 + 1024;
+    NERF_CUDA(cudaFuncSetAttribute(selftest_gemm_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    selftest_gemm_2cta_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(a, b, c, n, k);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+
+// selects the CTA-pair (cta_group::2) variant of the fused forward kernel (0 = single-CTA variant)
+extern "C" int nerf_debug_pair_mode(int on) { nerf::g_pair_mode = on; return NERF_OK; }

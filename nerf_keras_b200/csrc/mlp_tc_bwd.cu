@@ -522,8 +522,9 @@ int g_wg_debug = 0;
 
 int tc_train_alloc(nerf_ctx* ctx) {
     const nerf_config& c = ctx->cfg;
-    const int64_t tiles[2] = {ceil_div((int64_t)c.max_rays * c.ns_coarse, 256) * 2,
-                              ceil_div((int64_t)c.max_rays * (c.ns_coarse + c.ns_fine), 256) * 2};
+    // the CTA-pair forward kernel works on 512-row quads: size the per-tile storage for whole quads
+    const int64_t tiles[2] = {ceil_div((int64_t)c.max_rays * c.ns_coarse, 512) * 4,
+                              ceil_div((int64_t)c.max_rays * (c.ns_coarse + c.ns_fine), 512) * 4};
     for (int net = 0; net < 2; ++net) {
         NERF_CUDA(cudaMalloc((void**)&ctx->act_save[net], (size_t)(tiles[net] * SAVE_TILE_BYTES)));
         // rows of a ragged last tile are read by the weight-gradient GEMMs (times zero gradients): keep them finite

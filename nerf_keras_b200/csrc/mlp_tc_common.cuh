@@ -55,9 +55,10 @@ constexpr int SM_FULL = SM_BAR;                            // STAGES mbarriers
 constexpr int SM_EMPTY = SM_FULL + 8 * STAGES;             // STAGES
 constexpr int SM_ACCF = SM_EMPTY + 8 * STAGES;             // 2 sub-tiles x 2 N-halves
 constexpr int SM_ACTR = SM_ACCF + 32;                      // 2 sub-tiles x 2 K-halves
-constexpr int SM_TMEM = SM_ACTR + 32;                      // u32
+constexpr int SM_PFULL = SM_ACTR + 32;                     // STAGES mbarriers: peer CTA's ring slot is full (pair mode)
+constexpr int SM_TMEM = SM_PFULL + 8 * STAGES;             // u32
 constexpr int DIRB_ROWS = 5;                               // staged per-ray ddir biases per sub-tile (N >= 32 always fits)
-constexpr int SM_DIRB = SM_TMEM + 16;                      // 2 x DIRB_ROWS x 128 floats
+constexpr int SM_DIRB = (SM_TMEM + 16 + 15) & ~15;          // 2 x DIRB_ROWS x 128 floats (float4 aligned)
 constexpr int SM_TOTAL = SM_DIRB + 2 * DIRB_ROWS * 512;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory limit");
@@ -119,19 +120,22 @@ struct RowStore {
 };
 
 struct Barriers {
-    uint32_t full, empty, accf, actr;
+    uint32_t full, empty, accf, actr, pfull;
 };
 
-__device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B) {
+// pair = true: the CTA is one half of a cta_group::2 pair; the leader's A-tile barriers also collect the peer's workers
+__device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B, bool pair = false) {
     B.full = base + SM_FULL; B.empty = base + SM_EMPTY; B.accf = base + SM_ACCF; B.actr = base + SM_ACTR;
+    B.pfull = base + SM_PFULL;
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(B.full + 8 * i, 1);
-            mbar_init(B.empty + 8 * i, 2);   // one tcgen05.commit per sub-tile
+            mbar_init(B.empty + 8 * i, pair ? 1 : 2);   // single-CTA: both sub-tiles consume a chunk; pair: one consumer
+            mbar_init(B.pfull + 8 * i, 1);
         }
         for (int i = 0; i < 4; ++i) {                 // index = sub-tile * 2 + half
             mbar_init(B.accf + 8 * i, 1);
-            mbar_init(B.actr + 8 * i, TILE_M);
+            mbar_init(B.actr + 8 * i, pair ? 2 * TILE_M : TILE_M);
         }
         fence_barrier_init();
     }
@@ -216,6 +220,135 @@ __device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, ui
             mma_commit(bar_h1);
             actr_par ^= 1;
             trace_ev(trace, s, tile, ph, 2);              // issuer: all MMAs of the phase issued
+        }
+    }
+}
+
+// =====================================================================================================
+// CTA-pair mode (cta_group::2).  Two CTAs of a cluster (an SM pair) run the same program on 2 x 2 sub-tiles.
+// One MMA covers M = 256 rows (128 per CTA) x N = 256 columns; each CTA stages its own A rows and HALF of the
+// weight rows (B), so per-SM shared-memory operand traffic is half of the single-CTA kernel's -- the resource
+// that bounds it.  Only the leader (cluster rank 0) issues MMAs; hand-offs:
+//   * weights: every CTA fills its own ring slot; the peer forwards "slot full" to the leader's pfull barrier;
+//     tcgen05.commit multicasts "slot free" to both CTAs;
+//   * A tiles: the workers of BOTH CTAs arrive on the leader's actr barriers (count 256);
+//   * accumulators: tcgen05.commit multicasts to both CTAs' accf barriers.
+// Chunk stream per CTA and phase: k-blocks kb = 0..kbs-1 of N-half `rank` (phases with a single N-half, i.e. the
+// 128-wide ddir layer, take rows [64 rank, 64 rank + 64) of each chunk: 8 KB).
+// =====================================================================================================
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int code) {
+    uint32_t ok = 0, n = 0;
+    long long t0 = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((++n & 4095u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > TC5_TIMEOUT_CYCLES) {
+                printf("tc5: cluster mbarrier wait timeout code=%d block=%d thread=%d parity=%u\n", code, blockIdx.x,
+                       threadIdx.x, parity);
+                __trap();
+            }
+        }
+    }
+}
+
+// Ring order in pair mode ("merged" order): for every phase first the chunks of sub-tile 0, then the same chunks again
+// for sub-tile 1.  Each chunk has exactly one consumer, the two sub-tiles alternate on the tensor pipe phase by
+// phase, and one sub-tile's whole epilogue runs under the other's MMA phase.
+__device__ __forceinline__ void producer_loop_pair(uint32_t base, const Barriers& B, const __nv_bfloat16* chunks,
+                                                   const Program& prog, int rank, int n_tiles) {
+    int slot = 0;
+    uint32_t par = 1;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        int first = 0;
+        for (int ph = 0; ph < prog.n_phases; ++ph) {
+            const int n_ch = prog.chunks[ph], kbs = prog.kb[ph];
+            const bool single = (n_ch == kbs);                   // one N-half only: split its rows between the CTAs
+            const uint32_t bytes = single ? CHUNK_BYTES / 2 : CHUNK_BYTES;
+            for (int sub = 0; sub < 2; ++sub) {
+                for (int kb = 0; kb < kbs; ++kb) {
+                    const int c = first + (single ? kb : rank * kbs + kb);
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(chunks) + (size_t)c * CHUNK_BYTES +
+                                         (single ? rank * (CHUNK_BYTES / 2) : 0);
+                    mbar_wait(B.empty + 8 * slot, par, 1);
+                    mbar_arrive_expect_tx(B.full + 8 * slot, bytes);
+                    bulk_g2s(base + SM_RING + slot * CHUNK_BYTES, src, bytes, B.full + 8 * slot);
+                    if (++slot == STAGES) { slot = 0; par ^= 1; }
+                }
+            }
+            first += n_ch;
+        }
+    }
+}
+
+// peer CTA: forward "my ring slot is full" to the leader
+__device__ __forceinline__ void forwarder_loop_pair(const Barriers& B, int steps_total) {
+    int slot = 0;
+    uint32_t par = 0;
+    for (int g = 0; g < steps_total; ++g) {
+        mbar_wait(B.full + 8 * slot, par, 7);
+        mbar_arrive_cluster(map_to_cta(B.pfull + 8 * slot, 0));
+        if (++slot == STAGES) { slot = 0; par ^= 1; }
+    }
+}
+
+// leader CTA: one issuer thread per sub-tile pair; sub-tile s owns merged positions [base + s*kbs, base + (s+1)*kbs)
+__device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& B, uint32_t tmem_base, const Program& prog,
+                                                 int s, int n_tiles, long long* trace = nullptr, int dbg = 0) {
+    const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
+    const uint32_t lbo_bits = (16u >> 4) << 16;
+    const uint32_t a_tile = ((base + SM_ACT + s * 65536) & 0x3FFFF) >> 4;
+    const uint32_t ring0 = ((base + SM_RING) & 0x3FFFF) >> 4;
+    const uint32_t d_tmem = tmem_base + s * 256;
+    const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;
+    const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;
+    const uint32_t idesc256 = make_idesc_bf16(256, 256, 0, 0), idesc128 = make_idesc_bf16(256, 128, 0, 0);
+    uint32_t g_base = 0;          // merged ring position of the current phase's first chunk
+    uint32_t actr_par = 0;
+    (void)dbg;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        for (int ph = 0; ph < prog.n_phases; ++ph) {
+            const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
+            const uint32_t idesc = (n_ch == kbs) ? idesc128 : idesc256;
+            trace_ev(trace, s, tile, ph, 0);
+            mbar_wait_cluster(bar_lo, actr_par, 3);
+            mbar_wait_cluster(bar_hi, actr_par, 5);
+            trace_ev(trace, s, tile, ph, 1);
+            for (int kb = 0; kb < kbs; ++kb) {
+                const uint32_t g = g_base + s * kbs + kb;
+                const uint32_t lap = g / STAGES;
+                const uint32_t slot = g - lap * STAGES;
+                const uint32_t ring_par = lap & 1;
+                mbar_wait(B.full + 8 * slot, ring_par, 4);
+                mbar_wait_cluster(B.pfull + 8 * slot, ring_par, 8);
+                tc_fence_after();
+                const uint32_t a_lo = (a_tile + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
+                const uint32_t b_lo = (ring0 + slot * (CHUNK_BYTES >> 4)) | lbo_bits;
+                const bool acc0 = (kb > 0) || (flags & PH_ACC);
+                const int n_mma = ((flags & PH_ENC) && kb == 1) ? 1 : 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < n_mma) {
+                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                        mma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (acc0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                mma_commit_2cta(B.empty + 8 * slot, 0x3);      // frees the slot in both CTAs
+            }
+            mma_commit_2cta(bar_h0, 0x3);                       // all 256 columns complete at once in pair mode
+            mma_commit_2cta(bar_h1, 0x3);
+            actr_par ^= 1;
+            g_base += 2 * kbs;
+            trace_ev(trace, s, tile, ph, 2);
         }
     }
 }

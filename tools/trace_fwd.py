@@ -10,6 +10,7 @@ tr = nk.NeRFTrainer(c, f, B, Nc, Nf, 10, 4); tr.build()
 o, d = nk.get_rays(64, 64, 88.0, nk.pose_spherical(20.0, -30.0, 4.0))
 o, d = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
 t = nk.generate_t_vals(2.0, 6.0, B, Nc, False)
+L.nerf_debug_pair_mode(int(os.environ.get("PAIR", "0")))
 for _ in range(2): tr.mlp_forward_rays("coarse", o, d, t)
 buf = torch.zeros(4 * 3 * 16 * 4, dtype=torch.int64, device="cuda")
 L.nerf_debug_trace(buf.data_ptr())
