@@ -30,6 +30,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_SAMPLE_FWD = 1186816          # BASELINE.md section 3 (un-padded, both heads, one net)
+# dram__bytes_read.sum + dram__bytes_write.sum of the fused forward kernel per launch (mean of the coarse and fine
+# launches of one step) from the committed `ncu --set full` captures: profiles/r1_train_kernels_ncu_summary.txt
+# (training variant, writes the saved operand images) and profiles/r1_render_fwd_ncu_summary.txt (render variant)
+NCU_TRAFFIC_PER_LAUNCH = {"train": (0.012068e9 + 1.333799e9 + 0.031599e9 + 4.119096e9) / 2,
+                          "render": (4.589568e6 + 6.686720e6) / 2}
 CPU_SAMPLE_RAYS = 256                  # bounded CPU sample (rays per CPU step)
 
 
@@ -298,6 +303,17 @@ def main():
             kernel_ms[nm] = a_ms.value / args.steps
     e2e_ms = timed(step_e2e, args.steps)
 
+    extra = {}
+    if args.mode == "train":
+        # the metric names render AND train: time a few forward_pass steps on the same trainer / batches as well
+        def step_render(i):
+            img, o, d, t, u = dev_batches[i % R]
+            return trainer.forward_pass(o, d, t, u_pdf=u, maps_only=True)[0][1]
+        for i in range(3):
+            step_render(i)
+        r_ms = timed(step_render, max(3, args.steps // 2))
+        L.nerf_timing_read(0, C.byref(C.c_double()), C.byref(C.c_int64()))
+        extra["render_rays_per_sec"] = world * B / (r_ms / max(3, args.steps // 2) * 1e-3)
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     e2e_value = world * B / (e2e_ms / args.steps * 1e-3)
@@ -315,7 +331,8 @@ def main():
         achieved = flop_per_launch / (avg_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "nerf_mlp_fwd_tc_kernel", "achieved": achieved,
                     "peak": peaks["tensor_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor_sustained"],
-                    "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                    "traffic": NCU_TRAFFIC_PER_LAUNCH[args.mode], "traffic_unit": "bytes/launch (ncu, profiles/r1_*)",
+                    "peak_source": peaks["source"] + " (sustained bf16)",
                     "avg_launch_ms": avg_ms, "launches": k_n.value,
                     "share_of_step": k_ms.value / total_ms}
 
@@ -326,6 +343,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "kernel_ms_per_step": kernel_ms}
+    line.update(extra)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_arm(args.mode, conf, 3, 1, CPU_SAMPLE_RAYS)

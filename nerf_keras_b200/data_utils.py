@@ -46,6 +46,8 @@ def encode_position(x, pos_encode_dims):
         raise ValueError("encode_position expects a trailing dimension of 3")
     n = x.numel() // 3
     out = torch.empty(x.shape[:-1] + (3 + 6 * pos_encode_dims,), device=x.device, dtype=torch.float32)
+    if n == 0:
+        return out
     _lib.check(_lib.lib().nerf_encode_position(_ptr(x), n, int(pos_encode_dims), _ptr(out), _stream()),
                "encode_position")
     return out
@@ -81,6 +83,8 @@ def sample_rays(ray_origins, ray_directions, t_vals):
     B, N = t.shape
     rays = torch.empty((B, N, 3), device=o.device, dtype=torch.float32)
     dirs = torch.empty((B, N, 3), device=o.device, dtype=torch.float32)
+    if B == 0:
+        return rays, dirs
     _lib.check(_lib.lib().nerf_sample_rays(_ptr(o), _ptr(d), _ptr(t), B, N, _ptr(rays), _ptr(dirs), _stream()),
                "sample_rays")
     return rays, dirs
@@ -96,6 +100,8 @@ def volume_render(preds, t_vals, return_acc=False):
     depth = torch.empty((B,), device=p.device, dtype=torch.float32)
     w = torch.empty((B, N), device=p.device, dtype=torch.float32)
     acc = torch.empty((B,), device=p.device, dtype=torch.float32) if return_acc else None
+    if B == 0:
+        return (rgb, depth, w, acc) if return_acc else (rgb, depth, w)
     _lib.check(_lib.lib().nerf_volume_render(_ptr(p), _ptr(t), B, N, _ptr(rgb), _ptr(depth), _ptr(w), _ptr(acc),
                                              _stream()), "volume_render")
     return (rgb, depth, w, acc) if return_acc else (rgb, depth, w)
@@ -126,6 +132,8 @@ def generate_t_vals(near, far, batch_size, num_samples, rand_sampling=True, u=No
         else:
             raise ValueError("u must have shape (num_samples,) or (batch_size, num_samples)")
     t = torch.empty((B, N), device=dev, dtype=torch.float32)
+    if B == 0:
+        return t
     _lib.check(_lib.lib().nerf_generate_t_vals(float(near), float(far), B, N, _ptr(uu), per_ray, _ptr(t), _stream()),
                "generate_t_vals")
     return t
@@ -141,6 +149,8 @@ def sample_pdf(t_vals_mid, weights, ns_fine, u=None):
     if uu.shape != (B, ns_fine):
         raise ValueError("u must have shape (B, ns_fine)")
     out = torch.empty((B, ns_fine), device=w.device, dtype=torch.float32)
+    if B == 0:
+        return out
     _lib.check(_lib.lib().nerf_sample_pdf(_ptr(tm), _ptr(w), _ptr(uu), B, nc, int(ns_fine), _ptr(out), _stream()),
                "sample_pdf")
     return out
@@ -153,6 +163,8 @@ def resample_merge(t_vals, weights, ns_fine, u=None, return_index=False):
     uu = torch.rand((B, ns_fine), device=t.device, dtype=torch.float32) if u is None else _f32(u)
     out = torch.empty((B, nc + ns_fine), device=t.device, dtype=torch.float32)
     idx = torch.empty((B, nc + ns_fine), device=t.device, dtype=torch.int32) if return_index else None
+    if B == 0:
+        return (out, idx) if return_index else out
     _lib.check(_lib.lib().nerf_resample_merge(_ptr(t), _ptr(w), _ptr(uu), B, nc, int(ns_fine), _ptr(out), _ptr(idx),
                                               _stream()), "resample_merge")
     return (out, idx) if return_index else out

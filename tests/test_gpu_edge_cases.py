@@ -1,0 +1,147 @@
+"""GPU: edge cases of the public surface -- empty and ragged batches, small / odd sample counts, batches larger than
+the workspace, error behaviour (same exception types as the reference: TypeError / ValueError / KeyError)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from tests.util import golden_weights, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nk():
+    import nerf_keras_b200 as nk
+    return nk
+
+
+def _trainer(nk, wc, wf, batch, Nc, Nf, precision=None, compile_=False):
+    mc = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    mf = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    mc.set_flat_weights(O.flatten_weights(wc)); mf.set_flat_weights(O.flatten_weights(wf))
+    tr = nk.NeRFTrainer(mc, mf, batch, Nc, Nf, 10, 4, precision=nk.PRECISION_BF16_TC if precision is None else precision)
+    if compile_:
+        tr.compile(nk.Adam(learning_rate=5e-4), nk.MeanSquaredError())
+    else:
+        tr.build()
+    return tr
+
+
+def test_empty_inputs(nk):
+    z3 = np.zeros((0, 3), np.float32)
+    assert nk.encode_position(z3, 10).shape == (0, 63)
+    assert nk.generate_t_vals(2.0, 6.0, 0, 64, False).shape == (0, 64)
+    r, d, w = nk.volume_render(np.zeros((0, 16, 4), np.float32), np.zeros((0, 16), np.float32))
+    assert r.shape == (0, 3) and d.shape == (0,) and w.shape == (0, 16)
+    rays, dirs = nk.sample_rays(z3, z3, np.zeros((0, 8), np.float32))
+    assert rays.shape == (0, 8, 3)
+    assert nk.sample_pdf(np.zeros((0, 15), np.float32), np.zeros((0, 16), np.float32), 32).shape == (0, 32)
+
+
+@pytest.mark.parametrize("B", [1, 3, 127, 129, 300])
+def test_ragged_batches_match_fp32_kernel(nk, B):
+    """Batches that do not fill a 128-row tile / a 256-row tile pair (and a single ray)."""
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    Nc, Nf = 16, 32
+    rng = np.random.default_rng(B)
+    o, d = O.get_rays(20, 20, 27.8, O.pose_spherical(11.0, -30.0, 4.0))
+    sel = rng.choice(400, B, replace=False)
+    o, d = o.reshape(-1, 3)[sel].numpy(), d.reshape(-1, 3)[sel].numpy()
+    t = O.generate_t_vals(2.0, 6.0, B, Nc, True, u=g["u_t"]).numpy()
+    u = rng.random((B, Nf), dtype=np.float32)
+    tc = _trainer(nk, wc, wf, max(B, 4), Nc, Nf)
+    f32 = _trainer(nk, wc, wf, max(B, 4), Nc, Nf, precision=nk.PRECISION_FP32)
+    a = tc.mlp_forward_rays("coarse", o, d, t)
+    b = f32.mlp_forward_rays("coarse", o, d, t)
+    assert a.shape == (B, Nc, 4) and torch.isfinite(a).all()
+    assert (a - b).abs().max().item() <= 5e-2
+    full = tc.forward_pass(o, d, t, u_pdf=u)
+    assert full[0][1].shape == (B, 3) and full[2][1].shape == (B, Nc + Nf) and torch.isfinite(full[0][1]).all()
+
+
+@pytest.mark.parametrize("Nc,Nf", [(2, 1), (16, 32), (33, 7), (64, 128), (100, 60)])
+def test_sample_counts_fp32_forward_vs_oracle(nk, Nc, Nf):
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    B = 24
+    rng = np.random.default_rng(Nc * 1000 + Nf)
+    o, d = g["o"][:B], g["d"][:B]
+    t = O.generate_t_vals(2.0, 6.0, B, Nc, True, u=rng.random(Nc, dtype=np.float32)).numpy()
+    u = rng.random((B, Nf), dtype=np.float32)
+    tr = _trainer(nk, wc, wf, B, Nc, Nf, precision=nk.PRECISION_FP32)
+    rgbs, depths, ws, preds = tr.forward_pass(o, d, t, u_pdf=u)
+    with torch.no_grad():
+        ref = O.forward_pass(wc, wf, torch.from_numpy(o), torch.from_numpy(d), torch.from_numpy(t), 10, 4, Nf, torch.from_numpy(u))
+    np.testing.assert_allclose(rgbs[0].cpu().numpy(), ref[0][0].numpy(), atol=1e-5)
+    np.testing.assert_allclose(ws[0].cpu().numpy(), ref[2][0].numpy(), atol=1e-5)
+    np.testing.assert_allclose(rgbs[1].cpu().numpy(), ref[0][1].numpy(), atol=2e-4)
+    # same counts through the tensor-core kernel
+    tc = _trainer(nk, wc, wf, B, Nc, Nf)
+    rgbs_tc = tc.forward_pass(o, d, t, u_pdf=u)[0]
+    assert torch.isfinite(rgbs_tc[0]).all() and (rgbs_tc[0] - rgbs[0]).abs().median().item() < 1e-3
+
+
+def test_batch_larger_than_workspace_is_tiled(nk):
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    tr_small = _trainer(nk, wc, wf, 32, 16, 32)        # workspace of 32 rays
+    tr_big = _trainer(nk, wc, wf, 96, 16, 32)
+    a = tr_small.forward_pass(g["o"], g["d"], g["t"], u_pdf=g["u_pdf"])
+    b = tr_big.forward_pass(g["o"], g["d"], g["t"], u_pdf=g["u_pdf"])
+    assert a[0][1].shape == (96, 3)
+    assert (a[0][1] - b[0][1]).abs().max().item() <= 1e-6
+    # train_step grows the workspace when it sees a bigger batch than batch_size
+    tr = _trainer(nk, wc, wf, 32, 16, 32, compile_=True)
+    m = tr.train_step((g["img"], (g["o"], g["d"], g["t"])), u_pdf=g["u_pdf"])
+    assert np.isfinite(float(m["loss"]))
+
+
+def test_error_behaviour(nk):
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    with pytest.raises(ValueError):
+        nk.encode_position(np.zeros((4, 2), np.float32), 10)
+    with pytest.raises(ValueError):
+        nk.volume_render(np.zeros((4, 8, 4), np.float32), np.zeros((4, 7), np.float32))
+    with pytest.raises(ValueError):
+        nk.get_rays(4, 4, 1.0, np.eye(3, dtype=np.float32))
+    with pytest.raises(ValueError):
+        nk.generate_t_vals(2.0, 6.0, 4, 8, True, u=np.zeros(7, np.float32))
+    with pytest.raises(ValueError):
+        nk.sample_pdf(np.zeros((4, 8), np.float32), np.zeros((4, 8), np.float32), 4)
+    with pytest.raises(TypeError):
+        nk.NeRFTrainer("not a model", nk.create_nerf_complete_model(8, 256, 4, 10, 4), 8, 4, 8, 10, 4)
+    with pytest.raises(ValueError):
+        nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+    tr = _trainer(nk, wc, wf, 8, 16, 32)
+    with pytest.raises(RuntimeError):
+        tr.train_step((g["img"][:8], (g["o"][:8], g["d"][:8], g["t"][:8])))       # compile() not called
+    with pytest.raises(ValueError):
+        tr.forward_pass(g["o"][:8], g["d"][:8], g["t"][:8, :5])                   # wrong number of coarse samples
+    with pytest.raises(ValueError):
+        tr.forward_pass(g["o"][:8], g["d"][:8], g["t"][:8], 9, 4)                 # l_xyz differs from the trainer's
+    # a non 8x256 architecture has no tensor-core path: fp32 works, the tcgen05 request is refused
+    small = nk.create_nerf_complete_model(4, 64, 2, 6, 2)
+    out = small([np.zeros((5, 39), np.float32), np.zeros((5, 15), np.float32)])
+    assert out.shape == (5, 4)
+    tr2 = nk.NeRFTrainer(small, nk.create_nerf_complete_model(4, 64, 2, 6, 2), 8, 4, 8, 6, 2)
+    tr2.build()
+    with pytest.raises(ValueError):
+        tr2.forward_pass(g["o"][:8], g["d"][:8], g["t"][:8, :4], u_pdf=g["u_pdf"][:8, :8])
+
+
+def test_weights_roundtrip_and_save_load(nk, tmp_path):
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    tr = _trainer(nk, wc, wf, 96, 16, 32, compile_=True)
+    tr.train_step((g["img"], (g["o"], g["d"], g["t"])), u_pdf=g["u_pdf"])
+    path = str(tmp_path / "w.npz")
+    tr.save_weights(path)
+    before = tr.forward_pass(g["o"], g["d"], g["t"], u_pdf=g["u_pdf"])[0][1].clone()
+    tr2 = _trainer(nk, wc, wf, 96, 16, 32)
+    tr2.load_weights(path)
+    after = tr2.forward_pass(g["o"], g["d"], g["t"], u_pdf=g["u_pdf"])[0][1]
+    assert (before - after).abs().max().item() <= 1e-6
+    assert np.abs(tr.coarse_model.get_weights()["d0"]["W"] - wc["d0"]["W"].numpy()).max() > 0
