@@ -49,7 +49,7 @@ typedef struct nerf_config {
     int32_t batch_norm;  /* BATCH_NORM: must be 0 (out of scope this round)    */
     int32_t training;    /* 1: allocate gradient / Adam / saved-activation storage            */
     float learning_rate; /* LEARNING_RATE (Adam, Keras defaults b1 .9 b2 .999 eps 1e-7)       */
-    int32_t stop_grad_samples; /* 1: no gradient through the fine sample positions (reference: 0)  */
+    int32_t stop_grad_samples; /* 1: no gradient through the fine sample positions; 0: reference semantics */
 } nerf_config;
 
 typedef struct nerf_ctx nerf_ctx;
@@ -143,6 +143,13 @@ int nerf_timing_read(int kind, double* total_ms, int64_t* launches);
  * ctx gradient buffer (nerf_grad_buffer), the other net's half is zero. */
 int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t batch,
                          int num_samples, const float* d_preds, float* preds, void* stream);
+/* Diagnostics for the un-stopped sample-position gradient (quirk Q5): after nerf_debug_mlp_grads(net, ...),
+ * dtp (B,N) = < d_ray, d(sum(preds*d_preds))/d pts >; and the backward of sort(concat([t, sample_pdf])) alone:
+ * d_w (B,nc) from dL/dt_all given as a direct part dtp (B,Na) and/or dL/d(delta) of the fine compositing. */
+int nerf_debug_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t batch,
+                          int num_samples, float* dtp, void* stream);
+int nerf_sample_pdf_bwd(const float* t, const float* weights, const float* u, const int32_t* src_idx,
+                        const float* dtp, const float* d_delta, int64_t batch, int nc, int nf, float* d_w, void* stream);
 /* Timing experiments only: bit0 skip the CUDA-core side jobs, bit1 skip the MMAs, bit2 skip the final
  * reduction of the weight-gradient kernel (results are then wrong by construction). */
 int nerf_debug_flags(int flags);

@@ -57,6 +57,8 @@ SIGNATURES = {
     "nerf_timing_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(_L)]),
     "nerf_debug_mlp_grads": (_I, [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P]),
     "nerf_selftest_mma_rate": (_I, [_I, _I, _I, _P, _P]),
+    "nerf_debug_input_grad": (_I, [_P, _I, _P, _P, _P, _L, _I, _P, _P]),
+    "nerf_sample_pdf_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _P]),
     "nerf_debug_flags": (_I, [_I]),
     "nerf_debug_pair_mode": (_I, [_I]),
     "nerf_debug_trace": (_I, [_P]),

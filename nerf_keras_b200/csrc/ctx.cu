@@ -110,6 +110,9 @@ extern "C" int nerf_create(const nerf_config* cfg, nerf_ctx** out) {
         cudaMemset(ctx->tr_dpred_f, 0, (R * Na + 512) * 16);
         ALLOC(ctx->tr_drgb_c, R * 12);
         ALLOC(ctx->tr_drgb_f, R * 12);
+        ALLOC(ctx->tr_ddelta_f, R * Na * 4);
+        ALLOC(ctx->tr_dtp_f, R * Na * 4);
+        ALLOC(ctx->tr_dw_extra, R * Nc * 4);
     }
 #undef ALLOC
     if (tc_supported(*cfg, nullptr)) {
@@ -132,7 +135,8 @@ extern "C" int nerf_destroy(nerf_ctx* ctx) {
     cudaFree(ctx->fw_t_all); cudaFree(ctx->fw_src_idx); cudaFree(ctx->fw_rgb_c); cudaFree(ctx->fw_rgb_f);
     cudaFree(ctx->fw_dirbias);
     cudaFree(ctx->tr_dpred_c); cudaFree(ctx->tr_dpred_f); cudaFree(ctx->tr_drgb_c); cudaFree(ctx->tr_drgb_f);
-    cudaFree(ctx->tr_ddirbias);
+    cudaFree(ctx->tr_ddirbias); cudaFree(ctx->tr_ddelta_f); cudaFree(ctx->tr_dtp_f); cudaFree(ctx->tr_dw_extra);
+    cudaFree(ctx->w_ig);
     for (int n = 0; n < 2; ++n) { cudaFree(ctx->act_save[n]); cudaFree(ctx->dz_save[n]); cudaFree(ctx->mask_save[n]); }
     tc_free(ctx);
     delete ctx;
@@ -265,9 +269,6 @@ extern "C" int nerf_train_forward_backward(nerf_ctx* ctx, const float* images, c
     if (!ctx->cfg.training || !ctx->grads) return fail(NERF_ERR_STATE, "ctx was not created with training=1");
     std::string why;
     if (!tc_supported(ctx->cfg, &why)) return fail(NERF_ERR_INVALID, why);
-    if (!ctx->cfg.stop_grad_samples)
-        return fail(NERF_ERR_INVALID,
-                    "the CUDA backward implements stop_grad_samples=1 only this round (reference quirk Q5, DESIGN.md)");
     int rc = check_ready(ctx, 0);
     if (rc) return rc;
     if ((rc = check_ready(ctx, 1))) return rc;
@@ -277,13 +278,23 @@ extern "C" int nerf_train_forward_backward(nerf_ctx* ctx, const float* images, c
     if ((rc = nerf_metrics_grad(images, ctx->fw_rgb_c, ctx->fw_rgb_f, batch, metrics_dev, ctx->tr_drgb_c,
                                 ctx->tr_drgb_f, st)))
         return rc;
-    if ((rc = nerf_volume_render_bwd(ctx->fw_pred_c, t, ctx->tr_drgb_c, nullptr, batch, Nc, ctx->tr_dpred_c, nullptr, st)))
-        return rc;
-    if ((rc = nerf_volume_render_bwd(ctx->fw_pred_f, ctx->fw_t_all, ctx->tr_drgb_f, nullptr, batch, Na,
-                                     ctx->tr_dpred_f, nullptr, st)))
-        return rc;
+    const bool q5 = !ctx->cfg.stop_grad_samples;   // reference semantics: gradient flows through the fine sample positions
     NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * ctx->n_params * 4, st));
+    // fine net first: its input gradient feeds the coarse net through sort + sample_pdf (models.py:165-175)
+    if ((rc = nerf_volume_render_bwd(ctx->fw_pred_f, ctx->fw_t_all, ctx->tr_drgb_f, nullptr, batch, Na, ctx->tr_dpred_f,
+                                     q5 ? ctx->tr_ddelta_f : nullptr, st)))
+        return rc;
     if ((rc = tc_backward(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dpred_f, st))) return rc;
+    const float* d_w_extra = nullptr;
+    if (q5) {
+        if ((rc = tc_input_grad(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dtp_f, st))) return rc;
+        if ((rc = sample_pdf_backward(t, ctx->fw_w_c, u_pdf, ctx->fw_src_idx, ctx->tr_dtp_f, ctx->tr_ddelta_f, batch, Nc,
+                                      ctx->cfg.ns_fine, ctx->tr_dw_extra, st)))
+            return rc;
+        d_w_extra = ctx->tr_dw_extra;
+    }
+    if ((rc = nerf_volume_render_bwd(ctx->fw_pred_c, t, ctx->tr_drgb_c, d_w_extra, batch, Nc, ctx->tr_dpred_c, nullptr, st)))
+        return rc;
     if ((rc = tc_backward(ctx, NERF_NET_COARSE, o, d, t, batch, Nc, ctx->tr_dpred_c, st))) return rc;
     return NERF_OK;
 }
@@ -316,4 +327,12 @@ extern "C" int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, cons
     float* dp = net == 0 ? ctx->tr_dpred_c : ctx->tr_dpred_f;   // tile-padded staging buffer
     NERF_CUDA(cudaMemcpyAsync(dp, d_preds, (size_t)batch * num_samples * 16, cudaMemcpyDeviceToDevice, st));
     return tc_backward(ctx, net, o, d, t, batch, num_samples, dp, st);
+}
+
+// Diagnostics: after nerf_debug_mlp_grads(net, ...) -- dtp[m] = < d_ray, d(sum(preds * d_preds)) / d pts[m] >.
+extern "C" int nerf_debug_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t,
+                                     int64_t batch, int num_samples, float* dtp, void* stream) {
+    NERF_CHECK_ARG(ctx && o && d && t && dtp && batch >= 1, "bad arguments");
+    if (!ctx->cfg.training || !ctx->grads) return fail(NERF_ERR_STATE, "ctx was not created with training=1");
+    return tc_input_grad(ctx, net, o, d, t, batch, num_samples, dtp, (cudaStream_t)stream);
 }

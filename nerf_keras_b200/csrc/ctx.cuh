@@ -51,6 +51,9 @@ struct nerf_ctx {
     uint32_t* mask_save[2] = {nullptr, nullptr};
     float *tr_dpred_c = nullptr, *tr_dpred_f = nullptr, *tr_drgb_c = nullptr, *tr_drgb_f = nullptr;
     float* tr_ddirbias = nullptr;
+    // un-stopped gradient through the fine sample positions (stop_grad_samples = 0)
+    __nv_bfloat16* w_ig = nullptr;                 // W0^T / W5b^T operand image of the input-gradient kernel
+    float *tr_ddelta_f = nullptr, *tr_dtp_f = nullptr, *tr_dw_extra = nullptr;
 };
 
 namespace nerf {
@@ -66,6 +69,10 @@ int tc_supported(const nerf_config& cfg, std::string* why);
 int tc_alloc(nerf_ctx* ctx);
 void tc_free(nerf_ctx* ctx);
 int tc_pack_weights(nerf_ctx* ctx, int net, cudaStream_t st);
+int tc_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N, float* dtp,
+                  cudaStream_t st);
+int sample_pdf_backward(const float* t, const float* weights, const float* u, const int32_t* src_idx, const float* dtp,
+                        const float* d_delta, int64_t B, int nc, int nf, float* d_w, cudaStream_t st);
 int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
                     float* preds, bool save_acts, cudaStream_t st);
 

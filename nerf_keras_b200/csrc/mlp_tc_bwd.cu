@@ -514,6 +514,260 @@ __global__ void __launch_bounds__(256) head_bias_kernel(const float4* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 4. Input gradient of the (fine) MLP for the reference's un-stopped gradient through the fine sample positions
+// (models.py:166-175 has no stop_gradient):  d_enc = dZ0 W0^T + dZ5 W5[256:319]^T  (tcgen05, M=128, N=64),
+// positional-encoding backward per row, and  dtp[m] = < d_ray, dL/dpts[m] >  (data_utils.py:17-21,68-70).
+// ------------------------------------------------------------------------------------------------
+constexpr int IG_THREADS = 192;
+constexpr int IG_W_BYTES = 2 * 4 * 8192;               // W0^T and W5b^T: 4 K-blocks of [64 n x 64 k] each
+constexpr int IG_SM_W = 0;
+constexpr int IG_SM_A = IG_W_BYTES;                    // 2 stages x 64 KB (one dZ image each)
+constexpr int IG_SM_BAR = IG_SM_A + 2 * 65536;
+constexpr int IG_SMEM = IG_SM_BAR + 128 + 1024;
+
+__global__ void __launch_bounds__(256) pack_ig_kernel(const float* __restrict__ blob, BlobOffsets off,
+                                                      __nv_bfloat16* __restrict__ img) {
+    // img[w][kb][n (64) x k (64)]: B[n][k] = W0[n][kb*64+k] (w=0) or W5[256+n][kb*64+k] (w=1); rows n >= 63 are zero
+    const int total = 2 * 4 * 64 * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int w = i / (4 * 64 * 8), rem = i % (4 * 64 * 8);
+        const int kb = rem / (64 * 8), n = (rem / 8) % 64, kg = rem % 8;
+        uint32_t packed[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k0 = kb * 64 + kg * 8 + 2 * q;
+            float a = 0.f, b = 0.f;
+            if (n < ENC_X) {
+                const int64_t base = (w == 0) ? off.w[0] + (int64_t)n * H : off.w[5] + (int64_t)(H + n) * H;
+                a = blob[base + k0]; b = blob[base + k0 + 1];
+            }
+            packed[q] = pack_bf16x2(a, b);
+        }
+        uint8_t* dst = reinterpret_cast<uint8_t*>(img) + (size_t)(w * 4 + kb) * 8192 + sw128_offset(n, kg * 8);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
+struct IgParams {
+    const uint8_t* dz_save;
+    const __nv_bfloat16* w_img;
+    const float* o; const float* d; const float* t;
+    int N; int64_t M; int64_t n_tiles;
+    float* dtp;                      // (M) < d, dL/dpts >
+};
+
+__global__ void __launch_bounds__(IG_THREADS, 1) nerf_input_grad_tc_kernel(const IgParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // barriers: wfull, full[2], empty[2], accf[2], acce[2]
+    const uint32_t bar_w = base + IG_SM_BAR, bar_full = bar_w + 8, bar_empty = bar_full + 16, bar_accf = bar_empty + 16,
+                   bar_acce = bar_accf + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + IG_SM_BAR + 96);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+            mbar_init(bar_accf + 8 * i, 1);
+            mbar_init(bar_acce + 8 * i, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(base + IG_SM_BAR + 96, 128);     // two 64-column accumulators
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_tiles = (P.n_tiles > blockIdx.x) ? (int)((P.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_w, IG_W_BYTES);
+            bulk_g2s(base + IG_SM_W, P.w_img, IG_W_BYTES, bar_w);
+            int slot = 0; uint32_t par = 1;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int64_t tile = blockIdx.x + (int64_t)i * gridDim.x;
+                const uint8_t* tb = P.dz_save + tile * DZ_TILE_BYTES;
+                for (int img = 0; img < 2; ++img) {            // dZ0 then dZ5
+                    mbar_wait(bar_empty + 8 * slot, par, 21);
+                    mbar_arrive_expect_tx(bar_full + 8 * slot, 65536);
+                    bulk_g2s(base + IG_SM_A + slot * 65536, tb + DZ_Z + (img == 0 ? 0 : 5 * 65536), 65536, bar_full + 8 * slot);
+                    if (++slot == 2) { slot = 0; par ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+            mbar_wait(bar_w, 0, 22);
+            int slot = 0; uint32_t par = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int ab = i & 1;                           // accumulator buffer
+                const uint32_t ap = (uint32_t)((i >> 1) & 1);
+                if (i >= 2) mbar_wait(bar_acce + 8 * ab, ap ^ 1, 23);   // epilogue of tile i-2 has drained this buffer
+                tc_fence_after();
+                for (int img = 0; img < 2; ++img) {
+                    mbar_wait(bar_full + 8 * slot, par, 24);
+                    tc_fence_after();
+                    const uint32_t a0 = base + IG_SM_A + slot * 65536, b0 = base + IG_SM_W + img * 32768;
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = make_sdesc_sw128(a0 + kb * 16384 + k * 32, 16, 1024);
+                            const uint64_t bd = make_sdesc_sw128(b0 + kb * 8192 + k * 32, 16, 1024);
+                            mma_bf16_ss(tmem_base + ab * 64, ad, bd, idesc, (img > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    mma_commit(bar_empty + 8 * slot);
+                    if (++slot == 2) { slot = 0; par ^= 1; }
+                }
+                mma_commit(bar_accf + 8 * ab);
+            }
+        }
+    } else {
+        const int row = threadIdx.x;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int64_t tile = blockIdx.x + (int64_t)i * gridDim.x;
+            const int64_t m = tile * TILE_M + row;
+            const bool valid = m < P.M;
+            const int64_t mm = valid ? m : (P.M - 1);
+            const int64_t ray = mm / P.N;
+            const float tv = P.t[mm];
+            float dr[3], p[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                dr[c] = P.d[ray * 3 + c];
+                p[c] = __fadd_rn(P.o[ray * 3 + c], __fmul_rn(dr[c], tv));
+            }
+            const int ab = i & 1;
+            mbar_wait(bar_accf + 8 * ab, (uint32_t)((i >> 1) & 1), 25);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            const uint32_t ta = tmem_base + (uint32_t(32 * warp) << 16) + ab * 64;
+            tmem_ld32(ta, v0);
+            tmem_ld32(ta + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(bar_acce + 8 * ab);
+            float de[64];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) { de[q] = __uint_as_float(v0[q]); de[32 + q] = __uint_as_float(v1[q]); }
+            // encoding backward: e = [p, sin(2^i p), cos(2^i p)]_i  ->  dp = de_p + sum_i 2^i (cos * de_sin - sin * de_cos)
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float dp = de[c];
+                float sv, cv;
+#pragma unroll
+                for (int oct = 0; oct < 10; ++oct) {
+                    if (oct == 0 || oct == 5) sincosf((float)(1 << oct) * p[c], &sv, &cv);
+                    else { const float s2 = 2.f * sv * cv, c2 = fmaf(-2.f * sv, sv, 1.f); sv = s2; cv = c2; }
+                    dp = fmaf((float)(1 << oct), cv * de[3 + 6 * oct + c] - sv * de[3 + 6 * oct + 3 + c], dp);
+                }
+                acc = fmaf(dr[c], dp, acc);
+            }
+            if (valid) P.dtp[m] = acc;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 5. Backward of sort(concat([t, sample_pdf(...)])) + sample_pdf into the coarse compositing weights
+// (models.py:165-167, data_utils.py:179-220).  One warp per ray.
+//   d_t_all[pos] = dtp[pos] + d_delta[pos-1] - d_delta[pos]      (delta_n = t[n+1] - t[n] in the fine compositing)
+//   only sorted slots that came from sample_pdf (src_idx >= Nc) carry gradient; t, t_mid, u are constants.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) sample_pdf_bwd_kernel(const float* __restrict__ t, const float* __restrict__ weights,
+                                                             const float* __restrict__ u, const int32_t* __restrict__ src_idx,
+                                                             const float* __restrict__ dtp, const float* __restrict__ d_delta,
+                                                             int64_t B, int nc, int nf, float* __restrict__ d_w) {
+    extern __shared__ float smem_pb[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int per_warp = 3 * (nc + 1) + nc;
+    float* cdf = smem_pb + (size_t)wib * per_warp;      // nc + 1
+    float* tm = cdf + nc + 1;                           // nc - 1 (+pad)
+    float* dcdf = tm + nc + 1;                          // nc + 1
+    float* pdf = dcdf + nc + 1;                         // nc
+    const int na = nc + nf;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < B; ray += warps_total) {
+        const float* w = weights + ray * nc;
+        const float* tr = t + ray * nc;
+        // forward quantities (same arithmetic as build_cdf / invert_cdf in ops.cu)
+        float ssum = 0.f;
+        for (int n = lane; n < nc; n += 32) ssum += (w[n] + 1e-5f);
+        ssum = warp_sum_f(ssum);
+        float carry = 0.f;
+        if (lane == 0) cdf[0] = 0.f;
+        for (int b0 = 0; b0 < nc; b0 += 32) {
+            const int n = b0 + lane;
+            const float pv = (n < nc) ? __fdiv_rn(w[n] + 1e-5f, ssum) : 0.f;
+            float incl = pv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const float x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+            if (n < nc) { cdf[n + 1] = carry + incl; pdf[n] = pv; }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        for (int n = lane; n < nc - 1; n += 32) tm[n] = __fmul_rn(0.5f, __fadd_rn(tr[n + 1], tr[n]));
+        for (int n = lane; n <= nc; n += 32) dcdf[n] = 0.f;
+        __syncwarp();
+        for (int pos = lane; pos < na; pos += 32) {
+            const int k = src_idx[ray * na + pos];
+            if (k < nc) continue;
+            const int j = k - nc;
+            float g = dtp[ray * na + pos];
+            if (pos > 0) g += d_delta[ray * na + pos - 1];
+            if (pos < na - 1) g -= d_delta[ray * na + pos];
+            const float uu = u[ray * nf + j];
+            int lo = 0, hi = nc + 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] > uu) hi = mid; else lo = mid + 1; }
+            const int below = max(0, lo - 1), above = min(nc, lo);
+            const float cb = cdf[below], ca = cdf[above];
+            const float tb = tm[min(nc - 2, below)], ta = tm[min(nc - 2, above)];
+            const float den = ca - cb;
+            const float span = ta - tb;
+            if (den < 1e-5f) {
+                atomicAdd(&dcdf[below], -g * span);             // samples = tb + (u - cdf_b) * span
+            } else {
+                const float f = (uu - cb) / den;
+                atomicAdd(&dcdf[below], g * span * (f - 1.0f) / den);
+                atomicAdd(&dcdf[above], -g * span * f / den);
+            }
+        }
+        __syncwarp();
+        // d_pdf[i] = sum_{k > i} d_cdf[k]  (cdf = [0, cumsum(pdf)]); reverse scan in chunks of 32 from the top
+        float tail = 0.f, dot = 0.f;
+        for (int b0 = ((nc - 1) / 32) * 32; b0 >= 0; b0 -= 32) {
+            const int n = b0 + lane;
+            float v = (n < nc) ? dcdf[n + 1] : 0.f;
+            float incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const float x = __shfl_down_sync(0xffffffffu, incl, o); if (lane + o < 32) incl += x; }
+            const float dp = incl + tail;
+            if (n < nc) { dcdf[n + 1] = dp; dot += dp * pdf[n]; }
+            tail += __shfl_sync(0xffffffffu, incl, 0);
+        }
+        dot = warp_sum_f(dot);
+        __syncwarp();
+        for (int n = lane; n < nc; n += 32) d_w[ray * nc + n] = (dcdf[n + 1] - dot) / ssum;
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 namespace nerf {
@@ -533,6 +787,8 @@ int tc_train_alloc(nerf_ctx* ctx) {
         NERF_CUDA(cudaMalloc((void**)&ctx->mask_save[net], (size_t)(tiles[net] * MASK_TILE_BYTES)));
         NERF_CUDA(cudaMalloc((void**)&ctx->w_bwd[net], (size_t)B_CHUNKS * CHUNK_BYTES));
     }
+    NERF_CUDA(cudaMalloc((void**)&ctx->w_ig, IG_W_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_input_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM));
     NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     NERF_CUDA(cudaFuncSetAttribute(nerf_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     return NERF_OK;
@@ -612,3 +868,50 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
 }  // namespace nerf
 
 extern "C" int nerf_debug_flags(int flags) { nerf::g_wg_debug = flags; return NERF_OK; }
+
+namespace nerf {
+// dtp[m] = < d_ray, dL/dpts[m] > of one net from its saved dZ0 / dZ5 images (tc_backward must have run)
+int tc_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N, float* dtp,
+                  cudaStream_t st) {
+    const int64_t M = B * (int64_t)N;
+    BlobOffsets off = make_offsets(ctx);
+    pack_ig_kernel<<<16, 256, 0, st>>>(ctx->params + (int64_t)net * ctx->n_params, off, ctx->w_ig);
+    NERF_LAUNCHED();
+    IgParams P;
+    P.dz_save = reinterpret_cast<const uint8_t*>(ctx->dz_save[net]);
+    P.w_img = ctx->w_ig;
+    P.o = o; P.d = d; P.t = t; P.N = N; P.M = M;
+    P.n_tiles = ceil_div(M, TILE_M);
+    P.dtp = dtp;
+    const int grid = (int)(P.n_tiles < num_sms() ? P.n_tiles : num_sms());
+    nerf_input_grad_tc_kernel<<<grid, IG_THREADS, IG_SMEM, st>>>(P);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+
+int sample_pdf_backward(const float* t, const float* weights, const float* u, const int32_t* src_idx, const float* dtp,
+                        const float* d_delta, int64_t B, int nc, int nf, float* d_w, cudaStream_t st) {
+    const int threads = 128;
+    const size_t smem = (size_t)(threads / 32) * (3 * (nc + 1) + nc) * sizeof(float);
+    if (smem > 48 * 1024) return fail(NERF_ERR_INVALID, "sample_pdf_backward: nc too large");
+    sample_pdf_bwd_kernel<<<stream_grid(B * 32, threads), threads, smem, st>>>(t, weights, u, src_idx, dtp, d_delta, B, nc, nf, d_w);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+}  // namespace nerf
+
+// test hook: backward of sort(concat([t, sample_pdf])) given dL/dt_all contributions: dtp (direct) and, optionally,
+// d_delta (dL/d(delta_n) of the fine compositing, delta_n = t_all[n+1] - t_all[n]); either may be NULL (= zeros)
+extern "C" int nerf_sample_pdf_bwd(const float* t, const float* weights, const float* u, const int32_t* src_idx,
+                                   const float* dtp, const float* d_delta, int64_t batch, int nc, int nf, float* d_w,
+                                   void* stream) {
+    NERF_CHECK_ARG(t && weights && u && src_idx && d_w && batch >= 1 && nc >= 2 && nf >= 1, "bad arguments");
+    float* zeros = nullptr;
+    NERF_CUDA(cudaMalloc(&zeros, (size_t)batch * (nc + nf) * 4));
+    NERF_CUDA(cudaMemsetAsync(zeros, 0, (size_t)batch * (nc + nf) * 4, (cudaStream_t)stream));
+    int rc = nerf::sample_pdf_backward(t, weights, u, src_idx, dtp ? dtp : zeros, d_delta ? d_delta : zeros, batch, nc, nf,
+                                       d_w, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(zeros);
+    return rc;
+}

@@ -224,7 +224,7 @@ class NeRFTrainer:
     """models.py:64-225 -- coarse->fine forward pass, train/test steps, minibatched rendering."""
 
     def __init__(self, coarse_model, fine_model, batch_size, ns_coarse, ns_fine, l_xyz, l_dir,
-                 precision=PRECISION_BF16_TC, stop_grad_samples=True, process_group=None):
+                 precision=PRECISION_BF16_TC, stop_grad_samples=False, process_group=None):
         if not isinstance(coarse_model, NerfModel):
             raise TypeError("coarse_model must be a NerfModel (create_nerf_complete_model) instance")
         if not isinstance(fine_model, NerfModel):
@@ -332,7 +332,7 @@ class NeRFTrainer:
                                                     _ptr(out), _stream()), "mlp_forward_rays")
         return out
 
-    def debug_mlp_grads(self, net, ray_origins, ray_directions, t_vals, d_preds):
+    def debug_mlp_grads(self, net, ray_origins, ray_directions, t_vals, d_preds, return_input_grad=False):
         """Diagnostics: (preds, d(sum(preds*d_preds))/d(weights of `net`)) through the tcgen05 forward
         (saved activations) and backward kernels.  Needs compile() (training workspace)."""
         o, d, t, dp = _f32(ray_origins), _f32(ray_directions), _f32(t_vals), _f32(d_preds)
@@ -343,7 +343,13 @@ class NeRFTrainer:
                                                    _ptr(preds), _stream()), "debug_mlp_grads")
         g = self._ctx.grad_tensor()
         n = self._ctx.n_params
-        return preds, g[idx * n:(idx + 1) * n].clone()
+        grads = g[idx * n:(idx + 1) * n].clone()
+        if not return_input_grad:
+            return preds, grads
+        dtp = torch.empty((B, N), device=o.device, dtype=torch.float32)
+        _lib.check(_lib.lib().nerf_debug_input_grad(self._ctx.handle, idx, _ptr(o), _ptr(d), _ptr(t), B, N, _ptr(dtp),
+                                                    _stream()), "debug_input_grad")
+        return preds, grads, dtp
 
     def forward_pass_with_minibatch(self, ray_origins, ray_directions, t_vals, l_xyz=None, l_dir=None, batch_size=512,
                                     training=False, u_pdf=None, precision=None, maps_only=False):

@@ -17,12 +17,12 @@ def nk():
     return nk
 
 
-def _trainer(nk, g, wc, wf, batch=None, lr=5e-4):
+def _trainer(nk, g, wc, wf, batch=None, lr=5e-4, stop_grad=True):
     mc = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
     mf = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
     mc.set_flat_weights(O.flatten_weights(wc))
     mf.set_flat_weights(O.flatten_weights(wf))
-    tr = nk.NeRFTrainer(mc, mf, batch or g["o"].shape[0], int(g["Nc"]), int(g["Nf"]), 10, 4)
+    tr = nk.NeRFTrainer(mc, mf, batch or g["o"].shape[0], int(g["Nc"]), int(g["Nf"]), 10, 4, stop_grad_samples=stop_grad)
     tr.compile(nk.Adam(learning_rate=lr), nk.MeanSquaredError())
     return tr
 
@@ -172,3 +172,149 @@ def test_training_reduces_loss_like_the_oracle(nk):
     # weights round-trip through the trainer
     w_after = tr.coarse_model.get_flat_weights()
     assert np.isfinite(w_after).all() and np.abs(w_after - O.flatten_weights(golden_weights(g)[0])).max() > 1e-4
+
+
+# ---------------------------------------------------------------- reference semantics: no stop-gradient (quirk Q5)
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_sample_pdf_backward_matches_autograd(nk, name):
+    """d(sum(t_all * g)) / d(weights) through sort(concat([t, sample_pdf(t_mid, w, Nf)])) (models.py:165-167)."""
+    from nerf_keras_b200 import _lib
+    g = load_golden(name)
+    Nc, Nf = int(g["Nc"]), int(g["Nf"])
+    t = torch.from_numpy(g["t"]); u = torch.from_numpy(g["u_pdf"])
+    w = torch.from_numpy(g["wt_c"]).clone().requires_grad_(True)
+    gen = torch.Generator().manual_seed(9)
+    gt = torch.randn(t.shape[0], Nc + Nf, generator=gen)
+    t_mid = 0.5 * (t[:, 1:] + t[:, :-1])
+    t_all, _ = torch.sort(torch.cat([t, O.sample_pdf(t_mid, w, Nf, u=u)], -1), -1)
+    (t_all * gt).sum().backward()
+    t_all_c, idx = nk.resample_merge(g["t"], g["wt_c"], Nf, u=g["u_pdf"], return_index=True)
+    d_w = torch.empty(t.shape[0], Nc, device="cuda")
+    tc, wc_, uc, gc = cuda(g["t"]), cuda(g["wt_c"]), cuda(g["u_pdf"]), cuda(gt.numpy())
+    _lib.check(_lib.lib().nerf_sample_pdf_bwd(tc.data_ptr(), wc_.data_ptr(), uc.data_ptr(), idx.data_ptr(), gc.data_ptr(), 0,
+                                              t.shape[0], Nc, Nf, d_w.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    ref, got = w.grad.numpy(), d_w.cpu().numpy()
+    # per ray: direction and scale (knot gradients are ill-conditioned where a bin is nearly empty: 1/den)
+    num = (ref * got).sum(-1); den = np.linalg.norm(ref, axis=-1) * np.linalg.norm(got, axis=-1) + 1e-30
+    assert np.median(num / den) > 0.999 and (num / den > 0.98).mean() > 0.95
+    assert abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_delta_path_through_fine_compositing_matches_autograd(nk, name):
+    """Coarse weights -> sample_pdf -> sort -> fine compositing deltas -> colour, with FIXED fine predictions (fp32 end
+    to end, identical inputs): d(sum(rgb_f * g)) / d(w_c) via volume_render_bwd's d_delta and the resampling backward."""
+    from nerf_keras_b200 import _lib
+    g = load_golden(name)
+    Nc, Nf = int(g["Nc"]), int(g["Nf"])
+    B = g["t"].shape[0]
+    t = torch.from_numpy(g["t"]); u = torch.from_numpy(g["u_pdf"]); pred_f = torch.from_numpy(g["pred_f"])
+    w = torch.from_numpy(g["wt_c"]).clone().requires_grad_(True)
+    gr = torch.randn(B, 3, generator=torch.Generator().manual_seed(3))
+    t_mid = 0.5 * (t[:, 1:] + t[:, :-1])
+    t_all, _ = torch.sort(torch.cat([t, O.sample_pdf(t_mid, w, Nf, u=u)], -1), -1)
+    rgb, _, _ = O.volume_render(pred_f, t_all)
+    (rgb * gr).sum().backward()
+    ref = w.grad.numpy()
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    t_all_c, idx = nk.resample_merge(g["t"], g["wt_c"], Nf, u=g["u_pdf"], return_index=True)
+    pf, grc = cuda(g["pred_f"]), cuda(gr.numpy())
+    d_preds = torch.empty(B, Nc + Nf, 4, device="cuda"); d_delta = torch.empty(B, Nc + Nf, device="cuda")
+    _lib.check(L.nerf_volume_render_bwd(pf.data_ptr(), t_all_c.data_ptr(), grc.data_ptr(), 0, B, Nc + Nf, d_preds.data_ptr(),
+                                        d_delta.data_ptr(), st))
+    tc, wc_, uc = cuda(g["t"]), cuda(g["wt_c"]), cuda(g["u_pdf"])
+    d_w = torch.empty(B, Nc, device="cuda")
+    _lib.check(L.nerf_sample_pdf_bwd(tc.data_ptr(), wc_.data_ptr(), uc.data_ptr(), idx.data_ptr(), 0, d_delta.data_ptr(), B, Nc,
+                                     Nf, d_w.data_ptr(), st))
+    got = d_w.cpu().numpy()
+    num = (ref * got).sum(-1); den = np.linalg.norm(ref, axis=-1) * np.linalg.norm(got, axis=-1) + 1e-30
+    assert np.median(num / den) > 0.999 and (num / den > 0.98).mean() > 0.9, (np.median(num / den), (num / den > 0.98).mean())
+    assert abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1.0) < 0.1
+
+
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_input_gradient_matches_autograd(nk, name):
+    """< d_ray, dL/dpts > of the fine net (tcgen05 dZ0 W0^T + dZ5 W5b^T, positional-encoding backward) vs autograd."""
+    g = load_golden(name)
+    wc, wf = golden_weights(g)
+    o, d = torch.from_numpy(g["o"]), torch.from_numpy(g["d"])
+    t = torch.from_numpy(g["t_all"]).clone().requires_grad_(True)
+    d_preds = torch.tensor([0.05, -0.03, 0.04, 0.02]).expand(t.shape + (4,)).contiguous()
+    rays, dirs = O.sample_rays(o, d, t)
+    pred = O.nerf_mlp(wf, O.encode_position(rays, 10), O.encode_position(dirs.detach(), 4))
+    (pred * d_preds).sum().backward()
+    ref = t.grad.numpy()
+    tr = _trainer(nk, g, wc, wf, stop_grad=False)
+    _, _, dtp = tr.debug_mlp_grads("fine", g["o"], g["d"], g["t_all"], d_preds.numpy(), return_input_grad=True)
+    got = dtp.cpu().numpy()
+    assert np.isfinite(got).all()
+    cos = float((ref * got).sum() / (np.linalg.norm(ref) * np.linalg.norm(got)))
+    assert cos > 0.97 and abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1.0) < 0.1, (cos, np.linalg.norm(got), np.linalg.norm(ref))
+
+
+@pytest.mark.parametrize("name", ["lego_small", "fern_small"])
+def test_unstopped_gradient_into_coarse_weights_at_identical_inputs(nk, name):
+    """The whole extra path of the reference (fine loss -> fine compositing -> fine MLP input gradient ->
+    sort/sample_pdf -> dL/dw_coarse), CUDA kernels vs autograd on the oracle, starting from the SAME coarse weights
+    w_c.  (End to end the term is chaotic: a 1e-4 relative change of the coarse weights decorrelates it in the fp32
+    oracle itself, see DESIGN.md -- so it is pinned here with w_c held identical.)"""
+    from nerf_keras_b200 import _lib
+    g = load_golden(name)
+    wc, wf = golden_weights(g)
+    Nc, Nf = int(g["Nc"]), int(g["Nf"])
+    B = g["o"].shape[0]
+    L = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    tr = _trainer(nk, g, wc, wf, stop_grad=False)
+    # CUDA forward (bf16 tensor-core MLPs)
+    rgbs, depths, ws, preds, t_all = tr.forward_pass(g["o"], g["d"], g["t"], u_pdf=g["u_pdf"], return_t_all=True)
+    w_c = ws[0].contiguous()
+    _, idx = nk.resample_merge(g["t"], w_c, Nf, u=g["u_pdf"], return_index=True)
+    img = cuda(g["img"])
+    d_rgb_f = (2.0 * (rgbs[1] - img) / (3 * B)).contiguous()
+    d_pred_f = torch.empty(B, Nc + Nf, 4, device="cuda"); d_delta = torch.empty(B, Nc + Nf, device="cuda")
+    _lib.check(L.nerf_volume_render_bwd(preds[1].data_ptr(), t_all.data_ptr(), d_rgb_f.data_ptr(), 0, B, Nc + Nf,
+                                        d_pred_f.data_ptr(), d_delta.data_ptr(), st))
+    _, _, dtp = tr.debug_mlp_grads("fine", g["o"], g["d"], t_all, d_pred_f, return_input_grad=True)
+    tc, uc = cuda(g["t"]), cuda(g["u_pdf"])
+    d_w = torch.empty(B, Nc, device="cuda")
+    _lib.check(L.nerf_sample_pdf_bwd(tc.data_ptr(), w_c.data_ptr(), uc.data_ptr(), idx.data_ptr(), dtp.data_ptr(),
+                                     d_delta.data_ptr(), B, Nc, Nf, d_w.data_ptr(), st))
+    got = d_w.cpu().numpy()
+    # oracle from the same w_c (fp32 fine net)
+    o, d, t, u = map(torch.from_numpy, (g["o"], g["d"], g["t"], g["u_pdf"]))
+    w = w_c.cpu().clone().requires_grad_(True)
+    t_mid = 0.5 * (t[:, 1:] + t[:, :-1])
+    ta, _ = torch.sort(torch.cat([t, O.sample_pdf(t_mid, w, Nf, u=u)], -1), -1)
+    rays, dirs = O.sample_rays(o, d, ta)
+    pf = O.nerf_mlp(wf, O.encode_position(rays, 10), O.encode_position(dirs, 4))
+    rgb_f, _, _ = O.volume_render(pf, ta)
+    O.mse(torch.from_numpy(g["img"]), rgb_f).backward()
+    ref = w.grad.numpy()
+    assert np.isfinite(got).all()
+    num = (ref * got).sum(-1); den = np.linalg.norm(ref, axis=-1) * np.linalg.norm(got, axis=-1) + 1e-30
+    rn, gn = np.linalg.norm(ref, axis=-1), np.linalg.norm(got, axis=-1)
+    print(name, "per-ray cosine median", np.median(num / den), "frac > 0.9:", (num / den > 0.9).mean(),
+          "median norm ratio", np.median(gn / (rn + 1e-30)), "total norm", np.linalg.norm(got), np.linalg.norm(ref))
+    assert np.median(num / den) > 0.95 and (num / den > 0.8).mean() > 0.8
+    assert 0.8 < np.median(gn / (rn + 1e-30)) < 1.25
+
+
+def test_training_with_reference_semantics_reduces_loss(nk):
+    """40 Adam steps with the reference's (un-stopped) gradient.  The fine loss -- the one the reference reports as
+    `loss` -- goes down as in the oracle run of the same schedule; the coarse loss is driven by the chaotic
+    sample-position term in both implementations (it stalls or rises), so it is only required to stay finite."""
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    tr = _trainer(nk, g, wc, wf, stop_grad=False)
+    batch = (g["img"], (g["o"], g["d"], g["t"]))
+    fl = lambda logs: {k: float(v) for k, v in logs.items()}
+    first = fl(tr.train_step(batch, u_pdf=g["u_pdf"]))
+    tr.reset_metrics()
+    for _ in range(40):
+        last = fl(tr.train_step(batch, u_pdf=g["u_pdf"]))
+        tr.reset_metrics()
+    assert np.isfinite(list(last.values())).all()
+    assert last["loss"] < 0.6 * first["loss"], (first, last)          # oracle: 0.1334 -> 0.0447
+    assert last["loss_coarse"] < 1.0
