@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
             const int64_t ray0 = ((m_first < P.M) ? m_first : (P.M - 1)) / P.N;
             const int64_t m_last = (m_first + TILE_M - 1 < P.M) ? (m_first + TILE_M - 1) : (P.M - 1);
             const int n_rays = (int)(m_last / P.N - ray0) + 1;
-            const bool staged = n_rays <= DIRB_ROWS;
+            const bool staged = n_rays <= DIRB_ROWS && n_rays * 32 <= TILE_M;   // one float4 per thread
             float4 db_pref = make_float4(0.f, 0.f, 0.f, 0.f);
             const int db_idx = row;                          // thread i prefetches float4 i of the staged block
             if (staged && db_idx < n_rays * 32)
@@ -545,6 +545,267 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair forward kernel with 16 worker warps ("tc16").
+// Same program, weights, hand-offs and MMA issue as nerf_mlp_fwd_tc_kernel<SAVE, true> (cta_group::2, M = 256
+// MMAs over an SM pair, each CTA staging half of the weight rows), but every 128-row sub-tile is served by EIGHT
+// epilogue warps instead of four: warp w owns TMEM lane quarter (w & 3) and column half ((w >> 2) & 1), so a
+// row's 256 accumulator columns are converted by two threads in parallel.  The epilogue of one sub-tile then
+// fits under the other sub-tile's MMA phase (2048 cycles), which is what the pair kernel needs to keep the
+// tensor pipe busy.  Sigma / rgb head partial sums of the two column halves are combined through shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int NUM_THREADS16 = 608;   // 16 worker warps + producer warp + 2 issuer / forwarder warps
+
+template <bool RELU, bool SIGMA, bool SAVE, int HALF>
+__device__ __forceinline__ void trunk_half(uint32_t t_lane, const float* bias, const float* wsig, uint64_t& sig2,
+                                           uint32_t (&mask)[4], const RowStore& rs) {
+    uint32_t v[32];
+    tmem_ld32(t_lane + HALF * 128, v); tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, HALF * 4 + 0, true>(v, bias, wsig, sig2, mask[0], rs, nullptr);
+    tmem_ld32(t_lane + HALF * 128 + 32, v); tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, HALF * 4 + 1, true>(v, bias, wsig, sig2, mask[1], rs, nullptr);
+    tmem_ld32(t_lane + HALF * 128 + 64, v); tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, HALF * 4 + 2, true>(v, bias, wsig, sig2, mask[2], rs, nullptr);
+    tmem_ld32(t_lane + HALF * 128 + 96, v); tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, HALF * 4 + 3, true>(v, bias, wsig, sig2, mask[3], rs, nullptr);
+}
+
+// half of the positional encoding of one point, packed bf16x2: HALF 0 = channels 0..31 (x, y, z and octaves 0..4
+// except the last cosine), HALF 1 = channels 32..63 (cos(16 z), octaves 5..9, zero pad).  sincosf at the first
+// octave of each half, exact angle doubling for the next four.
+template <int HALF>
+__device__ __forceinline__ void encode_half(const float (&p)[3], uint32_t (&E)[16]) {
+    float e[32];
+    if (HALF == 0) {
+        e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
+    } else {
+        e[0] = cosf(16.f * p[2]);
+        e[31] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float sv, cv;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int i = HALF * 5 + j;
+            if (j == 0) sincosf((float)(1 << i) * p[c], &sv, &cv);
+            else {
+                const float s2 = 2.f * sv * cv;
+                const float c2 = fmaf(-2.f * sv, sv, 1.f);
+                sv = s2; cv = c2;
+            }
+            const int is = 3 + 6 * i + c - HALF * 32, ic = is + 3;
+            if (is < 32) e[is] = sv;
+            if (ic < 32) e[ic] = cv;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) E[q] = pack_bf16x2(e[2 * q], e[2 * q + 1]);
+}
+
+template <bool SAVE, int HALF>
+__device__ __forceinline__ void worker16(const FwdParams& P, uint8_t* smem, uint32_t base, const Barriers& B,
+                                         uint32_t tmem_base, const float* side, int s, int q4, int lane, int rank,
+                                         int unit, int n_units_grid, int my_units) {
+    const int row = 32 * q4 + lane;
+    const int sub_tid = HALF * TILE_M + row;                        // 0..255 inside the sub-tile's worker group
+    const uint32_t act_base = base + SM_ACT + s * 65536;
+    const uint32_t t_lane = tmem_base + (uint32_t(32 * q4) << 16) + s * 256;
+    const bool elected = (sub_tid == 0);
+    float* dbs = reinterpret_cast<float*>(smem + SM_DIRB) + s * (DIRB_ROWS * 128);
+    float4* part = reinterpret_cast<float4*>(smem + SM_ACT + s * 65536 + 49152) + row;   // head partial sums (K-block 3)
+    RowStore rs;
+    rs.init(act_base, row);
+    const uint32_t bar_l = B.actr + 16 * s + 8 * HALF;                // this column half's A-tile hand-off barrier
+    const uint32_t bar_mine = (rank != 0) ? map_to_cta(bar_l, 0) : bar_l;
+    const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;
+    uint32_t accf_par = 0;
+    uint32_t E[16];
+    uint32_t Elo[2] = {0u, 0u};
+    auto arrive = [&]() { if (rank != 0) mbar_arrive_cluster(bar_mine); else mbar_arrive(bar_mine); };
+    auto stage_enc = [&]() {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rs.store<0>(HALF * 4 + c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
+        if (HALF == 0) {
+            rs.store<1>(0, Elo[0], Elo[1], 0u, 0u);
+            rs.store<1>(1, 0u, 0u, 0u, 0u);
+        }
+    };
+
+    for (int it = 0; it < my_units; ++it) {
+        const int64_t wu = unit + (int64_t)it * n_units_grid;
+        const int64_t tile = wu * 4 + s * 2 + rank;
+        const int64_t g_row = tile * TILE_M + row;
+        const bool valid = g_row < P.M;
+        const int64_t gr = valid ? g_row : (P.M - 1);
+        const int64_t ray = gr / P.N;
+        uint8_t* save_tile = SAVE ? P.act_save + tile * SAVE_TILE_BYTES : nullptr;
+        uint32_t* mask_tile = SAVE ? P.mask_save + tile * (MASK_TILE_BYTES / 4) : nullptr;
+
+        const int64_t m_first = tile * TILE_M;
+        const int64_t ray0 = ((m_first < P.M) ? m_first : (P.M - 1)) / P.N;
+        const int64_t m_last = (m_first + TILE_M - 1 < P.M) ? (m_first + TILE_M - 1) : (P.M - 1);
+        const int n_rays = (int)(m_last / P.N - ray0) + 1;
+        const bool staged = n_rays <= DIRB_ROWS;
+        float4 db_pref = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (staged && sub_tid < n_rays * 32)
+            db_pref = __ldg(reinterpret_cast<const float4*>(P.dirbias + ray0 * 128) + sub_tid);
+
+        {
+            const float tv = P.t[gr];
+            float p[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(P.o[ray * 3 + c], __fmul_rn(P.d[ray * 3 + c], tv));
+            encode_half<HALF>(p, E);
+            if (HALF == 0) {
+                float lo[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) lo[c] = p[c] - __bfloat162float(__float2bfloat16_rn(p[c]));
+                Elo[0] = pack_bf16x2(lo[0], lo[1]);
+                Elo[1] = pack_bf16x2(lo[2], 0.f);
+            }
+        }
+        if (SAVE && elected) bulk_wait_read0();
+        named_bar_sync(1 + s, 2 * TILE_M);
+        stage_enc();
+        if (staged && sub_tid < n_rays * 32) reinterpret_cast<float4*>(dbs)[sub_tid] = db_pref;
+        tc_fence_before();
+        fence_proxy_async_all();
+        if (SAVE) {
+            named_bar_sync(1 + s, 2 * TILE_M);
+            if (elected) { bulk_s2g(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
+        }
+        arrive();
+
+        float sig = 0.f;
+        for (int ph = 0; ph < N_PHASES; ++ph) {
+            if (elected) trace_ev(P.trace, 2 + s, it, ph, 0);
+            mbar_wait(bar_h0, accf_par, 2);
+            mbar_wait(bar_h1, accf_par, 6);
+            accf_par ^= 1;
+            tc_fence_after();
+            if (elected) trace_ev(P.trace, 2 + s, it, ph, 1);
+            if (SAVE) {                                              // the previous image's bulk store has read the tile
+                if (elected) bulk_wait_read0();
+                named_bar_sync(1 + s, 2 * TILE_M);
+            }
+            if (ph == 5) {
+                stage_enc();
+                tc_fence_before();
+                fence_proxy_async_all();
+                arrive();
+                continue;
+            }
+            if (ph < 10) {
+                const int layer = (ph <= 4) ? ph : (ph == 6 ? 5 : (ph == 7 ? 6 : (ph == 8 ? 7 : 8)));
+                const float* bias = side + (layer < 8 ? SIDE_BIAS + layer * H : SIDE_BFEAT);
+                const bool relu = layer < 8;
+                const float* wsig = side + SIDE_WSIG;
+                uint32_t mask[4];
+                uint64_t sig2 = 0ull;
+                if (ph == 8) trunk_half<true, true, SAVE, HALF>(t_lane, bias, wsig, sig2, mask, rs);
+                else if (relu) trunk_half<true, false, SAVE, HALF>(t_lane, bias, wsig, sig2, mask, rs);
+                else trunk_half<false, false, SAVE, HALF>(t_lane, bias, wsig, sig2, mask, rs);
+                if (ph == 8) {
+                    float a, b;
+                    f2_unpack(sig2, a, b);
+                    sig = a + b;
+                }
+                tc_fence_before();
+                fence_proxy_async_all();
+                if (SAVE) {
+                    if (relu)
+                        *reinterpret_cast<uint4*>(mask_tile + ((size_t)layer * 128 + row) * 8 + HALF * 4) =
+                            make_uint4(mask[0], mask[1], mask[2], mask[3]);
+                    named_bar_sync(1 + s, 2 * TILE_M);
+                    if (elected) {
+                        int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
+                        bulk_s2g(save_tile + off, act_base, 65536);
+                        bulk_commit();
+                    }
+                }
+                if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);
+                arrive();
+            } else {
+                uint64_t r2 = 0ull, g2 = 0ull, b2 = 0ull;
+                uint32_t mask[2];
+                const float* db = staged ? (dbs + (int)(ray - ray0) * 128) : (P.dirbias + ray * 128);
+                uint32_t v[32];
+                tmem_ld32(t_lane + HALF * 64, v); tmem_ld_wait();
+                ddir_group<SAVE, 2 * HALF>(v, db, side, r2, g2, b2, mask[0], rs);
+                tmem_ld32(t_lane + HALF * 64 + 32, v); tmem_ld_wait();
+                ddir_group<SAVE, 2 * HALF + 1>(v, db, side, r2, g2, b2, mask[1], rs);
+                float ra, rb, ga, gb, ba, bb;
+                f2_unpack(r2, ra, rb); f2_unpack(g2, ga, gb); f2_unpack(b2, ba, bb);
+                if (HALF == 1) *part = make_float4(ra + rb, ga + gb, ba + bb, sig);
+                tc_fence_before();
+                if (SAVE) {
+                    uint32_t* mp = mask_tile + ((size_t)8 * 128 + row) * 8;
+                    *reinterpret_cast<uint2*>(mp + HALF * 2) = make_uint2(mask[0], mask[1]);
+                    if (HALF == 1) *reinterpret_cast<uint4*>(mp + 4) = make_uint4(0u, 0u, 0u, 0u);
+                    fence_proxy_async_all();
+                }
+                named_bar_sync(1 + s, 2 * TILE_M);
+                if (HALF == 0) {
+                    const float4 o = *part;
+                    if (valid)
+                        P.preds[g_row] = make_float4((ra + rb) + o.x + side[SIDE_BRGB], (ga + gb) + o.y + side[SIDE_BRGB + 1],
+                                                     (ba + bb) + o.z + side[SIDE_BRGB + 2], (sig + o.w) + side[SIDE_BSIG]);
+                }
+                if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);
+                if (SAVE && elected) { bulk_s2g(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
+            }
+        }
+    }
+    if (SAVE && elected) bulk_wait_all0();
+}
+
+template <bool SAVE>
+__global__ void __launch_bounds__(NUM_THREADS16, 1) nerf_mlp_fwd_tc16_kernel(const FwdParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int unit = (int)(blockIdx.x >> 1);
+    const int n_units_grid = (int)(gridDim.x >> 1);
+    const int64_t n_units = (P.n_pairs + 1) / 2;                      // 512-row quads, one per cluster
+    Barriers B;
+    init_barriers(base, B, true);
+    float* side = reinterpret_cast<float*>(smem + SM_SIDE);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
+    if (warp == 17) tmem_alloc_2cta(base + SM_TMEM, 512);
+    for (int i = threadIdx.x; i < SIDE_FLOATS; i += NUM_THREADS16) side[i] = P.side[i];
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_units = (n_units > unit) ? (int)((n_units - unit + n_units_grid - 1) / n_units_grid) : 0;
+    int steps_per_tile = 0;
+    for (int ph = 0; ph < N_PHASES; ++ph) steps_per_tile += c_fwd_prog.kb[ph];
+
+    if (warp == 16) {
+        if (lane == 0) producer_loop_pair(base, B, P.w_chunks, c_fwd_prog, rank, my_units);
+    } else if (warp >= 17) {
+        if (lane == 0) {
+            if (rank == 0) issuer_loop_pair(base, B, tmem_base, c_fwd_prog, warp - 17, my_units, P.trace, P.dbg);
+            else if (warp == 17) forwarder_loop_pair(B, my_units * steps_per_tile * 2);
+        }
+    } else {
+        const int s = warp >> 3, q4 = warp & 3;
+        if (((warp >> 2) & 1) == 0)
+            worker16<SAVE, 0>(P, smem, base, B, tmem_base, side, s, q4, lane, rank, unit, n_units_grid, my_units);
+        else
+            worker16<SAVE, 1>(P, smem, base, B, tmem_base, side, s, q4, lane, rank, unit, n_units_grid, my_units);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 17) tmem_dealloc_2cta(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // self-test GEMM (single CTA): validates descriptor / swizzle / TMEM conventions on hardware.
 // mode 0: A (128,K) , B (N,K)  row-major fp32 -> C = A * B^T      (K-major operands)
 // mode 1: A (K,128) , B (K,N)  row-major fp32 -> C = A^T * B      (MN-major operands)
@@ -693,6 +954,84 @@ selftest_gemm_2cta_kernel(const float* __restrict__ A, const float* __restrict__
     if (warp == 0) tmem_dealloc_2cta(tmem_base, 256);
 }
 
+// self-test of MMAs whose A operand lives in tensor memory: C (M, N) = A (M, K) x B (N, K)^T with A written to TMEM
+// by tcgen05.st as packed bf16 pairs and B K-major in shared memory.  PAIR: M = 256 over a CTA pair (cta_group::2,
+// each CTA holds its 128 rows of A in its own TMEM and N/2 rows of B), else M = 128 on one CTA.
+template <bool PAIR>
+__global__ void __launch_bounds__(128, 1)
+selftest_gemm_ts_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+    const int NB = PAIR ? N / 2 : N;                        // B rows held by this CTA
+    const uint32_t b_bytes = NB * K * 2;
+    uint8_t* b_img = smem;
+    const uint32_t bar = base + b_bytes;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + b_bytes + 16);
+    for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
+        int r = i / K, k = i - r * K;
+        uint32_t off = (k >> 6) * (NB * 128) + sw128_offset(r, k & 63);
+        *reinterpret_cast<__nv_bfloat16*>(b_img + off) = __float2bfloat16(B[(size_t)(rank * NB + r) * K + k]);
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        if (PAIR) tmem_alloc_2cta(base + b_bytes + 16, 512); else tmem_alloc(base + b_bytes + 16, 512);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_lane = tmem_base + (uint32_t(32 * warp) << 16);
+    constexpr uint32_t A_COL = 256;
+    {
+        const float* arow = A + (size_t)(rank * 128 + threadIdx.x) * K;
+        for (int g = 0; g < K / 32; ++g) {
+            uint32_t v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = pack_bf16x2(arow[g * 32 + 2 * q], arow[g * 32 + 2 * q + 1]);
+            tmem_st16(t_lane + A_COL + 16 * g, v);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync();
+    tc_fence_after();
+    if (rank == 0 && threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, N, 0, 0);
+        for (int k16 = 0; k16 < K / 16; ++k16) {
+            int kb = k16 >> 2, kk = k16 & 3;
+            uint64_t bd = make_sdesc_sw128(base + kb * (NB * 128) + kk * 32, 16, 1024);
+            if (PAIR) mma_bf16_ts_2cta(tmem_base, tmem_base + A_COL + k16 * 8, bd, idesc, k16 > 0 ? 1u : 0u);
+            else mma_bf16_ts(tmem_base, tmem_base + A_COL + k16 * 8, bd, idesc, k16 > 0 ? 1u : 0u);
+        }
+        if (PAIR) mma_commit_2cta(bar, 0x3); else mma_commit(bar);
+    }
+    mbar_wait(bar, 0, 9);
+    tc_fence_after();
+    const int row = rank * 128 + threadIdx.x;
+    for (int cg = 0; cg < N / 32; ++cg) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + cg * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) C[(int64_t)row * N + cg * 32 + q] = __uint_as_float(v[q]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (PAIR) cluster_sync();
+    if (warp == 0) {
+        if (PAIR) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // MMA issue-rate probe: `reps` back-to-back passes of K=64 (4 MMAs) over fixed smem operands, N columns.
 // Reports elapsed SM cycles from first issue to commit completion.  mode 0: K-major, 1: MN-major.
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int reps, int mode, long long* out) {
@@ -763,6 +1102,8 @@ int tc_alloc(nerf_ctx* ctx) {
     NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     return NERF_OK;
 }
 
@@ -805,23 +1146,26 @@ int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, cons
     P.act_save = save_acts ? reinterpret_cast<uint8_t*>(ctx->act_save[net]) : nullptr;
     P.mask_save = save_acts ? ctx->mask_save[net] : nullptr;
     P.trace = g_trace_buf;
-    P.dbg = g_pair_mode >> 1;
+    P.dbg = g_pair_mode >> 3;
     if (save_acts && !ctx->act_save[net]) return fail(NERF_ERR_STATE, "tc_forward_rays: ctx was not created with training=1");
     timing_begin(0, st);
-    if (g_pair_mode & 1) {
+    if (g_pair_mode & 5) {
         // CTA pairs: clusters of 2 over 512-row quads
         const int64_t n_quads = (P.n_pairs + 1) / 2;
         const int clusters = (int)(n_quads < num_sms() / 2 ? n_quads : num_sms() / 2);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * clusters);
-        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.blockDim = dim3((g_pair_mode & 4) ? NUM_THREADS16 : NUM_THREADS);
         cfg.dynamicSmemBytes = SMEM_BYTES;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (save_acts) NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc_kernel<true, true>, P));
+        if (g_pair_mode & 4) {
+            if (save_acts) NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc16_kernel<true>, P));
+            else NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc16_kernel<false>, P));
+        } else if (save_acts) NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc_kernel<true, true>, P));
         else NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc_kernel<false, true>, P));
     } else {
         int grid = (int)(P.n_pairs < num_sms() ? P.n_pairs : num_sms());
@@ -875,3 +1219,25 @@ extern "C" int nerf_selftest_gemm_2cta(const float* a, const float* b, float* c,
 
 // selects the CTA-pair (cta_group::2) variant of the fused forward kernel (0 = single-CTA variant)
 extern "C" int nerf_debug_pair_mode(int on) { nerf::g_pair_mode = on; return NERF_OK; }
+
+// self-test of TMEM-resident A operands ("TS" MMAs): pair = 0 -> C (128, n), pair = 1 -> C (256, n) over a CTA pair
+extern "C" int nerf_selftest_gemm_ts(const float* a, const float* b, float* c, int n, int k, int pair, void* stream) {
+    NERF_CHECK_ARG(a && b && c && (n == 128 || n == 256) && k >= 64 && k <= 256 && (k % 64) == 0, "bad arguments");
+    const int nb = pair ? n / 2 : n;
+    size_t smem = (size_t)nb * k * 2 + 64 + 1024;
+    if (pair) {
+        NERF_CUDA(cudaFuncSetAttribute(selftest_gemm_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        NERF_CUDA(cudaLaunchKernelEx(&cfg, selftest_gemm_ts_kernel<true>, a, b, c, n, k));
+    } else {
+        NERF_CUDA(cudaFuncSetAttribute(selftest_gemm_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        selftest_gemm_ts_kernel<false><<<1, 128, smem, (cudaStream_t)stream>>>(a, b, c, n, k);
+    }
+    NERF_LAUNCHED();
+    return NERF_OK;
+}

@@ -322,13 +322,17 @@ __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& 
             mbar_wait_cluster(bar_lo, actr_par, 3);
             mbar_wait_cluster(bar_hi, actr_par, 5);
             trace_ev(trace, s, tile, ph, 1);
+            uint32_t w_full = 0, w_pfull = 0;     // diagnostics: cycles spent waiting for weight chunks
             for (int kb = 0; kb < kbs; ++kb) {
                 const uint32_t g = g_base + s * kbs + kb;
                 const uint32_t lap = g / STAGES;
                 const uint32_t slot = g - lap * STAGES;
                 const uint32_t ring_par = lap & 1;
+                const long long tw0 = trace ? clock64() : 0;
                 mbar_wait(B.full + 8 * slot, ring_par, 4);
+                const long long tw1 = trace ? clock64() : 0;
                 mbar_wait_cluster(B.pfull + 8 * slot, ring_par, 8);
+                if (trace) { w_full += (uint32_t)(tw1 - tw0); w_pfull += (uint32_t)(clock64() - tw1); }
                 tc_fence_after();
                 const uint32_t a_lo = (a_tile + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
                 const uint32_t b_lo = (ring0 + slot * (CHUNK_BYTES >> 4)) | lbo_bits;
@@ -349,6 +353,8 @@ __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& 
             actr_par ^= 1;
             g_base += 2 * kbs;
             trace_ev(trace, s, tile, ph, 2);
+            if (trace && blockIdx.x == 0 && tile < 3)
+                trace[((s * 3 + tile) * 16 + ph) * 4 + 3] = (long long)w_full | ((long long)w_pfull << 32);
         }
     }
 }

@@ -18,7 +18,7 @@ tr.mlp_forward_rays("coarse", o, d, t)
 torch.cuda.synchronize()
 L.nerf_debug_trace(None)
 a = buf.cpu().numpy().reshape(4, 3, 16, 4)
-t0 = a[a > 0].min()
+t0 = a[..., :3][a[..., :3] > 0].min()
 names = ["issA", "issB", "wrkA", "wrkB"]
 for tile in range(2):
     print(f"tile {tile}: per phase [wait_start, ready, done] relative cycles")
@@ -27,4 +27,5 @@ for tile in range(2):
         for who in range(4):
             e = a[who, tile, ph]
             row.append(f"{names[who]}: " + " ".join(f"{(x - t0) if x > 0 else -1:7d}" for x in e[:3]))
+            if who < 2 and e[3] > 0: row[-1] += f" (wait full {int(e[3]) & 0xffffffff} pfull {int(e[3]) >> 32})"
         print(f"  ph{ph:2d} | " + " | ".join(row))
