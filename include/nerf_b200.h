@@ -158,9 +158,14 @@ int nerf_debug_flags(int flags);
 int nerf_debug_trace(long long* dev_buf);
 /* Self-test of the CTA-pair (cta_group::2) path: C (256,n) = A (256,k) x B (n,k)^T. */
 int nerf_selftest_gemm_2cta(const float* a, const float* b, float* c, int n, int k, void* stream);
-/* C = A * B^T with the A operand resident in tensor memory (tcgen05.st + TMEM-A MMAs); pair = 1: M = 256 over a CTA pair */
-int nerf_selftest_gemm_ts(const float* a, const float* b, float* c, int n, int k, int pair, void* stream);
-/* Selects the CTA-pair (cta_group::2, M = 256 MMAs over an SM pair) variant of the fused forward kernel. */
+/* C = A * B^T with the A operand resident in tensor memory (tcgen05.st + TMEM-A MMAs); pair = 1: M = 256 over a CTA pair.
+   reps > 1 repeats the MMA sequence (issue-rate probe; C is then reps x the product), probe = 2 adds a tcgen05.commit
+   per four MMAs, cycles_dev (optional) receives the SM cycles from first issue to completion */
+int nerf_selftest_gemm_ts(const float* a, const float* b, float* c, int n, int k, int pair, int reps, int probe,
+                          long long* cycles_dev, void* stream);
+/* Selects an experimental variant of the fused forward kernel (same results within bf16 rounding; slower than the default,
+   kept for the measurements in DESIGN.md): 0 = default single-CTA kernel, 1 = CTA pair (cta_group::2, M = 256 MMAs over an
+   SM pair), 4 = CTA pair with the activations resident in tensor memory (TMEM-A "TS" MMAs). */
 int nerf_debug_pair_mode(int on);
 /* MMA issue-rate probe (cycles for `reps` x 4 back-to-back 128 x n x 16 MMAs). */
 int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycles_dev, void* stream);

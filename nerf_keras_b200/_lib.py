@@ -63,7 +63,7 @@ SIGNATURES = {
     "nerf_debug_pair_mode": (_I, [_I]),
     "nerf_debug_trace": (_I, [_P]),
     "nerf_selftest_gemm_2cta": (_I, [_P, _P, _P, _I, _I, _P]),
-    "nerf_selftest_gemm_ts": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "nerf_selftest_gemm_ts": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nerf_selftest_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     # internal building blocks exported for unit tests (not part of the public header)
     "nerf_volume_render_bwd": (_I, [_P, _P, _P, _P, _L, _I, _P, _P, _P]),

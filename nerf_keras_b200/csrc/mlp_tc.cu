@@ -545,95 +545,139 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA-pair forward kernel with 16 worker warps ("tc16").
-// Same program, weights, hand-offs and MMA issue as nerf_mlp_fwd_tc_kernel<SAVE, true> (cta_group::2, M = 256
-// MMAs over an SM pair, each CTA staging half of the weight rows), but every 128-row sub-tile is served by EIGHT
-// epilogue warps instead of four: warp w owns TMEM lane quarter (w & 3) and column half ((w >> 2) & 1), so a
-// row's 256 accumulator columns are converted by two threads in parallel.  The epilogue of one sub-tile then
-// fits under the other sub-tile's MMA phase (2048 cycles), which is what the pair kernel needs to keep the
-// tensor pipe busy.  Sigma / rgb head partial sums of the two column halves are combined through shared memory.
+// "TS" forward kernel: CTA pairs (cta_group::2) with the activations resident in TENSOR MEMORY.
+//
+// The fused kernels above are bound by shared-memory bandwidth: every MMA re-reads its A tile from shared memory
+// and every epilogue writes the next A tile back there.  Here the epilogue writes the next layer's input as packed
+// bf16 pairs straight into TMEM (tcgen05.st) and the MMAs take their A operand from TMEM, so shared memory only
+// carries the weight stream.  One 128-row tile per CTA, 256 rows per CTA pair (M = 256 MMAs, each CTA staging 64 of
+// the 128 weight rows of a chunk):
+//   TMEM columns   [0,256)  fp32 accumulator, two 128-column N-halves
+//                  [256,384) / [384,512)  activation buffers (128 columns = 256 bf16 K-elements), ping-pong
+//   shared memory  positional encoding (the only SS operand: layer 0 and the skip rows of layer 5), a 16-stage ring
+//                  of 8 KB weight sub-chunks, the bias/head side table
+// Sixteen epilogue warps: warp w owns TMEM lane quarter (w & 3) and 32-column group (w >> 2) of each N-half, so an
+// N-half is converted by all 512 threads at once.  Layer l+1's MMAs over K-blocks 0,1 start as soon as N-half 0 of
+// layer l has been converted (aready[0]); K-blocks 2,3 follow aready[1]; the conversion of N-half 0 of layer l+1
+// overlaps the MMAs of its N-half 1.
 // ------------------------------------------------------------------------------------------------
-constexpr int NUM_THREADS16 = 608;   // 16 worker warps + producer warp + 2 issuer / forwarder warps
+namespace ts {
+constexpr int WORKER_WARPS = 16;
+constexpr int THREADS = (WORKER_WARPS + 2) * 32;     // + producer warp + issuer (leader) / forwarder (peer) warp
+constexpr int STAGES_TS = 16;
+constexpr int SUB_BYTES = CHUNK_BYTES / 2;           // this CTA's 64 weight rows of a 16 KB chunk
+constexpr int SM_ENC = 0;                            // 2 x 16 KB: bf16(enc) K-block, xyz residual K-block
+constexpr int SM_RING_TS = 2 * 16384;
+constexpr int SM_SIDE_TS = SM_RING_TS + STAGES_TS * SUB_BYTES;
+constexpr int SM_DIRB_TS = SM_SIDE_TS + SIDE_FLOATS * 4;           // 4 rays x 128 floats
+constexpr int SM_PART = SM_DIRB_TS + 4 * 512;                      // float4 [128 rows][4 column groups]
+constexpr int SM_FULL_TS = SM_PART + 128 * 4 * 16;
+constexpr int SM_EMPTY_TS = SM_FULL_TS + 8 * STAGES_TS;
+constexpr int SM_PFULL_TS = SM_EMPTY_TS + 8 * STAGES_TS;
+constexpr int SM_ACCF_TS = SM_PFULL_TS + 8 * STAGES_TS;            // 2: accumulator N-half complete
+constexpr int SM_AREADY_TS = SM_ACCF_TS + 16;                      // 2: activation K-half written (leader's copy counts)
+constexpr int SM_TMEM_TS = SM_AREADY_TS + 16;
+constexpr int SMEM_TS = SM_TMEM_TS + 16 + 1024;
+static_assert(SM_DIRB_TS % 16 == 0 && SM_FULL_TS % 8 == 0, "alignment");
+static_assert(SMEM_TS <= 232448, "exceeds the 227 KB shared memory limit");
+constexpr uint32_t T_ACC = 0, T_ABUF = 256;
+}  // namespace ts
 
-template <bool RELU, bool SIGMA, bool SAVE, int HALF>
-__device__ __forceinline__ void trunk_half(uint32_t t_lane, const float* bias, const float* wsig, uint64_t& sig2,
-                                           uint32_t (&mask)[4], const RowStore& rs) {
-    uint32_t v[32];
-    tmem_ld32(t_lane + HALF * 128, v); tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, HALF * 4 + 0, true>(v, bias, wsig, sig2, mask[0], rs, nullptr);
-    tmem_ld32(t_lane + HALF * 128 + 32, v); tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, HALF * 4 + 1, true>(v, bias, wsig, sig2, mask[1], rs, nullptr);
-    tmem_ld32(t_lane + HALF * 128 + 64, v); tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, HALF * 4 + 2, true>(v, bias, wsig, sig2, mask[2], rs, nullptr);
-    tmem_ld32(t_lane + HALF * 128 + 96, v); tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, HALF * 4 + 3, true>(v, bias, wsig, sig2, mask[3], rs, nullptr);
+// bias (+ReLU) + bf16 pack of one 32-column accumulator group; optional sigma head partial sum and ReLU mask
+template <bool RELU, bool SIGMA, bool SAVE>
+__device__ __forceinline__ void ts_group(const uint32_t (&v)[32], const float* bias, const float* wsig, uint64_t& sig2,
+                                         uint32_t& mk, uint32_t (&pk)[16]) {
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias);
+    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(wsig);
+    mk = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const ulonglong2 bb = b2[q];
+        float x0, x1, x2, x3;
+        f2_unpack(f2_add(f2_pack(v[4 * q], v[4 * q + 1]), bb.x), x0, x1);
+        f2_unpack(f2_add(f2_pack(v[4 * q + 2], v[4 * q + 3]), bb.y), x2, x3);
+        if (SIGMA) {
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+            const ulonglong2 ws = s2[q];
+            sig2 = f2_fma(f2_pack(__float_as_uint(x0), __float_as_uint(x1)), ws.x, sig2);
+            sig2 = f2_fma(f2_pack(__float_as_uint(x2), __float_as_uint(x3)), ws.y, sig2);
+        }
+        if (SAVE && RELU) {
+            mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
+            mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
+            mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
+            mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
+        }
+        pk[2 * q] = cvt_bf16x2<RELU>(x0, x1);
+        pk[2 * q + 1] = cvt_bf16x2<RELU>(x2, x3);
+    }
 }
 
-// half of the positional encoding of one point, packed bf16x2: HALF 0 = channels 0..31 (x, y, z and octaves 0..4
-// except the last cosine), HALF 1 = channels 32..63 (cos(16 z), octaves 5..9, zero pad).  sincosf at the first
-// octave of each half, exact angle doubling for the next four.
-template <int HALF>
-__device__ __forceinline__ void encode_half(const float (&p)[3], uint32_t (&E)[16]) {
-    float e[32];
-    if (HALF == 0) {
-        e[0] = p[0]; e[1] = p[1]; e[2] = p[2];
-    } else {
-        e[0] = cosf(16.f * p[2]);
-        e[31] = 0.f;
-    }
+// 16 channels [16 CQ, 16 CQ + 16) of the positional encoding of one point, packed bf16x2.  sincosf at the first
+// octave the quarter needs, exact angle doubling (at most three times) for the following ones.
+template <int CQ>
+__device__ __forceinline__ void encode_quarter(const float (&p)[3], uint32_t (&E)[8]) {
+    constexpr int LO = 16 * CQ;
+    constexpr int I0 = (CQ == 0) ? 0 : (CQ == 1) ? 2 : (CQ == 2) ? 4 : 7;
+    constexpr int I1 = (CQ == 0) ? 2 : (CQ == 1) ? 4 : (CQ == 2) ? 7 : 9;
+    float e[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) e[j] = 0.f;
+    if (CQ == 0) { e[0] = p[0]; e[1] = p[1]; e[2] = p[2]; }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float sv, cv;
 #pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            const int i = HALF * 5 + j;
-            if (j == 0) sincosf((float)(1 << i) * p[c], &sv, &cv);
+        for (int i = I0; i <= I1; ++i) {
+            if (i == I0) sincosf((float)(1 << i) * p[c], &sv, &cv);
             else {
                 const float s2 = 2.f * sv * cv;
                 const float c2 = fmaf(-2.f * sv, sv, 1.f);
                 sv = s2; cv = c2;
             }
-            const int is = 3 + 6 * i + c - HALF * 32, ic = is + 3;
-            if (is < 32) e[is] = sv;
-            if (ic < 32) e[ic] = cv;
+            const int is = 3 + 6 * i + c - LO, ic = is + 3;
+            if (is >= 0 && is < 16) e[is] = sv;
+            if (ic >= 0 && ic < 16) e[ic] = cv;
         }
     }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) E[q] = pack_bf16x2(e[2 * q], e[2 * q + 1]);
+    for (int q = 0; q < 8; ++q) E[q] = pack_bf16x2(e[2 * q], e[2 * q + 1]);
 }
 
-template <bool SAVE, int HALF>
-__device__ __forceinline__ void worker16(const FwdParams& P, uint8_t* smem, uint32_t base, const Barriers& B,
-                                         uint32_t tmem_base, const float* side, int s, int q4, int lane, int rank,
-                                         int unit, int n_units_grid, int my_units) {
-    const int row = 32 * q4 + lane;
-    const int sub_tid = HALF * TILE_M + row;                        // 0..255 inside the sub-tile's worker group
-    const uint32_t act_base = base + SM_ACT + s * 65536;
-    const uint32_t t_lane = tmem_base + (uint32_t(32 * q4) << 16) + s * 256;
-    const bool elected = (sub_tid == 0);
-    float* dbs = reinterpret_cast<float*>(smem + SM_DIRB) + s * (DIRB_ROWS * 128);
-    float4* part = reinterpret_cast<float4*>(smem + SM_ACT + s * 65536 + 49152) + row;   // head partial sums (K-block 3)
-    RowStore rs;
-    rs.init(act_base, row);
-    const uint32_t bar_l = B.actr + 16 * s + 8 * HALF;                // this column half's A-tile hand-off barrier
-    const uint32_t bar_mine = (rank != 0) ? map_to_cta(bar_l, 0) : bar_l;
-    const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;
-    uint32_t accf_par = 0;
-    uint32_t E[16];
-    uint32_t Elo[2] = {0u, 0u};
-    auto arrive = [&]() { if (rank != 0) mbar_arrive_cluster(bar_mine); else mbar_arrive(bar_mine); };
-    auto stage_enc = [&]() {
+// 32 bf16 (64 contiguous bytes after the swizzle) of one row of a saved [128 x 64] image block, straight to global
+__device__ __forceinline__ void save_row_half(uint8_t* block, int row, int chunk0, const uint32_t (&pk)[16]) {
+    uint8_t* rp = block + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) rs.store<0>(HALF * 4 + c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
-        if (HALF == 0) {
-            rs.store<1>(0, Elo[0], Elo[1], 0u, 0u);
-            rs.store<1>(1, 0u, 0u, 0u, 0u);
-        }
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(rp + (((chunk0 + c) ^ (row & 7)) << 4)) =
+            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
+
+template <bool SAVE, int CQ>
+__device__ __forceinline__ void ts_worker(const FwdParams& P, uint8_t* smem, uint32_t base, uint32_t tmem_base,
+                                          const float* side, int q4, int lane, int rank, int unit, int n_units_grid,
+                                          int my_units) {
+    using namespace ts;
+    const int row = 32 * q4 + lane;
+    const int wtid = CQ * TILE_M + row;                               // 0..511 among the workers
+    const bool elected = (wtid == 0);
+    const uint32_t t_lane = tmem_base + (uint32_t(32 * q4) << 16);
+    float* dbs = reinterpret_cast<float*>(smem + SM_DIRB_TS);
+    float4* part = reinterpret_cast<float4*>(smem + SM_PART) + row * 4;
+    const uint32_t accf0 = base + SM_ACCF_TS, accf1 = accf0 + 8;
+    const uint32_t ar0 = rank ? map_to_cta(base + SM_AREADY_TS, 0) : base + SM_AREADY_TS;
+    const uint32_t ar1 = rank ? map_to_cta(base + SM_AREADY_TS + 8, 0) : base + SM_AREADY_TS + 8;
+    // the warp's TMEM / shared-memory writes are complete and fenced; one lane signals the leader's issuer
+    auto arrive = [&](uint32_t bar) {
+        __syncwarp();
+        if (lane == 0) { if (rank) mbar_arrive_cluster(bar); else mbar_arrive(bar); }
     };
+    const uint32_t enc_row = base + SM_ENC + (row >> 3) * 1024 + (row & 7) * 128;
+    uint32_t accf_par = 0;
 
     for (int it = 0; it < my_units; ++it) {
         const int64_t wu = unit + (int64_t)it * n_units_grid;
-        const int64_t tile = wu * 4 + s * 2 + rank;
+        const int64_t tile = wu * 2 + rank;
         const int64_t g_row = tile * TILE_M + row;
         const bool valid = g_row < P.M;
         const int64_t gr = valid ? g_row : (P.M - 1);
@@ -645,122 +689,147 @@ __device__ __forceinline__ void worker16(const FwdParams& P, uint8_t* smem, uint
         const int64_t ray0 = ((m_first < P.M) ? m_first : (P.M - 1)) / P.N;
         const int64_t m_last = (m_first + TILE_M - 1 < P.M) ? (m_first + TILE_M - 1) : (P.M - 1);
         const int n_rays = (int)(m_last / P.N - ray0) + 1;
-        const bool staged = n_rays <= DIRB_ROWS;
-        float4 db_pref = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (staged && sub_tid < n_rays * 32)
-            db_pref = __ldg(reinterpret_cast<const float4*>(P.dirbias + ray0 * 128) + sub_tid);
+        const bool staged = n_rays <= 4;
+        if (staged && wtid < n_rays * 32)
+            reinterpret_cast<float4*>(dbs)[wtid] = __ldg(reinterpret_cast<const float4*>(P.dirbias + ray0 * 128) + wtid);
 
+        // ---- positional encoding: this thread's 16 channels -> two 16-byte chunks of the SS operand block ----
         {
             const float tv = P.t[gr];
             float p[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) p[c] = __fadd_rn(P.o[ray * 3 + c], __fmul_rn(P.d[ray * 3 + c], tv));
-            encode_half<HALF>(p, E);
-            if (HALF == 0) {
+            uint32_t E[8];
+            encode_quarter<CQ>(p, E);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(enc_row + (uint32_t((2 * CQ) ^ (row & 7)) << 4)),
+                         "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(enc_row + (uint32_t((2 * CQ + 1) ^ (row & 7)) << 4)),
+                         "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]) : "memory");
+            if (SAVE) {
+                uint8_t* rp = save_tile + SAVE_ENC + (row >> 3) * 1024 + (row & 7) * 128;
+                *reinterpret_cast<uint4*>(rp + (((2 * CQ) ^ (row & 7)) << 4)) = make_uint4(E[0], E[1], E[2], E[3]);
+                *reinterpret_cast<uint4*>(rp + (((2 * CQ + 1) ^ (row & 7)) << 4)) = make_uint4(E[4], E[5], E[6], E[7]);
+            }
+            if (CQ == 0) {
                 float lo[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) lo[c] = p[c] - __bfloat162float(__float2bfloat16_rn(p[c]));
-                Elo[0] = pack_bf16x2(lo[0], lo[1]);
-                Elo[1] = pack_bf16x2(lo[2], 0.f);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(enc_row + 16384 + (uint32_t(0 ^ (row & 7)) << 4)),
+                             "r"(pack_bf16x2(lo[0], lo[1])), "r"(pack_bf16x2(lo[2], 0.f)), "r"(0u), "r"(0u) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(enc_row + 16384 + (uint32_t(1 ^ (row & 7)) << 4)),
+                             "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
             }
         }
-        if (SAVE && elected) bulk_wait_read0();
-        named_bar_sync(1 + s, 2 * TILE_M);
-        stage_enc();
-        if (staged && sub_tid < n_rays * 32) reinterpret_cast<float4*>(dbs)[sub_tid] = db_pref;
         tc_fence_before();
         fence_proxy_async_all();
-        if (SAVE) {
-            named_bar_sync(1 + s, 2 * TILE_M);
-            if (elected) { bulk_s2g(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
-        }
-        arrive();
+        arrive(ar0);
+        arrive(ar1);
 
         float sig = 0.f;
+        int e = 0;                                                    // epilogues done in this tile: writes buffer e & 1
         for (int ph = 0; ph < N_PHASES; ++ph) {
-            if (elected) trace_ev(P.trace, 2 + s, it, ph, 0);
-            mbar_wait(bar_h0, accf_par, 2);
-            mbar_wait(bar_h1, accf_par, 6);
-            accf_par ^= 1;
-            tc_fence_after();
-            if (elected) trace_ev(P.trace, 2 + s, it, ph, 1);
-            if (SAVE) {                                              // the previous image's bulk store has read the tile
-                if (elected) bulk_wait_read0();
-                named_bar_sync(1 + s, 2 * TILE_M);
-            }
-            if (ph == 5) {
-                stage_enc();
-                tc_fence_before();
-                fence_proxy_async_all();
-                arrive();
-                continue;
-            }
+            if (ph == 5) continue;                                    // layer 5 accumulates on through phase 6
             if (ph < 10) {
                 const int layer = (ph <= 4) ? ph : (ph == 6 ? 5 : (ph == 7 ? 6 : (ph == 8 ? 7 : 8)));
-                const float* bias = side + (layer < 8 ? SIDE_BIAS + layer * H : SIDE_BFEAT);
+                const float* bias = side + (layer < 8 ? SIDE_BIAS + layer * H : SIDE_BFEAT) + CQ * 32;
+                const float* wsig = side + SIDE_WSIG + CQ * 32;
                 const bool relu = layer < 8;
-                const float* wsig = side + SIDE_WSIG;
-                uint32_t mask[4];
                 uint64_t sig2 = 0ull;
-                if (ph == 8) trunk_half<true, true, SAVE, HALF>(t_lane, bias, wsig, sig2, mask, rs);
-                else if (relu) trunk_half<true, false, SAVE, HALF>(t_lane, bias, wsig, sig2, mask, rs);
-                else trunk_half<false, false, SAVE, HALF>(t_lane, bias, wsig, sig2, mask, rs);
+                const uint32_t a_dst = t_lane + T_ABUF + (e & 1) * 128 + CQ * 16;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (elected) trace_ev(P.trace, 2, it, ph, h ? 3 : 0);
+                    mbar_wait(h ? accf1 : accf0, accf_par, 2 + 4 * h);
+                    tc_fence_after();
+                    if (elected && h == 0) trace_ev(P.trace, 2, it, ph, 1);
+                    uint32_t v[32], pk[16], mk;
+                    tmem_ld32(t_lane + T_ACC + h * 128 + CQ * 32, v);
+                    tmem_ld_wait();
+                    if (ph == 8) ts_group<true, true, SAVE>(v, bias + h * 128, wsig + h * 128, sig2, mk, pk);
+                    else if (relu) ts_group<true, false, SAVE>(v, bias + h * 128, wsig, sig2, mk, pk);
+                    else ts_group<false, false, SAVE>(v, bias + h * 128, wsig, sig2, mk, pk);
+                    tmem_st16(a_dst + h * 64, pk);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    arrive(h ? ar1 : ar0);
+                    if (SAVE) {
+                        uint8_t* img = save_tile + ((layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT);
+                        save_row_half(img + (h * 2 + (CQ >> 1)) * 16384, row, (CQ & 1) * 4, pk);
+                        if (relu) mask_tile[((size_t)layer * 128 + row) * 8 + h * 4 + CQ] = mk;
+                    }
+                }
+                if (elected) trace_ev(P.trace, 2, it, ph, 2);
+                accf_par ^= 1;
+                ++e;
                 if (ph == 8) {
                     float a, b;
                     f2_unpack(sig2, a, b);
                     sig = a + b;
                 }
+            } else {
+                // ddir epilogue: + (bias + per-ray direction term), ReLU, rgb head partial sums over this thread's 32 columns
+                mbar_wait(accf0, accf_par, 2);
+                mbar_wait(accf1, accf_par, 6);
+                accf_par ^= 1;
+                tc_fence_after();
+                const float* db = (staged ? (dbs + (int)(ray - ray0) * 128) : (P.dirbias + ray * 128)) + CQ * 32;
+                const ulonglong2* d2 = reinterpret_cast<const ulonglong2*>(db);
+                const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + CQ * 32);
+                const ulonglong2* wg = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 128 + CQ * 32);
+                const ulonglong2* wb = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 256 + CQ * 32);
+                uint64_t r2 = 0ull, g2 = 0ull, b2 = 0ull;
+                uint32_t v[32], pk[16], mk = 0;
+                tmem_ld32(t_lane + T_ACC + CQ * 32, v);
+                tmem_ld_wait();
                 tc_fence_before();
-                fence_proxy_async_all();
-                if (SAVE) {
-                    if (relu)
-                        *reinterpret_cast<uint4*>(mask_tile + ((size_t)layer * 128 + row) * 8 + HALF * 4) =
-                            make_uint4(mask[0], mask[1], mask[2], mask[3]);
-                    named_bar_sync(1 + s, 2 * TILE_M);
-                    if (elected) {
-                        int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
-                        bulk_s2g(save_tile + off, act_base, 65536);
-                        bulk_commit();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const ulonglong2 dd = d2[q];
+                    float x0, x1, x2, x3;
+                    f2_unpack(f2_add(f2_pack(v[4 * q], v[4 * q + 1]), dd.x), x0, x1);
+                    f2_unpack(f2_add(f2_pack(v[4 * q + 2], v[4 * q + 3]), dd.y), x2, x3);
+                    x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+                    const uint64_t x01 = f2_pack(__float_as_uint(x0), __float_as_uint(x1));
+                    const uint64_t x23 = f2_pack(__float_as_uint(x2), __float_as_uint(x3));
+                    const ulonglong2 a = wr[q], b = wg[q], c = wb[q];
+                    r2 = f2_fma(x01, a.x, r2); r2 = f2_fma(x23, a.y, r2);
+                    g2 = f2_fma(x01, b.x, g2); g2 = f2_fma(x23, b.y, g2);
+                    b2 = f2_fma(x01, c.x, b2); b2 = f2_fma(x23, c.y, b2);
+                    if (SAVE) {
+                        mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
+                        mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
+                        mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
+                        mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
+                        pk[2 * q] = cvt_bf16x2<false>(x0, x1);
+                        pk[2 * q + 1] = cvt_bf16x2<false>(x2, x3);
                     }
                 }
-                if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);
-                arrive();
-            } else {
-                uint64_t r2 = 0ull, g2 = 0ull, b2 = 0ull;
-                uint32_t mask[2];
-                const float* db = staged ? (dbs + (int)(ray - ray0) * 128) : (P.dirbias + ray * 128);
-                uint32_t v[32];
-                tmem_ld32(t_lane + HALF * 64, v); tmem_ld_wait();
-                ddir_group<SAVE, 2 * HALF>(v, db, side, r2, g2, b2, mask[0], rs);
-                tmem_ld32(t_lane + HALF * 64 + 32, v); tmem_ld_wait();
-                ddir_group<SAVE, 2 * HALF + 1>(v, db, side, r2, g2, b2, mask[1], rs);
                 float ra, rb, ga, gb, ba, bb;
                 f2_unpack(r2, ra, rb); f2_unpack(g2, ga, gb); f2_unpack(b2, ba, bb);
-                if (HALF == 1) *part = make_float4(ra + rb, ga + gb, ba + bb, sig);
-                tc_fence_before();
+                part[CQ] = make_float4(ra + rb, ga + gb, ba + bb, sig);
                 if (SAVE) {
+                    save_row_half(save_tile + SAVE_HD + (CQ >> 1) * 16384, row, (CQ & 1) * 4, pk);
                     uint32_t* mp = mask_tile + ((size_t)8 * 128 + row) * 8;
-                    *reinterpret_cast<uint2*>(mp + HALF * 2) = make_uint2(mask[0], mask[1]);
-                    if (HALF == 1) *reinterpret_cast<uint4*>(mp + 4) = make_uint4(0u, 0u, 0u, 0u);
-                    fence_proxy_async_all();
+                    mp[CQ] = mk;
+                    mp[4 + CQ] = 0u;
                 }
-                named_bar_sync(1 + s, 2 * TILE_M);
-                if (HALF == 0) {
-                    const float4 o = *part;
-                    if (valid)
-                        P.preds[g_row] = make_float4((ra + rb) + o.x + side[SIDE_BRGB], (ga + gb) + o.y + side[SIDE_BRGB + 1],
-                                                     (ba + bb) + o.z + side[SIDE_BRGB + 2], (sig + o.w) + side[SIDE_BSIG]);
+                named_bar_sync(1, WORKER_WARPS * 32);
+                if (CQ == 0 && valid) {
+                    const float4 p0 = part[0], p1 = part[1], p2 = part[2], p3 = part[3];
+                    P.preds[g_row] = make_float4((p0.x + p1.x) + (p2.x + p3.x) + side[SIDE_BRGB],
+                                                 (p0.y + p1.y) + (p2.y + p3.y) + side[SIDE_BRGB + 1],
+                                                 (p0.z + p1.z) + (p2.z + p3.z) + side[SIDE_BRGB + 2],
+                                                 (p0.w + p1.w) + (p2.w + p3.w) + side[SIDE_BSIG]);
                 }
-                if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);
-                if (SAVE && elected) { bulk_s2g(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
+                if (elected) trace_ev(P.trace, 2, it, ph, 2);
             }
         }
     }
-    if (SAVE && elected) bulk_wait_all0();
 }
 
 template <bool SAVE>
-__global__ void __launch_bounds__(NUM_THREADS16, 1) nerf_mlp_fwd_tc16_kernel(const FwdParams P) {
+__global__ void __launch_bounds__(ts::THREADS, 1) nerf_mlp_fwd_ts_kernel(const FwdParams P) {
+    using namespace ts;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -769,40 +838,144 @@ __global__ void __launch_bounds__(NUM_THREADS16, 1) nerf_mlp_fwd_tc16_kernel(con
     const int rank = (int)cluster_ctarank();
     const int unit = (int)(blockIdx.x >> 1);
     const int n_units_grid = (int)(gridDim.x >> 1);
-    const int64_t n_units = (P.n_pairs + 1) / 2;                      // 512-row quads, one per cluster
-    Barriers B;
-    init_barriers(base, B, true);
-    float* side = reinterpret_cast<float*>(smem + SM_SIDE);
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
-    if (warp == 17) tmem_alloc_2cta(base + SM_TMEM, 512);
-    for (int i = threadIdx.x; i < SIDE_FLOATS; i += NUM_THREADS16) side[i] = P.side[i];
+    const int64_t n_units = P.n_pairs;                                // 256-row units, one per CTA pair
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES_TS; ++i) {
+            mbar_init(base + SM_FULL_TS + 8 * i, 1);
+            mbar_init(base + SM_EMPTY_TS + 8 * i, 1);
+            mbar_init(base + SM_PFULL_TS + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(base + SM_ACCF_TS + 8 * i, 1);
+            mbar_init(base + SM_AREADY_TS + 8 * i, 2 * WORKER_WARPS);   // one arrival per worker warp of both CTAs
+        }
+        fence_barrier_init();
+    }
+    float* side = reinterpret_cast<float*>(smem + SM_SIDE_TS);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_TS);
+    if (warp == WORKER_WARPS + 1) tmem_alloc_2cta(base + SM_TMEM_TS, 512);
+    for (int i = threadIdx.x; i < SIDE_FLOATS; i += THREADS) side[i] = P.side[i];
     tc_fence_before();
     __syncthreads();
     cluster_sync();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int my_units = (n_units > unit) ? (int)((n_units - unit + n_units_grid - 1) / n_units_grid) : 0;
-    int steps_per_tile = 0;
-    for (int ph = 0; ph < N_PHASES; ++ph) steps_per_tile += c_fwd_prog.kb[ph];
 
-    if (warp == 16) {
-        if (lane == 0) producer_loop_pair(base, B, P.w_chunks, c_fwd_prog, rank, my_units);
-    } else if (warp >= 17) {
+    if (warp == WORKER_WARPS) {
+        // ---- producer: this CTA's half (64 weight rows) of every chunk, in stream order ----
         if (lane == 0) {
-            if (rank == 0) issuer_loop_pair(base, B, tmem_base, c_fwd_prog, warp - 17, my_units, P.trace, P.dbg);
-            else if (warp == 17) forwarder_loop_pair(B, my_units * steps_per_tile * 2);
+            int slot = 0;
+            uint32_t par = 1;
+            const uint8_t* src0 = reinterpret_cast<const uint8_t*>(P.w_chunks) + rank * SUB_BYTES;
+            for (int it = 0; it < my_units; ++it)
+                for (int c = 0; c < N_CHUNKS; ++c) {
+                    mbar_wait(base + SM_EMPTY_TS + 8 * slot, par, 1);
+                    mbar_arrive_expect_tx(base + SM_FULL_TS + 8 * slot, SUB_BYTES);
+                    bulk_g2s(base + SM_RING_TS + slot * SUB_BYTES, src0 + (size_t)c * CHUNK_BYTES, SUB_BYTES,
+                             base + SM_FULL_TS + 8 * slot);
+                    if (++slot == STAGES_TS) { slot = 0; par ^= 1; }
+                }
+        }
+    } else if (warp == WORKER_WARPS + 1) {
+        if (lane == 0 && rank != 0) {
+            // ---- peer: forward "my ring slot is full" to the leader ----
+            int slot = 0;
+            uint32_t par = 0;
+            for (int g = 0; g < my_units * N_CHUNKS; ++g) {
+                mbar_wait(base + SM_FULL_TS + 8 * slot, par, 7);
+                mbar_arrive_cluster(map_to_cta(base + SM_PFULL_TS + 8 * slot, 0));
+                if (++slot == STAGES_TS) { slot = 0; par ^= 1; }
+            }
+        } else if (lane == 0) {
+            // ---- leader: the MMA issuer ----
+            const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
+            const uint32_t lbo_bits = (16u >> 4) << 16;
+            const uint32_t enc0 = ((base + SM_ENC) & 0x3FFFF) >> 4;
+            const uint32_t ring0 = ((base + SM_RING_TS) & 0x3FFFF) >> 4;
+            const uint32_t idesc = make_idesc_bf16(256, 128, 0, 0);
+            const uint32_t accf0 = base + SM_ACCF_TS, ar0 = base + SM_AREADY_TS;
+            int slot = 0;
+            uint32_t ring_par = 0, ar_par = 0;
+            for (int it = 0; it < my_units; ++it) {
+                int e = 0;                                            // epilogues so far: TS phases read buffer (e - 1) & 1
+                for (int ph = 0; ph < N_PHASES; ++ph) {
+                    const int n_ch = c_fwd_prog.chunks[ph], kbs = c_fwd_prog.kb[ph], flags = c_fwd_prog.flags[ph];
+                    const int halves = n_ch / kbs;
+                    const bool enc = (flags & PH_ENC) != 0, acc_in = (flags & PH_ACC) != 0;
+                    const bool consumes = !(enc && acc_in);           // phase 6 only adds the skip rows: nothing new to wait for
+                    const bool has_epi = (ph != 5);
+                    const uint32_t a_buf = tmem_base + T_ABUF + ((e - 1) & 1) * 128;
+                    trace_ev(P.trace, 0, it, ph, 0);
+                    long long w_full = 0, w_pfull = 0, w_issue = 0;   // diagnostics
+                    for (int h = 0; h < halves; ++h) {
+                        const uint32_t d_tmem = tmem_base + T_ACC + h * 128;
+                        for (int kb = 0; kb < kbs; ++kb) {
+                            if (consumes && h == 0) {
+                                if (kb == 0) {
+                                    mbar_wait_cluster(ar0, ar_par, 3);
+                                    if (enc) mbar_wait_cluster(ar0 + 8, ar_par, 5);
+                                    trace_ev(P.trace, 0, it, ph, 1);
+                                } else if (!enc && kb == kbs / 2) {
+                                    mbar_wait_cluster(ar0 + 8, ar_par, 5);
+                                    trace_ev(P.trace, 0, it, ph, 3);
+                                }
+                            }
+                            const long long tw0 = P.trace ? clock64() : 0;
+                            mbar_wait(base + SM_FULL_TS + 8 * slot, ring_par, 4);
+                            const long long tw1 = P.trace ? clock64() : 0;
+                            mbar_wait_cluster(base + SM_PFULL_TS + 8 * slot, ring_par, 8);
+                            const long long tw2 = P.trace ? clock64() : 0;
+                            tc_fence_after();
+                            const uint32_t b_lo = (ring0 + slot * (SUB_BYTES >> 4)) | lbo_bits;
+                            const bool acc0 = (kb > 0) || acc_in;
+                            const int n_mma = (enc && kb == 1) ? 1 : 4;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < n_mma) {
+                                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                                    const uint32_t accum = (acc0 || k > 0) ? 1u : 0u;
+                                    if (enc) {
+                                        const uint32_t a_lo = (enc0 + kb * (16384 >> 4)) | lbo_bits;
+                                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+                                        mma_bf16_ss_2cta(d_tmem, ad, bd, idesc, accum);
+                                    } else {
+                                        mma_bf16_ts_2cta(d_tmem, a_buf + kb * 32 + k * 8, bd, idesc, accum);
+                                    }
+                                }
+                            }
+                            mma_commit_2cta(base + SM_EMPTY_TS + 8 * slot, 0x3);
+                            if (P.trace) { w_full += tw1 - tw0; w_pfull += tw2 - tw1; w_issue += clock64() - tw2; }
+                            if (++slot == STAGES_TS) { slot = 0; ring_par ^= 1; }
+                        }
+                        if (has_epi) {
+                            mma_commit_2cta(accf0 + 8 * h, 0x3);
+                            if (halves == 1) mma_commit_2cta(accf0 + 8, 0x3);
+                        }
+                    }
+                    if (consumes) ar_par ^= 1;
+                    if (has_epi) ++e;
+                    trace_ev(P.trace, 0, it, ph, 2);
+                    if (P.trace && blockIdx.x == 0 && it < 3) {
+                        long long* tp = P.trace + ((1 * 3 + it) * 16 + ph) * 4;
+                        tp[0] = w_full; tp[1] = w_pfull; tp[2] = w_issue;
+                    }
+                }
+            }
         }
     } else {
-        const int s = warp >> 3, q4 = warp & 3;
-        if (((warp >> 2) & 1) == 0)
-            worker16<SAVE, 0>(P, smem, base, B, tmem_base, side, s, q4, lane, rank, unit, n_units_grid, my_units);
-        else
-            worker16<SAVE, 1>(P, smem, base, B, tmem_base, side, s, q4, lane, rank, unit, n_units_grid, my_units);
+        const int q4 = warp & 3;
+        switch (warp >> 2) {
+            case 0: ts_worker<SAVE, 0>(P, smem, base, tmem_base, side, q4, lane, rank, unit, n_units_grid, my_units); break;
+            case 1: ts_worker<SAVE, 1>(P, smem, base, tmem_base, side, q4, lane, rank, unit, n_units_grid, my_units); break;
+            case 2: ts_worker<SAVE, 2>(P, smem, base, tmem_base, side, q4, lane, rank, unit, n_units_grid, my_units); break;
+            default: ts_worker<SAVE, 3>(P, smem, base, tmem_base, side, q4, lane, rank, unit, n_units_grid, my_units); break;
+        }
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync();
-    if (warp == 17) tmem_dealloc_2cta(tmem_base, 512);
+    cluster_sync();                       // the leader's MMAs read the peer's shared and tensor memory: leave together
+    if (warp == WORKER_WARPS + 1) tmem_dealloc_2cta(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -959,7 +1132,8 @@ selftest_gemm_2cta_kernel(const float* __restrict__ A, const float* __restrict__
 // each CTA holds its 128 rows of A in its own TMEM and N/2 rows of B), else M = 128 on one CTA.
 template <bool PAIR>
 __global__ void __launch_bounds__(128, 1)
-selftest_gemm_ts_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int N, int K) {
+selftest_gemm_ts_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int N, int K,
+                        int reps, int probe, long long* cycles) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -970,7 +1144,7 @@ selftest_gemm_ts_kernel(const float* __restrict__ A, const float* __restrict__ B
     const uint32_t b_bytes = NB * K * 2;
     uint8_t* b_img = smem;
     const uint32_t bar = base + b_bytes;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + b_bytes + 16);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + b_bytes + 32);
     for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
         int r = i / K, k = i - r * K;
         uint32_t off = (k >> 6) * (NB * 128) + sw128_offset(r, k & 63);
@@ -978,10 +1152,11 @@ selftest_gemm_ts_kernel(const float* __restrict__ A, const float* __restrict__ B
     }
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 8, (1u << 20) - 1);
         fence_barrier_init();
     }
     if (warp == 0) {
-        if (PAIR) tmem_alloc_2cta(base + b_bytes + 16, 512); else tmem_alloc(base + b_bytes + 16, 512);
+        if (PAIR) tmem_alloc_2cta(base + b_bytes + 32, 512); else tmem_alloc(base + b_bytes + 32, 512);
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -1006,14 +1181,31 @@ selftest_gemm_ts_kernel(const float* __restrict__ A, const float* __restrict__ B
     tc_fence_after();
     if (rank == 0 && threadIdx.x == 0) {
         const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, N, 0, 0);
-        for (int k16 = 0; k16 < K / 16; ++k16) {
-            int kb = k16 >> 2, kk = k16 & 3;
-            uint64_t bd = make_sdesc_sw128(base + kb * (NB * 128) + kk * 32, 16, 1024);
-            if (PAIR) mma_bf16_ts_2cta(tmem_base, tmem_base + A_COL + k16 * 8, bd, idesc, k16 > 0 ? 1u : 0u);
-            else mma_bf16_ts(tmem_base, tmem_base + A_COL + k16 * 8, bd, idesc, k16 > 0 ? 1u : 0u);
+        uint64_t bd[16];
+#pragma unroll
+        for (int k16 = 0; k16 < 16; ++k16) {
+            const int kc = (k16 < K / 16) ? k16 : 0, kb = kc >> 2, kk = kc & 3;
+            bd[k16] = make_sdesc_sw128(base + kb * (NB * 128) + kk * 32, 16, 1024);
+        }
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int k16 = 0; k16 < 16; ++k16) {
+                if (k16 < K / 16) {
+                    const uint32_t acc = (k16 > 0 || r > 0) ? 1u : 0u;
+                    if (PAIR) mma_bf16_ts_2cta(tmem_base, tmem_base + A_COL + k16 * 8, bd[k16], idesc, acc);
+                    else mma_bf16_ts(tmem_base, tmem_base + A_COL + k16 * 8, bd[k16], idesc, acc);
+                    if (probe >= 2 && (k16 & 3) == 3) {          // probe: cost of a commit per 4 MMAs (barrier never waited on)
+                        if (PAIR) mma_commit_2cta(bar + 8, 0x3); else mma_commit(bar + 8);
+                    }
+                }
+            }
         }
         if (PAIR) mma_commit_2cta(bar, 0x3); else mma_commit(bar);
+        mbar_wait(bar, 0, 9);
+        if (cycles) cycles[0] = clock64() - t0;
     }
+    __syncthreads();                                         // nobody spins beside the issuing thread
     mbar_wait(bar, 0, 9);
     tc_fence_after();
     const int row = rank * 128 + threadIdx.x;
@@ -1083,7 +1275,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int reps, int m
 namespace nerf {
 
 long long* g_trace_buf = nullptr;
-int g_pair_mode = 0;   // 1: cta_group::2 forward kernel (nerf_debug_pair_mode)
+int g_pair_mode = 0;   // nerf_debug_pair_mode: 1 = cta_group::2 kernel, 4 = cta_group::2 kernel with TMEM-resident activations
 
 int tc_supported(const nerf_config& c, std::string* why) {
     if (c.num_layers != 8 || c.hidden_dim != 256 || c.skip_layer != 4 || c.l_xyz != 10 || c.l_dir != 4) {
@@ -1102,8 +1294,8 @@ int tc_alloc(nerf_ctx* ctx) {
     NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_tc16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_TS));
+    NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_fwd_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM_TS));
     return NERF_OK;
 }
 
@@ -1149,23 +1341,34 @@ int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, cons
     P.dbg = g_pair_mode >> 3;
     if (save_acts && !ctx->act_save[net]) return fail(NERF_ERR_STATE, "tc_forward_rays: ctx was not created with training=1");
     timing_begin(0, st);
-    if (g_pair_mode & 5) {
+    if (g_pair_mode & 4) {
+        // CTA pairs, activations in tensor memory: one 256-row unit per cluster
+        const int clusters = (int)(P.n_pairs < num_sms() / 2 ? P.n_pairs : num_sms() / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(ts::THREADS);
+        cfg.dynamicSmemBytes = ts::SMEM_TS;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (save_acts) NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_ts_kernel<true>, P));
+        else NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_ts_kernel<false>, P));
+    } else if (g_pair_mode & 1) {
         // CTA pairs: clusters of 2 over 512-row quads
         const int64_t n_quads = (P.n_pairs + 1) / 2;
         const int clusters = (int)(n_quads < num_sms() / 2 ? n_quads : num_sms() / 2);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * clusters);
-        cfg.blockDim = dim3((g_pair_mode & 4) ? NUM_THREADS16 : NUM_THREADS);
+        cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = SMEM_BYTES;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (g_pair_mode & 4) {
-            if (save_acts) NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc16_kernel<true>, P));
-            else NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc16_kernel<false>, P));
-        } else if (save_acts) NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc_kernel<true, true>, P));
+        if (save_acts) NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc_kernel<true, true>, P));
         else NERF_CUDA(cudaLaunchKernelEx(&cfg, nerf_mlp_fwd_tc_kernel<false, true>, P));
     } else {
         int grid = (int)(P.n_pairs < num_sms() ? P.n_pairs : num_sms());
@@ -1217,12 +1420,15 @@ extern "C" int nerf_selftest_gemm_2cta(const float* a, const float* b, float* c,
     return NERF_OK;
 }
 
-// selects the CTA-pair (cta_group::2) variant of the fused forward kernel (0 = single-CTA variant)
+// selects an experimental variant of the fused forward kernel: 0 = default (single CTA), 1 = CTA pair (cta_group::2),
+// 4 = CTA pair with the activations resident in tensor memory ("TS" MMAs)
 extern "C" int nerf_debug_pair_mode(int on) { nerf::g_pair_mode = on; return NERF_OK; }
 
 // self-test of TMEM-resident A operands ("TS" MMAs): pair = 0 -> C (128, n), pair = 1 -> C (256, n) over a CTA pair
-extern "C" int nerf_selftest_gemm_ts(const float* a, const float* b, float* c, int n, int k, int pair, void* stream) {
+extern "C" int nerf_selftest_gemm_ts(const float* a, const float* b, float* c, int n, int k, int pair, int reps, int probe,
+                                     long long* cycles_dev, void* stream) {
     NERF_CHECK_ARG(a && b && c && (n == 128 || n == 256) && k >= 64 && k <= 256 && (k % 64) == 0, "bad arguments");
+    NERF_CHECK_ARG(reps >= 1 && (probe == 0 || probe == 2), "reps must be >= 1; probe mode 0 or 2");
     const int nb = pair ? n / 2 : n;
     size_t smem = (size_t)nb * k * 2 + 64 + 1024;
     if (pair) {
@@ -1233,10 +1439,10 @@ extern "C" int nerf_selftest_gemm_ts(const float* a, const float* b, float* c, i
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        NERF_CUDA(cudaLaunchKernelEx(&cfg, selftest_gemm_ts_kernel<true>, a, b, c, n, k));
+        NERF_CUDA(cudaLaunchKernelEx(&cfg, selftest_gemm_ts_kernel<true>, a, b, c, n, k, reps, probe, cycles_dev));
     } else {
         NERF_CUDA(cudaFuncSetAttribute(selftest_gemm_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        selftest_gemm_ts_kernel<false><<<1, 128, smem, (cudaStream_t)stream>>>(a, b, c, n, k);
+        selftest_gemm_ts_kernel<false><<<1, 128, smem, (cudaStream_t)stream>>>(a, b, c, n, k, reps, probe, cycles_dev);
     }
     NERF_LAUNCHED();
     return NERF_OK;

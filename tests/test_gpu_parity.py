@@ -193,6 +193,44 @@ def test_tcgen05_selftest_gemm(nk, mode, N, K):
     np.testing.assert_allclose(c.cpu().numpy(), ref.numpy(), atol=2e-3, rtol=1e-4)
 
 
+@pytest.mark.parametrize("pair,N,K", [(0, 128, 64), (0, 256, 256), (1, 128, 128), (1, 256, 256)])
+def test_tcgen05_selftest_gemm_tmem_a(nk, pair, N, K):
+    """MMAs whose A operand lives in tensor memory (written by tcgen05.st), single CTA and CTA pair (M = 256)."""
+    from nerf_keras_b200 import _lib
+    M = 256 if pair else 128
+    gen = torch.Generator().manual_seed(pair * 1000 + N + K)
+    a = torch.randn(M, K, generator=gen); b = torch.randn(N, K, generator=gen)
+    ref = a.bfloat16().float() @ b.bfloat16().float().T
+    c = torch.zeros(M, N, device="cuda")
+    a_d, b_d = a.cuda(), b.cuda()
+    _lib.check(_lib.lib().nerf_selftest_gemm_ts(a_d.data_ptr(), b_d.data_ptr(), c.data_ptr(), N, K, pair, 1, 0, None,
+                                                torch.cuda.current_stream().cuda_stream), "selftest")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(c.cpu().numpy(), ref.numpy(), atol=2e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", [1, 4])
+def test_pair_kernel_variants_match_default(nk, mode):
+    """The opt-in CTA-pair forward kernels (cta_group::2; mode 4 keeps the activations in tensor memory) agree with the
+    default kernel: mode 1 bit for bit, mode 4 within bf16 rounding of the encoding (its octave recurrence differs)."""
+    from nerf_keras_b200 import _lib
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    tr = _trainer(nk, g, wc, wf, nk.PRECISION_BF16_TC)
+    L = _lib.lib()
+    try:
+        L.nerf_debug_pair_mode(0)
+        ref = tr.mlp_forward_rays("fine", g["o"], g["d"], g["t_all"]).clone()
+        L.nerf_debug_pair_mode(mode)
+        got = tr.mlp_forward_rays("fine", g["o"], g["d"], g["t_all"]).clone()
+        torch.cuda.synchronize()
+    finally:
+        L.nerf_debug_pair_mode(0)
+    err = (got - ref).abs().max().item()
+    assert err == 0.0 if mode == 1 else err <= 2e-2, err
+    assert np.abs(got.cpu().numpy() - g["pred_f"]).max() <= 5e-2
+
+
 # ---------------------------------------------------------------- MLP
 @pytest.mark.parametrize("name", ["lego_small", "fern_small"])
 def test_mlp_fp32_model_call(nk, name):
