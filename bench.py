@@ -33,8 +33,8 @@ FLOP_PER_SAMPLE_FWD = 1186816          # BASELINE.md section 3 (un-padded, both 
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused forward kernel per launch (mean of the coarse and fine
 # launches of one step) from the committed `ncu --set full` captures: profiles/r1_train_kernels_ncu_summary.txt
 # (training variant, writes the saved operand images) and profiles/r1_render_fwd_ncu_summary.txt (render variant)
-NCU_TRAFFIC_PER_LAUNCH = {"train": (0.012068e9 + 1.333799e9 + 0.031599e9 + 4.119096e9) / 2,
-                          "render": (4.589568e6 + 6.686720e6) / 2}
+NCU_TRAFFIC_PER_LAUNCH = {"train": (0.025934e9 + 1.348226e9 + 0.073420e9 + 4.165228e9) / 2,
+                          "render": (4.590592e6 + 6.688768e6 + 1.280e3) / 2}
 CPU_SAMPLE_RAYS = 256                  # bounded CPU sample (rays per CPU step)
 
 
