@@ -146,6 +146,18 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ 
     }
 }
 
+// ReLU sign masks for the backward pass, one funnel shift per element: `neg` collects the fp32 sign bits of the
+// pre-activations in arrival order (element 0 ends up in bit 31); the mask is the bit-reversed complement, i.e.
+// bit q = (x_q >= +0).  (x == +0.0 exactly counts as active; TF's ReLU'(0) = 0 differs only on that measure-zero set.)
+__device__ __forceinline__ uint32_t push_signs(uint32_t neg, float x0, float x1, float x2, float x3) {
+    neg = __funnelshift_l(__float_as_uint(x0), neg, 1);
+    neg = __funnelshift_l(__float_as_uint(x1), neg, 1);
+    neg = __funnelshift_l(__float_as_uint(x2), neg, 1);
+    neg = __funnelshift_l(__float_as_uint(x3), neg, 1);
+    return neg;
+}
+__device__ __forceinline__ uint32_t signs_to_mask(uint32_t neg) { return ~__brev(neg); }
+
 // ---- epilogue building blocks ---------------------------------------------------------------------
 // one 32-column group of a trunk / feature layer: acc + bias (packed fp32x2 adds), fused ReLU + bf16
 // convert, optional sigma head accumulation and ReLU mask, then four 16-byte swizzled stores.
@@ -155,7 +167,7 @@ __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float
     const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias + CG * 32);
     const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(wsig + CG * 32);
     uint32_t pk[16];
-    mk = 0;
+    uint32_t neg = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const ulonglong2 bb = b2[q];
@@ -164,21 +176,17 @@ __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float
         float x0, x1, x2, x3;
         f2_unpack(x01, x0, x1);
         f2_unpack(x23, x2, x3);
+        if (SAVE && RELU) neg = push_signs(neg, x0, x1, x2, x3);
         if (SIGMA) {
             x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
             const ulonglong2 ws = s2[q];
             sig2 = f2_fma(f2_pack(__float_as_uint(x0), __float_as_uint(x1)), ws.x, sig2);
             sig2 = f2_fma(f2_pack(__float_as_uint(x2), __float_as_uint(x3)), ws.y, sig2);
         }
-        if (SAVE && RELU) {
-            mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
-            mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
-            mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
-            mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
-        }
         pk[2 * q] = cvt_bf16x2<RELU>(x0, x1);
         pk[2 * q + 1] = cvt_bf16x2<RELU>(x2, x3);
     }
+    mk = signs_to_mask(neg);
     if (STORE) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -240,13 +248,14 @@ __device__ __forceinline__ void ddir_group(const uint32_t (&v)[32], const float*
     const ulonglong2* wg = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 128 + CG * 32);
     const ulonglong2* wb = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 256 + CG * 32);
     uint32_t pk[16];
-    mk = 0;
+    uint32_t neg = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const ulonglong2 dd = d2[q];
         float x0, x1, x2, x3;
         f2_unpack(f2_add(f2_pack(v[4 * q], v[4 * q + 1]), dd.x), x0, x1);
         f2_unpack(f2_add(f2_pack(v[4 * q + 2], v[4 * q + 3]), dd.y), x2, x3);
+        if (SAVE) neg = push_signs(neg, x0, x1, x2, x3);
         x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
         const uint64_t x01 = f2_pack(__float_as_uint(x0), __float_as_uint(x1));
         const uint64_t x23 = f2_pack(__float_as_uint(x2), __float_as_uint(x3));
@@ -255,14 +264,11 @@ __device__ __forceinline__ void ddir_group(const uint32_t (&v)[32], const float*
         g2 = f2_fma(x01, b.x, g2); g2 = f2_fma(x23, b.y, g2);
         b2acc = f2_fma(x01, c.x, b2acc); b2acc = f2_fma(x23, c.y, b2acc);
         if (SAVE) {
-            mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
-            mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
-            mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
-            mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
             pk[2 * q] = cvt_bf16x2<false>(x0, x1);
             pk[2 * q + 1] = cvt_bf16x2<false>(x2, x3);
         }
     }
+    mk = signs_to_mask(neg);
     if (SAVE) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -563,12 +569,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
 // ------------------------------------------------------------------------------------------------
 namespace ts {
 constexpr int WORKER_WARPS = 16;
-constexpr int THREADS = (WORKER_WARPS + 2) * 32;     // + producer warp + issuer (leader) / forwarder (peer) warp
-constexpr int STAGES_TS = 16;
+constexpr int NI = 1;                                // MMA issuer warps (leader CTA); see the note on NI > 1 at the issuer loop
+constexpr int THREADS = (WORKER_WARPS + 1 + NI) * 32;   // workers + producer warp + issuer warps (peer: one forwarder)
+constexpr int STAGES_TS = 8;
 constexpr int SUB_BYTES = CHUNK_BYTES / 2;           // this CTA's 64 weight rows of a 16 KB chunk
+constexpr int SLOT_BYTES = 2 * SUB_BYTES;            // a ring slot = two consecutive K-blocks of one N-half = 8 MMAs
 constexpr int SM_ENC = 0;                            // 2 x 16 KB: bf16(enc) K-block, xyz residual K-block
 constexpr int SM_RING_TS = 2 * 16384;
-constexpr int SM_SIDE_TS = SM_RING_TS + STAGES_TS * SUB_BYTES;
+constexpr int SM_SIDE_TS = SM_RING_TS + STAGES_TS * SLOT_BYTES;
 constexpr int SM_DIRB_TS = SM_SIDE_TS + SIDE_FLOATS * 4;           // 4 rays x 128 floats
 constexpr int SM_PART = SM_DIRB_TS + 4 * 512;                      // float4 [128 rows][4 column groups]
 constexpr int SM_FULL_TS = SM_PART + 128 * 4 * 16;
@@ -576,7 +584,8 @@ constexpr int SM_EMPTY_TS = SM_FULL_TS + 8 * STAGES_TS;
 constexpr int SM_PFULL_TS = SM_EMPTY_TS + 8 * STAGES_TS;
 constexpr int SM_ACCF_TS = SM_PFULL_TS + 8 * STAGES_TS;            // 2: accumulator N-half complete
 constexpr int SM_AREADY_TS = SM_ACCF_TS + 16;                      // 2: activation K-half written (leader's copy counts)
-constexpr int SM_TMEM_TS = SM_AREADY_TS + 16;
+constexpr int SM_TOK_TS = SM_AREADY_TS + 16;                       // NI: issue token of the relay
+constexpr int SM_TMEM_TS = SM_TOK_TS + 8 * NI;
 constexpr int SMEM_TS = SM_TMEM_TS + 16 + 1024;
 static_assert(SM_DIRB_TS % 16 == 0 && SM_FULL_TS % 8 == 0, "alignment");
 static_assert(SMEM_TS <= 232448, "exceeds the 227 KB shared memory limit");
@@ -589,28 +598,24 @@ __device__ __forceinline__ void ts_group(const uint32_t (&v)[32], const float* b
                                          uint32_t& mk, uint32_t (&pk)[16]) {
     const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias);
     const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(wsig);
-    mk = 0;
+    uint32_t neg = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const ulonglong2 bb = b2[q];
         float x0, x1, x2, x3;
         f2_unpack(f2_add(f2_pack(v[4 * q], v[4 * q + 1]), bb.x), x0, x1);
         f2_unpack(f2_add(f2_pack(v[4 * q + 2], v[4 * q + 3]), bb.y), x2, x3);
+        if (SAVE && RELU) neg = push_signs(neg, x0, x1, x2, x3);
         if (SIGMA) {
             x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
             const ulonglong2 ws = s2[q];
             sig2 = f2_fma(f2_pack(__float_as_uint(x0), __float_as_uint(x1)), ws.x, sig2);
             sig2 = f2_fma(f2_pack(__float_as_uint(x2), __float_as_uint(x3)), ws.y, sig2);
         }
-        if (SAVE && RELU) {
-            mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
-            mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
-            mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
-            mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
-        }
         pk[2 * q] = cvt_bf16x2<RELU>(x0, x1);
         pk[2 * q + 1] = cvt_bf16x2<RELU>(x2, x3);
     }
+    mk = signs_to_mask(neg);
 }
 
 // 16 channels [16 CQ, 16 CQ + 16) of the positional encoding of one point, packed bf16x2.  sincosf at the first
@@ -778,7 +783,7 @@ __device__ __forceinline__ void ts_worker(const FwdParams& P, uint8_t* smem, uin
                 const ulonglong2* wg = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 128 + CQ * 32);
                 const ulonglong2* wb = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 256 + CQ * 32);
                 uint64_t r2 = 0ull, g2 = 0ull, b2 = 0ull;
-                uint32_t v[32], pk[16], mk = 0;
+                uint32_t v[32], pk[16], neg = 0;
                 tmem_ld32(t_lane + T_ACC + CQ * 32, v);
                 tmem_ld_wait();
                 tc_fence_before();
@@ -788,6 +793,7 @@ __device__ __forceinline__ void ts_worker(const FwdParams& P, uint8_t* smem, uin
                     float x0, x1, x2, x3;
                     f2_unpack(f2_add(f2_pack(v[4 * q], v[4 * q + 1]), dd.x), x0, x1);
                     f2_unpack(f2_add(f2_pack(v[4 * q + 2], v[4 * q + 3]), dd.y), x2, x3);
+                    if (SAVE) neg = push_signs(neg, x0, x1, x2, x3);
                     x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
                     const uint64_t x01 = f2_pack(__float_as_uint(x0), __float_as_uint(x1));
                     const uint64_t x23 = f2_pack(__float_as_uint(x2), __float_as_uint(x3));
@@ -796,10 +802,6 @@ __device__ __forceinline__ void ts_worker(const FwdParams& P, uint8_t* smem, uin
                     g2 = f2_fma(x01, b.x, g2); g2 = f2_fma(x23, b.y, g2);
                     b2 = f2_fma(x01, c.x, b2); b2 = f2_fma(x23, c.y, b2);
                     if (SAVE) {
-                        mk |= (x0 > 0.f ? 1u : 0u) << (4 * q);
-                        mk |= (x1 > 0.f ? 1u : 0u) << (4 * q + 1);
-                        mk |= (x2 > 0.f ? 1u : 0u) << (4 * q + 2);
-                        mk |= (x3 > 0.f ? 1u : 0u) << (4 * q + 3);
                         pk[2 * q] = cvt_bf16x2<false>(x0, x1);
                         pk[2 * q + 1] = cvt_bf16x2<false>(x2, x3);
                     }
@@ -810,7 +812,7 @@ __device__ __forceinline__ void ts_worker(const FwdParams& P, uint8_t* smem, uin
                 if (SAVE) {
                     save_row_half(save_tile + SAVE_HD + (CQ >> 1) * 16384, row, (CQ & 1) * 4, pk);
                     uint32_t* mp = mask_tile + ((size_t)8 * 128 + row) * 8;
-                    mp[CQ] = mk;
+                    mp[CQ] = signs_to_mask(neg);
                     mp[4 + CQ] = 0u;
                 }
                 named_bar_sync(1, WORKER_WARPS * 32);
@@ -849,7 +851,9 @@ __global__ void __launch_bounds__(ts::THREADS, 1) nerf_mlp_fwd_ts_kernel(const F
             mbar_init(base + SM_ACCF_TS + 8 * i, 1);
             mbar_init(base + SM_AREADY_TS + 8 * i, 2 * WORKER_WARPS);   // one arrival per worker warp of both CTAs
         }
+        for (int i = 0; i < NI; ++i) mbar_init(base + SM_TOK_TS + 8 * i, 1);
         fence_barrier_init();
+        mbar_arrive(base + SM_TOK_TS);                                   // the first issuer holds the token
     }
     float* side = reinterpret_cast<float*>(smem + SM_SIDE_TS);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM_TS);
@@ -861,42 +865,53 @@ __global__ void __launch_bounds__(ts::THREADS, 1) nerf_mlp_fwd_ts_kernel(const F
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int my_units = (n_units > unit) ? (int)((n_units - unit + n_units_grid - 1) / n_units_grid) : 0;
+    // ring slots per tile: one per (phase, N-half, pair of K-blocks), in weight-stream order
+    int slots_per_tile = 0;
+    for (int ph = 0; ph < N_PHASES; ++ph) slots_per_tile += c_fwd_prog.chunks[ph] / 2;
 
     if (warp == WORKER_WARPS) {
-        // ---- producer: this CTA's half (64 weight rows) of every chunk, in stream order ----
+        // ---- producer: this CTA's half (64 weight rows) of two consecutive chunks per slot, in stream order ----
         if (lane == 0) {
             int slot = 0;
             uint32_t par = 1;
             const uint8_t* src0 = reinterpret_cast<const uint8_t*>(P.w_chunks) + rank * SUB_BYTES;
             for (int it = 0; it < my_units; ++it)
-                for (int c = 0; c < N_CHUNKS; ++c) {
+                for (int c = 0; c < N_CHUNKS; c += 2) {
+                    const uint32_t full = base + SM_FULL_TS + 8 * slot, dst = base + SM_RING_TS + slot * SLOT_BYTES;
                     mbar_wait(base + SM_EMPTY_TS + 8 * slot, par, 1);
-                    mbar_arrive_expect_tx(base + SM_FULL_TS + 8 * slot, SUB_BYTES);
-                    bulk_g2s(base + SM_RING_TS + slot * SUB_BYTES, src0 + (size_t)c * CHUNK_BYTES, SUB_BYTES,
-                             base + SM_FULL_TS + 8 * slot);
+                    mbar_arrive_expect_tx(full, SLOT_BYTES);
+                    bulk_g2s(dst, src0 + (size_t)c * CHUNK_BYTES, SUB_BYTES, full);
+                    bulk_g2s(dst + SUB_BYTES, src0 + (size_t)(c + 1) * CHUNK_BYTES, SUB_BYTES, full);
                     if (++slot == STAGES_TS) { slot = 0; par ^= 1; }
                 }
         }
-    } else if (warp == WORKER_WARPS + 1) {
+    } else if (warp > WORKER_WARPS) {
+        const int k = warp - (WORKER_WARPS + 1);                          // issuer index in the relay
         if (lane == 0 && rank != 0) {
-            // ---- peer: forward "my ring slot is full" to the leader ----
-            int slot = 0;
-            uint32_t par = 0;
-            for (int g = 0; g < my_units * N_CHUNKS; ++g) {
-                mbar_wait(base + SM_FULL_TS + 8 * slot, par, 7);
-                mbar_arrive_cluster(map_to_cta(base + SM_PFULL_TS + 8 * slot, 0));
-                if (++slot == STAGES_TS) { slot = 0; par ^= 1; }
+            if (k == 0) {
+                // ---- peer: forward "my ring slot is full" to the leader ----
+                int slot = 0;
+                uint32_t par = 0;
+                for (int g = 0; g < my_units * slots_per_tile; ++g) {
+                    mbar_wait(base + SM_FULL_TS + 8 * slot, par, 7);
+                    mbar_arrive_cluster(map_to_cta(base + SM_PFULL_TS + 8 * slot, 0));
+                    if (++slot == STAGES_TS) { slot = 0; par ^= 1; }
+                }
             }
         } else if (lane == 0) {
-            // ---- leader: the MMA issuer ----
+            // ---- leader: MMA issuer.  The loop is written as a relay of NI issuer threads (slot seq is issued by thread
+            // seq % NI after it has waited for the slot's inputs and for a token), but NI must stay 1: with NI = 4 the
+            // kernel ran 1.4x faster and produced WRONG results on hardware -- MMAs issued by different threads into
+            // the same accumulator are not ordered by tcgen05.fence + mbarrier hand-off (only completion, i.e.
+            // tcgen05.commit + wait, orders them), so a zero-initialising MMA can be overtaken. ----
             const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
             const uint32_t lbo_bits = (16u >> 4) << 16;
             const uint32_t enc0 = ((base + SM_ENC) & 0x3FFFF) >> 4;
             const uint32_t ring0 = ((base + SM_RING_TS) & 0x3FFFF) >> 4;
             const uint32_t idesc = make_idesc_bf16(256, 128, 0, 0);
             const uint32_t accf0 = base + SM_ACCF_TS, ar0 = base + SM_AREADY_TS;
-            int slot = 0;
-            uint32_t ring_par = 0, ar_par = 0;
+            const uint32_t tok_mine = base + SM_TOK_TS + 8 * k, tok_next = base + SM_TOK_TS + 8 * ((k + 1) % NI);
+            uint32_t seq = 0, ar_par = 0, tok_par = 0;
             for (int it = 0; it < my_units; ++it) {
                 int e = 0;                                            // epilogues so far: TS phases read buffer (e - 1) & 1
                 for (int ph = 0; ph < N_PHASES; ++ph) {
@@ -906,60 +921,57 @@ __global__ void __launch_bounds__(ts::THREADS, 1) nerf_mlp_fwd_ts_kernel(const F
                     const bool consumes = !(enc && acc_in);           // phase 6 only adds the skip rows: nothing new to wait for
                     const bool has_epi = (ph != 5);
                     const uint32_t a_buf = tmem_base + T_ABUF + ((e - 1) & 1) * 128;
-                    trace_ev(P.trace, 0, it, ph, 0);
-                    long long w_full = 0, w_pfull = 0, w_issue = 0;   // diagnostics
                     for (int h = 0; h < halves; ++h) {
                         const uint32_t d_tmem = tmem_base + T_ACC + h * 128;
-                        for (int kb = 0; kb < kbs; ++kb) {
+                        for (int kp = 0; kp < kbs / 2; ++kp, ++seq) {
+                            if ((int)(seq % NI) != k) continue;
+                            const uint32_t slot = seq % STAGES_TS, ring_par = (seq / STAGES_TS) & 1;
+                            if (k == 0) trace_ev(P.trace, 0, it, ph, 0);
+                            // the first slot that touches a K-half waits for it; later slots follow it in the relay
                             if (consumes && h == 0) {
-                                if (kb == 0) {
-                                    mbar_wait_cluster(ar0, ar_par, 3);
-                                    if (enc) mbar_wait_cluster(ar0 + 8, ar_par, 5);
-                                    trace_ev(P.trace, 0, it, ph, 1);
-                                } else if (!enc && kb == kbs / 2) {
-                                    mbar_wait_cluster(ar0 + 8, ar_par, 5);
-                                    trace_ev(P.trace, 0, it, ph, 3);
-                                }
+                                if (kp == 0) mbar_wait_cluster(ar0, ar_par, 3);
+                                if (enc || kp == 1) mbar_wait_cluster(ar0 + 8, ar_par, 5);
                             }
-                            const long long tw0 = P.trace ? clock64() : 0;
                             mbar_wait(base + SM_FULL_TS + 8 * slot, ring_par, 4);
-                            const long long tw1 = P.trace ? clock64() : 0;
                             mbar_wait_cluster(base + SM_PFULL_TS + 8 * slot, ring_par, 8);
-                            const long long tw2 = P.trace ? clock64() : 0;
+                            mbar_wait(tok_mine, tok_par, 9);
+                            tok_par ^= 1;
                             tc_fence_after();
-                            const uint32_t b_lo = (ring0 + slot * (SUB_BYTES >> 4)) | lbo_bits;
-                            const bool acc0 = (kb > 0) || acc_in;
-                            const int n_mma = (enc && kb == 1) ? 1 : 4;
+                            if (k == 0) trace_ev(P.trace, 0, it, ph, 1);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k < n_mma) {
-                                    const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
-                                    const uint32_t accum = (acc0 || k > 0) ? 1u : 0u;
-                                    if (enc) {
-                                        const uint32_t a_lo = (enc0 + kb * (16384 >> 4)) | lbo_bits;
-                                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
-                                        mma_bf16_ss_2cta(d_tmem, ad, bd, idesc, accum);
-                                    } else {
-                                        mma_bf16_ts_2cta(d_tmem, a_buf + kb * 32 + k * 8, bd, idesc, accum);
+                            for (int sub = 0; sub < 2; ++sub) {
+                                const int kb = 2 * kp + sub;
+                                const uint32_t b_lo = (ring0 + slot * (SLOT_BYTES >> 4) + sub * (SUB_BYTES >> 4)) | lbo_bits;
+                                const bool acc0 = (kb > 0) || acc_in;
+                                const int n_mma = (enc && kb == 1) ? 1 : 4;
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk) {
+                                    if (kk < n_mma) {
+                                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * kk);
+                                        const uint32_t accum = (acc0 || kk > 0) ? 1u : 0u;
+                                        if (enc) {
+                                            const uint32_t a_lo = (enc0 + kb * (16384 >> 4)) | lbo_bits;
+                                            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * kk);
+                                            mma_bf16_ss_2cta(d_tmem, ad, bd, idesc, accum);
+                                        } else {
+                                            mma_bf16_ts_2cta(d_tmem, a_buf + kb * 32 + kk * 8, bd, idesc, accum);
+                                        }
                                     }
                                 }
                             }
                             mma_commit_2cta(base + SM_EMPTY_TS + 8 * slot, 0x3);
-                            if (P.trace) { w_full += tw1 - tw0; w_pfull += tw2 - tw1; w_issue += clock64() - tw2; }
-                            if (++slot == STAGES_TS) { slot = 0; ring_par ^= 1; }
-                        }
-                        if (has_epi) {
-                            mma_commit_2cta(accf0 + 8 * h, 0x3);
-                            if (halves == 1) mma_commit_2cta(accf0 + 8, 0x3);
+                            // the last slot of an N-half: its MMAs depend (accumulator chain) on every earlier one
+                            if (has_epi && kp == kbs / 2 - 1) {
+                                mma_commit_2cta(accf0 + 8 * h, 0x3);
+                                if (halves == 1) mma_commit_2cta(accf0 + 8, 0x3);
+                            }
+                            tc_fence_before();                        // my MMAs are ordered before the next issuer's
+                            mbar_arrive(tok_next);
+                            if (k == 0) trace_ev(P.trace, 0, it, ph, 2);
                         }
                     }
                     if (consumes) ar_par ^= 1;
                     if (has_epi) ++e;
-                    trace_ev(P.trace, 0, it, ph, 2);
-                    if (P.trace && blockIdx.x == 0 && it < 3) {
-                        long long* tp = P.trace + ((1 * 3 + it) * 16 + ph) * 4;
-                        tp[0] = w_full; tp[1] = w_pfull; tp[2] = w_issue;
-                    }
                 }
             }
         }

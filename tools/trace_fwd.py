@@ -11,10 +11,17 @@ o, d = nk.get_rays(64, 64, 88.0, nk.pose_spherical(20.0, -30.0, 4.0))
 o, d = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
 t = nk.generate_t_vals(2.0, 6.0, B, Nc, False)
 L.nerf_debug_pair_mode(int(os.environ.get("PAIR", "0")))
-for _ in range(2): tr.mlp_forward_rays("coarse", o, d, t)
+SAVE = int(os.environ.get("SAVE", "0"))       # 1: trace the training variant (saves operand images)
+if SAVE:
+    tr.compile(nk.Adam(5e-4), nk.MeanSquaredError())
+    dp = torch.randn(B, Nc, 4, device="cuda")
+    run = lambda: tr.debug_mlp_grads("coarse", o, d, t, dp)
+else:
+    run = lambda: tr.mlp_forward_rays("coarse", o, d, t)
+for _ in range(2): run()
 buf = torch.zeros(4 * 3 * 16 * 4, dtype=torch.int64, device="cuda")
 L.nerf_debug_trace(buf.data_ptr())
-tr.mlp_forward_rays("coarse", o, d, t)
+run()
 torch.cuda.synchronize()
 L.nerf_debug_trace(None)
 a = buf.cpu().numpy().reshape(4, 3, 16, 4)
