@@ -32,7 +32,21 @@ def test_train_lego_and_inference_scripts(tmp_path):
     assert frames.shape == (2, 100, 100, 3) and frames.dtype == np.uint8 and frames.std() > 0
 
 
-def test_train_fern_script(tmp_path):
+def test_train_fern_script_with_callback(tmp_path):
+    """train_fern.py plus the reference's per-epoch TrainCallback outputs (train_fern.py:169-268): validation PNG,
+    weights and history JSON per epoch."""
+    import json
     cfg = os.path.join(ROOT, "config", "fern_batch_debug.json")
-    out = _run([os.path.join(ROOT, "train_fern.py"), "--config", cfg, "--steps-per-epoch", "10", "--views", "4"], str(tmp_path))
+    out = _run([os.path.join(ROOT, "train_fern.py"), "--config", cfg, "--steps-per-epoch", "10", "--views", "4",
+                "--checkpoint-dir", "ckpt"], str(tmp_path))
     assert out.count("Epoch") == 2 and "nan" not in out.lower()
+    conf = json.load(open(cfg))
+    hist = [f for f in os.listdir(tmp_path / "ckpt") if f.startswith("history_")]
+    assert len(hist) == 1
+    h = json.load(open(tmp_path / "ckpt" / hist[0]))
+    assert len(h["losses"]) == len(h["psnrs"]) == len(h["losses_coarse"]) == conf["EPOCHS"]
+    assert any(f.endswith(".npz") for f in os.listdir(tmp_path / "ckpt"))
+    from PIL import Image
+    for e in range(conf["EPOCHS"]):
+        im = Image.open(tmp_path / "images" / "ckpt" / f"{e:03d}.png")
+        assert im.size == (2 * conf["WIDTH"], conf["HEIGHT"])            # predicted image | depth map

@@ -148,3 +148,18 @@ def test_gloo_world_size_2(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "rank0_ok" in r.stdout and "rank1_ok" in r.stdout
+
+
+def test_keras_bridge_role_table_matches_layer_shapes():
+    """tools/keras_weights_bridge.py (run on the reference side) and the host mirror agree on roles and (in, out) shapes."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("keras_weights_bridge", os.path.join(ROOT, "tools", "keras_weights_bridge.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from nerf_keras_b200.models import layer_shapes
+    for conf in ({"NUM_LAYERS": 8, "HIDDEN_DIM": 256, "SKIP_LAYER": 4, "L_XYZ": 10, "L_DIR": 4},
+                 {"NUM_LAYERS": 4, "HIDDEN_DIM": 64, "SKIP_LAYER": 2, "L_XYZ": 6, "L_DIR": 2}):
+        roles, shapes = mod.expected_shapes(conf)
+        want = layer_shapes(conf["NUM_LAYERS"], conf["HIDDEN_DIM"], conf["SKIP_LAYER"], conf["L_XYZ"], conf["L_DIR"])
+        assert roles == [r for r, _, _ in want]
+        assert shapes == [(fi, fo) for _, fi, fo in want]

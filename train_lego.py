@@ -17,13 +17,27 @@ def main(dataset="lego"):
     ap.add_argument("--config", type=str, default=f"config/{dataset}_batch_debug.json")
     ap.add_argument("--steps-per-epoch", type=int, default=None)
     ap.add_argument("--views", type=int, default=10)
+    ap.add_argument("--checkpoint-dir", type=str, default=None,
+                    help="per-epoch validation render (PNG), weights and history JSON, as the reference's TrainCallback")
+    ap.add_argument("--data", type=str, default=None,
+                    help="real data instead of the synthetic scene: tiny_nerf_data.npz or a Blender scene directory "
+                         "(lego), an LLFF scene directory with poses_bounds.npy (fern)")
     args = ap.parse_args()
     conf = load_config(args.config)
     name = os.path.splitext(os.path.basename(args.config))[0]
     rank, local, world = init_from_env()
     nk.set_random_seed(42)
-    prep = prepare_lego_data if dataset == "lego" else prepare_fern_data
-    train, val, (near, far), focal = prep(conf["HEIGHT"], conf["WIDTH"], n_views=args.views)
+    if args.data is not None:
+        from nerf_keras_b200 import real_data
+        if dataset == "fern":
+            train, val, (near, far), focal = real_data.prepare_fern_data(conf["HEIGHT"], conf["WIDTH"], datadir=args.data)
+        elif os.path.isdir(args.data):
+            train, val, (near, far), focal = real_data.prepare_blender_data(conf["HEIGHT"], conf["WIDTH"], args.data)
+        else:
+            train, val, (near, far), focal = real_data.prepare_lego_data(conf["HEIGHT"], conf["WIDTH"], npz_path=args.data)
+    else:
+        prep = prepare_lego_data if dataset == "lego" else prepare_fern_data
+        train, val, (near, far), focal = prep(conf["HEIGHT"], conf["WIDTH"], n_views=args.views)
     B, Nc, Nf = conf["BATCH_SIZE"], conf["NS_COARSE"], conf["NS_FINE"]
     train_ds = BatchedRayDataset(*train, Nc, B, near, far, shuffle=True, steps_per_epoch=args.steps_per_epoch,
                                  rank=rank, world=world)
@@ -33,7 +47,15 @@ def main(dataset="lego"):
     fine = nk.create_nerf_complete_model(**model_kwargs(conf))
     trainer = nk.NeRFTrainer(coarse, fine, B // world, Nc, Nf, conf["L_XYZ"], conf["L_DIR"])
     trainer.compile(optimizer=nk.Adam(learning_rate=conf["LEARNING_RATE"]), loss_fn=nk.MeanSquaredError())
-    history = trainer.fit(train_ds, validation_data=val_ds, epochs=conf["EPOCHS"], verbose=int(rank == 0))
+    callbacks = []
+    if args.checkpoint_dir and rank == 0:
+        from nerf_keras_b200.callbacks import TrainCallback
+        tag = f"l{conf['NUM_LAYERS']}_d{conf['HIDDEN_DIM']}_n{Nc + Nf}_ep{conf['EPOCHS']}"
+        callbacks.append(TrainCallback(trainer, val[1], val[2], conf["HEIGHT"], conf["WIDTH"], near, far, Nc,
+                                       args.checkpoint_dir, weight_name=f"nerf_{dataset}_{tag}.npz",
+                                       history_name=f"history_{tag}.json"))
+    history = trainer.fit(train_ds, validation_data=val_ds, epochs=conf["EPOCHS"], callbacks=callbacks,
+                          verbose=int(rank == 0))
     if rank == 0:
         os.makedirs("models", exist_ok=True)
         trainer.save_weights(f"models/nerf_{dataset}_l{conf['NUM_LAYERS']}_d{conf['HIDDEN_DIM']}_n{Nc + Nf}_{name}.npz")
