@@ -158,12 +158,37 @@ __device__ __forceinline__ uint32_t push_signs(uint32_t neg, float x0, float x1,
 }
 __device__ __forceinline__ uint32_t signs_to_mask(uint32_t neg) { return ~__brev(neg); }
 
+// Training variant: how the saved operand images reach HBM.  false (default): the tile is bulk-stored (TMA engine)
+// from shared memory after each epilogue; that costs another 64 KB of shared-memory reads per sub-tile and phase plus a
+// wait + barrier before the tile may be overwritten.  true: every epilogue thread writes its own row pieces straight
+// from registers with 256-bit global stores (two swizzled 16-byte chunks = one 32-byte sector).  Measured on B200,
+// forward of both nets per 4096-ray step: bulk stores 1.85 ms, 256-bit register stores 2.06 ms, 128-bit register
+// stores 2.44 ms -- the LSU path loses to the TMA engine even though it spares the shared-memory reads.
+constexpr bool kDirectSave = false;
+__device__ __forceinline__ void st_global_v4(uint64_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Two adjacent 16-byte chunks (2j, 2j+1) of a swizzled row share one 32-byte sector (the XOR only swaps them on odd
+// rows): one 256-bit store writes the whole sector.  pk8 = chunk 2j then chunk 2j+1; off_c0 = address of chunk 2j.
+__device__ __forceinline__ void st_global_pair(uint64_t gimg, uint32_t off_c0, bool odd_row, const uint32_t* pk8) {
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        lo[i] = odd_row ? pk8[4 + i] : pk8[i];
+        hi[i] = odd_row ? pk8[i] : pk8[4 + i];
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gimg + (off_c0 & ~16u)), "r"(lo[0]),
+                 "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
+                 : "memory");
+}
+
 // ---- epilogue building blocks ---------------------------------------------------------------------
 // one 32-column group of a trunk / feature layer: acc + bias (packed fp32x2 adds), fused ReLU + bf16
 // convert, optional sigma head accumulation and ReLU mask, then four 16-byte swizzled stores.
 template <bool RELU, bool SIGMA, bool SAVE, int CG, bool STORE>
 __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float* bias, const float* wsig,
-                                            uint64_t& sig2, uint32_t& mk, const RowStore& rs, uint32_t* held) {
+                                            uint64_t& sig2, uint32_t& mk, const RowStore& rs, uint32_t* held,
+                                            uint64_t gimg /* image base minus the tile's shared address */) {
     const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias + CG * 32);
     const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(wsig + CG * 32);
     uint32_t pk[16];
@@ -195,22 +220,28 @@ __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float
 #pragma unroll
         for (int q = 0; q < 16; ++q) held[CG * 16 + q] = pk[q];
     }
+    if (SAVE && kDirectSave) {
+        const bool odd = (rs.off[0] >> 7) & 1;                 // row parity (bit 7 of the row's shared-memory address)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            st_global_pair(gimg + (CG / 2) * (TILE_M * 128), rs.off[(CG & 1) * 4 + 2 * j], odd, pk + 8 * j);
+    }
 }
 
 // First half of a trunk / feature epilogue: columns 0..127 (runs while the MMAs of columns 128..255 are still in
 // flight).  The converted bf16 values are HELD in registers: K-blocks 0,1 of the A tile are still being read.
 template <bool RELU, bool SIGMA, bool SAVE>
 __device__ __forceinline__ void trunk_part1(uint32_t t_lane, const float* bias, const float* wsig, uint64_t& sig2,
-                                            uint32_t (&mask)[8], const RowStore& rs, uint32_t (&held)[64]) {
+                                            uint32_t (&mask)[8], const RowStore& rs, uint32_t (&held)[64], uint64_t gimg) {
     uint32_t v[32];
     tmem_ld32(t_lane, v); tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, 0, false>(v, bias, wsig, sig2, mask[0], rs, held);
+    trunk_group<RELU, SIGMA, SAVE, 0, false>(v, bias, wsig, sig2, mask[0], rs, held, gimg);
     tmem_ld32(t_lane + 32, v); tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, 1, false>(v, bias, wsig, sig2, mask[1], rs, held);
+    trunk_group<RELU, SIGMA, SAVE, 1, false>(v, bias, wsig, sig2, mask[1], rs, held, gimg);
     tmem_ld32(t_lane + 64, v); tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, 2, false>(v, bias, wsig, sig2, mask[2], rs, held);
+    trunk_group<RELU, SIGMA, SAVE, 2, false>(v, bias, wsig, sig2, mask[2], rs, held, gimg);
     tmem_ld32(t_lane + 96, v); tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, 3, false>(v, bias, wsig, sig2, mask[3], rs, held);
+    trunk_group<RELU, SIGMA, SAVE, 3, false>(v, bias, wsig, sig2, mask[3], rs, held, gimg);
 }
 // all MMAs of the phase are complete: K-blocks 0,1 may be overwritten with the held first half
 __device__ __forceinline__ void store_held(const RowStore& rs, const uint32_t (&held)[64]) {
@@ -222,27 +253,27 @@ __device__ __forceinline__ void store_held(const RowStore& rs, const uint32_t (&
 // second half: columns 128..255 straight into K-blocks 2,3 (TMEM loads pipelined one group ahead)
 template <bool RELU, bool SIGMA, bool SAVE>
 __device__ __forceinline__ void trunk_part2(uint32_t t_lane, const float* bias, const float* wsig, uint64_t& sig2,
-                                            uint32_t (&mask)[8], const RowStore& rs) {
+                                            uint32_t (&mask)[8], const RowStore& rs, uint64_t gimg) {
     uint32_t va[32], vb[32];
     tmem_ld32(t_lane + 128, va);
     tmem_ld_wait();
     tmem_ld32(t_lane + 160, vb);
-    trunk_group<RELU, SIGMA, SAVE, 4, true>(va, bias, wsig, sig2, mask[4], rs, nullptr);
+    trunk_group<RELU, SIGMA, SAVE, 4, true>(va, bias, wsig, sig2, mask[4], rs, nullptr, gimg);
     tmem_ld_wait();
     tmem_ld32(t_lane + 192, va);
-    trunk_group<RELU, SIGMA, SAVE, 5, true>(vb, bias, wsig, sig2, mask[5], rs, nullptr);
+    trunk_group<RELU, SIGMA, SAVE, 5, true>(vb, bias, wsig, sig2, mask[5], rs, nullptr, gimg);
     tmem_ld_wait();
     tmem_ld32(t_lane + 224, vb);
-    trunk_group<RELU, SIGMA, SAVE, 6, true>(va, bias, wsig, sig2, mask[6], rs, nullptr);
+    trunk_group<RELU, SIGMA, SAVE, 6, true>(va, bias, wsig, sig2, mask[6], rs, nullptr, gimg);
     tmem_ld_wait();
-    trunk_group<RELU, SIGMA, SAVE, 7, true>(vb, bias, wsig, sig2, mask[7], rs, nullptr);
+    trunk_group<RELU, SIGMA, SAVE, 7, true>(vb, bias, wsig, sig2, mask[7], rs, nullptr, gimg);
 }
 
 // one 32-column group of the ddir epilogue: + (bias + per-ray direction bias), ReLU, rgb head dot products
 template <bool SAVE, int CG>
 __device__ __forceinline__ void ddir_group(const uint32_t (&v)[32], const float* dbias /* this ray, 128 floats */,
                                            const float* side, uint64_t& r2, uint64_t& g2, uint64_t& b2acc, uint32_t& mk,
-                                           const RowStore& rs) {
+                                           const RowStore& rs, uint64_t gimg) {
     const ulonglong2* d2 = reinterpret_cast<const ulonglong2*>(dbias + CG * 32);
     const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + CG * 32);
     const ulonglong2* wg = reinterpret_cast<const ulonglong2*>(side + SIDE_WRGB + 128 + CG * 32);
@@ -271,8 +302,16 @@ __device__ __forceinline__ void ddir_group(const uint32_t (&v)[32], const float*
     mk = signs_to_mask(neg);
     if (SAVE) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        if (kDirectSave) {
+            const bool odd = (rs.off[0] >> 7) & 1;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                st_global_pair(gimg + (CG / 2) * (TILE_M * 128), rs.off[(CG & 1) * 4 + 2 * j], odd, pk + 8 * j);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                rs.store<CG / 2>((CG & 1) * 4 + c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
     }
 }
 
@@ -407,7 +446,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
             }
             // every thread of the sub-tile is past the previous tile's ddir epilogue (last reader of the staged
             // biases), and in training mode the previous tile's last bulk store has finished reading the tile
-            if (SAVE && elected) bulk_wait_read0();
+            if (SAVE && !kDirectSave && elected) bulk_wait_read0();
             named_bar_sync(1 + s, TILE_M);
 #pragma unroll
             for (int c = 0; c < 8; ++c) rs.store<0>(c, E[4 * c], E[4 * c + 1], E[4 * c + 2], E[4 * c + 3]);
@@ -416,7 +455,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
             if (staged && db_idx < n_rays * 32) reinterpret_cast<float4*>(dbs)[db_idx] = db_pref;
             tc_fence_before();
             fence_async();
-            if (SAVE) {
+            if (SAVE && kDirectSave) {
+                const uint64_t genc = reinterpret_cast<uint64_t>(save_tile + SAVE_ENC) - act_base;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st_global_pair(genc, rs.off[2 * j], (rs.off[0] >> 7) & 1, E + 8 * j);
+            } else if (SAVE) {
                 named_bar_sync(1 + s, TILE_M);
                 if (elected) { bulk_s2g(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
             }
@@ -434,7 +477,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     mbar_wait(bar_h1, accf_par, 6);
                     accf_par ^= 1;
                     tc_fence_after();
-                    if (SAVE) {
+                    if (SAVE && !kDirectSave) {
                         if (elected) bulk_wait_read0();
                         named_bar_sync(1 + s, TILE_M);
                     }
@@ -457,13 +500,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     uint32_t mask[8];
                     uint32_t held[64];
                     uint64_t sig2 = 0ull;
-                    if (ph == 8) trunk_part1<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held);
-                    else if (relu) trunk_part1<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held);
-                    else trunk_part1<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held);
+                    const uint64_t gimg = SAVE ? reinterpret_cast<uint64_t>(save_tile + ((layer < 8) ? SAVE_H + 65536 * layer
+                                                                                                    : SAVE_FEAT)) - act_base
+                                               : 0ull;
+                    if (ph == 8) trunk_part1<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held, gimg);
+                    else if (relu) trunk_part1<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held, gimg);
+                    else trunk_part1<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held, gimg);
                     mbar_wait(bar_h1, accf_par, 6);                    // every MMA of the phase is complete
                     accf_par ^= 1;
                     tc_fence_after();
-                    if (SAVE) {
+                    if (SAVE && !kDirectSave) {
                         if (elected) bulk_wait_read0();
                         named_bar_sync(1 + s, TILE_M);
                     }
@@ -471,9 +517,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     tc_fence_before();
                     fence_async();
                     arrive(bar_lo);                                    // next phase may start on K-blocks 0,1
-                    if (ph == 8) trunk_part2<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
-                    else if (relu) trunk_part2<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
-                    else trunk_part2<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs);
+                    if (ph == 8) trunk_part2<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
+                    else if (relu) trunk_part2<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
+                    else trunk_part2<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
                     if (ph == 8) {
                         float a, b;
                         f2_unpack(sig2, a, b);
@@ -487,11 +533,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                             mp[0] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
                             mp[1] = make_uint4(mask[4], mask[5], mask[6], mask[7]);
                         }
-                        named_bar_sync(1 + s, TILE_M);
-                        if (elected) {
-                            int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
-                            bulk_s2g(save_tile + off, act_base, 65536);
-                            bulk_commit();
+                        if (!kDirectSave) {
+                            named_bar_sync(1 + s, TILE_M);
+                            if (elected) {
+                                int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
+                                bulk_s2g(save_tile + off, act_base, 65536);
+                                bulk_commit();
+                            }
                         }
                     }
                     if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);  // worker: epilogue done
@@ -500,10 +548,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     // ddir epilogue: + (bias + per-ray direction bias), ReLU, rgb head (fp32), write preds
                     mbar_wait(bar_h1, accf_par, 6);
                     accf_par ^= 1;
-                    if (SAVE) {
+                    if (SAVE && !kDirectSave) {
                         if (elected) bulk_wait_read0();
                         named_bar_sync(1 + s, TILE_M);
                     }
+                    const uint64_t ghd = SAVE ? reinterpret_cast<uint64_t>(save_tile + SAVE_HD) - act_base : 0ull;
                     uint64_t r2 = 0ull, g2 = 0ull, b2 = 0ull;
                     uint32_t mask[4];
                     // staged copy lives in shared memory; ragged tiles with many short rays fall back to global
@@ -512,15 +561,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     tmem_ld32(t_lane, va);
                     tmem_ld_wait();
                     tmem_ld32(t_lane + 32, vb);
-                    ddir_group<SAVE, 0>(va, db, side, r2, g2, b2, mask[0], rs);
+                    ddir_group<SAVE, 0>(va, db, side, r2, g2, b2, mask[0], rs, ghd);
                     tmem_ld_wait();
                     tmem_ld32(t_lane + 64, va);
-                    ddir_group<SAVE, 1>(vb, db, side, r2, g2, b2, mask[1], rs);
+                    ddir_group<SAVE, 1>(vb, db, side, r2, g2, b2, mask[1], rs, ghd);
                     tmem_ld_wait();
                     tmem_ld32(t_lane + 96, vb);
-                    ddir_group<SAVE, 2>(va, db, side, r2, g2, b2, mask[2], rs);
+                    ddir_group<SAVE, 2>(va, db, side, r2, g2, b2, mask[2], rs, ghd);
                     tmem_ld_wait();
-                    ddir_group<SAVE, 3>(vb, db, side, r2, g2, b2, mask[3], rs);
+                    ddir_group<SAVE, 3>(vb, db, side, r2, g2, b2, mask[3], rs, ghd);
                     float ra, rb, ga, gb, ba, bb;
                     f2_unpack(r2, ra, rb); f2_unpack(g2, ga, gb); f2_unpack(b2, ba, bb);
                     if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);
@@ -532,14 +581,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                         uint4* mp = reinterpret_cast<uint4*>(mask_tile + ((size_t)8 * 128 + row) * 8);
                         mp[0] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
                         mp[1] = make_uint4(0u, 0u, 0u, 0u);
-                        fence_async();
-                        named_bar_sync(1 + s, TILE_M);
-                        if (elected) { bulk_s2g(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
+                        if (!kDirectSave) {
+                            fence_async();
+                            named_bar_sync(1 + s, TILE_M);
+                            if (elected) { bulk_s2g(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
+                        }
                     }
                 }
             }
         }
-        if (SAVE && elected) bulk_wait_all0();
+        if (SAVE && !kDirectSave && elected) bulk_wait_all0();
     }
 
     tc_fence_before();
