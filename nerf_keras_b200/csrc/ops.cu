@@ -674,13 +674,157 @@ __global__ void __launch_bounds__(128) resample_merge_kernel(const float* __rest
     }
 }
 
+// Fast path of the fused resample + merge: the coarse samples of a ray are already sorted (generate_t_vals is
+// monotone), so only the nf fine samples need sorting.  They are sorted IN REGISTERS (FI keys + source indices per lane,
+// bitonic network: partner distances < 32 through warp shuffles, >= 32 between a lane's own registers) and the two
+// sorted sequences are merged by rank: a fine sample lands at (its sorted rank) + #(coarse <= it), a coarse sample at
+// (its index) + #(fine < it) -- ~1.1 K warp instructions per ray instead of ~10 K for the 256-key shared-memory
+// bitonic sort below.  Pairs move together, so equal keys cannot break the permutation.  A ray whose coarse samples
+// are NOT sorted takes the rank-counting path (all keys, ties broken by index).
+template <int FI>
+__global__ void __launch_bounds__(128) resample_merge_sorted_kernel(const float* __restrict__ t,
+                                                                    const float* __restrict__ weights,
+                                                                    const float* __restrict__ u, int64_t B, int nc, int nf,
+                                                                    float* __restrict__ t_all,
+                                                                    int32_t* __restrict__ src_idx) {
+    constexpr int P = 32 * FI;
+    extern __shared__ float smem_rm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int per_warp = (2 * nc + 2) + nc + P;
+    float* cdf = smem_rm + (size_t)wib * per_warp;
+    float* tm = cdf + nc + 1;
+    float* ck = tm + nc + 1;          // coarse keys
+    float* fk = ck + nc;              // fine keys: raw, then sorted
+    const int na = nc + nf;
+    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < B; ray += warps_total) {
+        const float* tr = t + ray * nc;
+        float* out_t = t_all + ray * na;
+        int32_t* out_i = src_idx ? src_idx + ray * na : nullptr;
+        build_cdf(weights + ray * nc, nc, cdf, lane);
+        bool ok = true;
+        for (int n = lane; n < nc; n += 32) {
+            const float tn = tr[n];
+            ck[n] = tn;
+            if (n < nc - 1) {
+                const float tn1 = tr[n + 1];
+                tm[n] = __fmul_rn(0.5f, __fadd_rn(tn1, tn));
+                ok = ok && (tn <= tn1);
+            }
+        }
+        const bool sorted = __all_sync(0xffffffffu, ok);
+        __syncwarp();
+        float key[FI];
+        int idx[FI];
+#pragma unroll
+        for (int r = 0; r < FI; ++r) {
+            const int j = r * 32 + lane;
+            key[r] = (j < nf) ? invert_cdf(cdf, tm, nc, u[ray * nf + j]) : __int_as_float(0x7f800000);
+            idx[r] = (j < nf) ? nc + j : -1;
+        }
+        if (!sorted) {
+            // rank counting over all keys, ties broken by source index
+#pragma unroll
+            for (int r = 0; r < FI; ++r) fk[r * 32 + lane] = key[r];
+            __syncwarp();
+            for (int e = lane; e < na; e += 32) {
+                const float x = (e < nc) ? ck[e] : fk[e - nc];
+                int pos = 0;
+                for (int k = 0; k < na; ++k) {
+                    const float y = (k < nc) ? ck[k] : fk[k - nc];
+                    pos += (y < x || (y == x && k < e)) ? 1 : 0;
+                }
+                out_t[pos] = x;
+                if (out_i) out_i[pos] = e;
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---- bitonic sort of P (key, idx) pairs, element e = r * 32 + lane ----
+#pragma unroll
+        for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 32) {
+#pragma unroll
+                    for (int r = 0; r < FI; ++r) {
+                        const int rp = r ^ (j >> 5);
+                        if (rp > r) {
+                            const bool up = (((r * 32) & k) == 0);          // bits >= 5 of e come from r
+                            const bool sw = up ? (key[r] > key[rp]) : (key[r] <= key[rp]);
+                            if (sw) {
+                                const float tk = key[r]; key[r] = key[rp]; key[rp] = tk;
+                                const int ti = idx[r]; idx[r] = idx[rp]; idx[rp] = ti;
+                            }
+                        }
+                    }
+                } else {
+                    const bool lower = (lane & j) == 0;
+#pragma unroll
+                    for (int r = 0; r < FI; ++r) {
+                        const float ok_ = __shfl_xor_sync(0xffffffffu, key[r], j);
+                        const int oi = __shfl_xor_sync(0xffffffffu, idx[r], j);
+                        const bool up = ((((r * 32) + lane) & k) == 0);
+                        const bool le = lower ? (key[r] <= ok_) : (ok_ <= key[r]);   // (lower element <= upper element)
+                        const bool take = up ? !le : le;                               // ascending: swap when lower > upper
+                        if (take) { key[r] = ok_; idx[r] = oi; }
+                    }
+                }
+            }
+        }
+        // sorted fine keys to shared memory for the coarse samples' rank search
+#pragma unroll
+        for (int r = 0; r < FI; ++r) fk[r * 32 + lane] = key[r];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < FI; ++r) {
+            const int e = r * 32 + lane;
+            if (e < nf) {
+                int lo = 0, hi = nc;                                    // #(coarse <= key): upper bound
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ck[mid] <= key[r]) lo = mid + 1; else hi = mid;
+                }
+                out_t[e + lo] = key[r];
+                if (out_i) out_i[e + lo] = idx[r];
+            }
+        }
+        for (int n = lane; n < nc; n += 32) {
+            const float c = ck[n];
+            int lo = 0, hi = nf;                                        // #(fine < c): lower bound
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (fk[mid] < c) lo = mid + 1; else hi = mid;
+            }
+            out_t[n + lo] = c;
+            if (out_i) out_i[n + lo] = n;
+        }
+        __syncwarp();
+    }
+}
+
 extern "C" int nerf_resample_merge(const float* t, const float* weights, const float* u, int64_t batch, int nc, int nf,
                                    float* t_all, int32_t* src_idx, void* stream) {
     NERF_CHECK_ARG(t && weights && u && t_all && batch >= 0 && nc >= 2 && nf >= 1, "bad arguments");
     if (batch == 0) return NERF_OK;
+    int threads = 128;
+    if (nf <= 256 && nc <= 1024) {
+        // fine samples sorted in registers, merged with the (sorted) coarse samples by rank
+        const int fi = nf <= 32 ? 1 : nf <= 64 ? 2 : nf <= 128 ? 4 : 8;
+        size_t smem_fast = (size_t)(threads / 32) * ((2 * nc + 2) + nc + 32 * fi) * sizeof(float);
+        const int grid = stream_grid(batch * 32, threads);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (smem_fast <= 48 * 1024) {
+            if (fi == 1) resample_merge_sorted_kernel<1><<<grid, threads, smem_fast, st>>>(t, weights, u, batch, nc, nf, t_all, src_idx);
+            else if (fi == 2) resample_merge_sorted_kernel<2><<<grid, threads, smem_fast, st>>>(t, weights, u, batch, nc, nf, t_all, src_idx);
+            else if (fi == 4) resample_merge_sorted_kernel<4><<<grid, threads, smem_fast, st>>>(t, weights, u, batch, nc, nf, t_all, src_idx);
+            else resample_merge_sorted_kernel<8><<<grid, threads, smem_fast, st>>>(t, weights, u, batch, nc, nf, t_all, src_idx);
+            NERF_LAUNCHED();
+            return NERF_OK;
+        }
+    }
     int P = 1;
     while (P < nc + nf) P <<= 1;
-    int threads = 128;
     size_t smem = (size_t)(threads / 32) * ((2 * nc + 2) + 2 * P) * sizeof(float);
     NERF_CHECK_ARG(smem <= 96 * 1024, "nc+nf too large");
     if (smem > 48 * 1024)

@@ -174,6 +174,34 @@ def test_sample_pdf_edge_cases(nk):
     assert got.min() >= float(t_mid[0, 0]) - 1e-6 and got.max() <= float(t_mid[0, -1]) + 1e-6
 
 
+@pytest.mark.parametrize("Nc,Nf", [(64, 128), (16, 32), (33, 47), (64, 64), (8, 200), (100, 256), (64, 300)])
+@pytest.mark.parametrize("case", ["sorted", "ties", "unsorted"])
+def test_resample_merge_is_sort_of_concat(nk, Nc, Nf, case):
+    """models.py:165-167: t_all = sort(concat([t, sample_pdf(t_mid, w, Nf)])), plus the source-index permutation the
+    backward pass uses.  Covers the register-sort fast path (Nf <= 256, sorted coarse samples), its rank-counting
+    path for unsorted coarse samples, equal keys, and the shared-memory bitonic fallback (Nf > 256)."""
+    B = 257
+    rng = np.random.default_rng(Nc * 1000 + Nf)
+    t = np.sort(rng.uniform(2.0, 6.0, (B, Nc)).astype(np.float32), axis=1)
+    w = rng.random((B, Nc), dtype=np.float32) ** 4
+    u = rng.random((B, Nf), dtype=np.float32)
+    if case == "ties":
+        t[:, 5] = t[:, 4]                      # equal coarse keys
+        u[:, 1::2] = u[:, 0::2][:, :u[:, 1::2].shape[1]]   # equal draws -> equal fine keys
+        w[: B // 2] = 0.0                      # flat pdf: samples pile up on bin edges
+    if case == "unsorted":
+        t = t[:, ::-1].copy() if Nc % 2 else np.ascontiguousarray(rng.permuted(t, axis=1))
+    tt, ww, uu = torch.from_numpy(t).cuda(), torch.from_numpy(w).cuda(), torch.from_numpy(u).cuda()
+    t_all, src = nk.resample_merge(tt, ww, Nf, u=uu, return_index=True)
+    t_mid = 0.5 * (tt[:, 1:] + tt[:, :-1])
+    fine = nk.sample_pdf(t_mid, ww, Nf, u=uu)
+    cat = torch.cat([tt, fine], dim=1)
+    assert torch.equal(t_all, torch.sort(cat, dim=1).values)
+    s = src.long()
+    assert torch.equal(torch.sort(s, dim=1).values, torch.arange(Nc + Nf, device="cuda").expand(B, -1))   # a permutation
+    assert torch.equal(torch.gather(cat, 1, s), t_all)
+
+
 # ---------------------------------------------------------------- tcgen05 building block
 @pytest.mark.parametrize("mode,N,K", [(0, 128, 64), (0, 128, 256), (0, 256, 128), (1, 128, 16), (1, 128, 128), (1, 256, 128)])
 def test_tcgen05_selftest_gemm(nk, mode, N, K):
