@@ -46,7 +46,7 @@ typedef struct nerf_config {
     int32_t ns_coarse;   /* NS_COARSE         */
     int32_t ns_fine;     /* NS_FINE           */
     int32_t max_rays;    /* largest ray batch any call will pass (workspace is sized for it) */
-    int32_t batch_norm;  /* BATCH_NORM: must be 0 (out of scope this round)    */
+    int32_t batch_norm;  /* BATCH_NORM: must be 0 here; the host mirror folds BN inference into W, b   */
     int32_t training;    /* 1: allocate gradient / Adam / saved-activation storage            */
     float learning_rate; /* LEARNING_RATE (Adam, Keras defaults b1 .9 b2 .999 eps 1e-7)       */
     int32_t stop_grad_samples; /* 1: no gradient through the fine sample positions; 0: reference semantics */

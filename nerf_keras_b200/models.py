@@ -90,7 +90,7 @@ class _Ctx:
     def __init__(self, arch: dict, ns_coarse, ns_fine, max_rays, training, learning_rate, stop_grad_samples=True):
         _dev()
         cfg = _lib.NerfConfig(arch["num_layers"], arch["hidden_dim"], arch["skip_layer"], arch["lxyz"], arch["ldir"],
-                              int(ns_coarse), int(ns_fine), int(max_rays), int(bool(arch["bn"])), int(bool(training)),
+                              int(ns_coarse), int(ns_fine), int(max_rays), 0, int(bool(training)),   # BN is folded on the host
                               float(learning_rate), int(bool(stop_grad_samples)))
         self.cfg = cfg
         self.handle = C.c_void_p()
@@ -137,9 +137,9 @@ class NerfModel:
     Callable like the Keras model: `model([rays_enc, dirs_enc])` -> (..., 4) = [r,g,b,sigma] raw
     (fp32 kernels).  Weights follow the Keras Dense convention y = x @ W + b, W (in, out)."""
 
+    BN_EPS = 1e-3   # keras.layers.BatchNormalization default epsilon (momentum 0.99 is only used in training)
+
     def __init__(self, num_layers, hidden_dim, skip_layer, lxyz, ldir, bn=False):
-        if bn:
-            raise ValueError("BATCH_NORM=true is not supported by the B200 path (DESIGN.md, out of scope)")
         self.arch = dict(num_layers=int(num_layers), hidden_dim=int(hidden_dim), skip_layer=int(skip_layer),
                          lxyz=int(lxyz), ldir=int(ldir), bn=bool(bn))
         self.shapes = layer_shapes(num_layers, hidden_dim, skip_layer, lxyz, ldir)
@@ -152,27 +152,72 @@ class NerfModel:
         self._host_blob = np.concatenate(parts)
         self._owner: Optional[Tuple[_Ctx, int]] = None
         self._own_ctx: Optional[_Ctx] = None
+        # BATCH_NORM=true (models.py:30-33, 49-52): one BatchNormalization after every trunk Dense and after the
+        # direction Dense.  INFERENCE only: the moving statistics are folded into the Dense weights on the host,
+        #   y = ((xW + b) - mean) * gamma / sqrt(var + eps) + beta  =  x (W s) + ((b - mean) s + beta),  s = gamma / sqrt(var + eps)
+        # so the device kernels are unchanged.  Training with batch statistics is not supported.
+        self.bn: Optional[Dict[str, Dict[str, np.ndarray]]] = None
+        if bn:
+            self.bn = {role: {"gamma": np.ones(fo, np.float32), "beta": np.zeros(fo, np.float32),
+                              "mean": np.zeros(fo, np.float32), "var": np.ones(fo, np.float32)}
+                       for role, _, fo in self.shapes if role.startswith("d")}      # d0..d7 and ddir
 
     # -- weights ----------------------------------------------------------------------------------
     def count_params(self) -> int:
         return int(self._host_blob.size)
 
     def get_flat_weights(self) -> np.ndarray:
-        if self._owner is not None:
+        """The Dense kernels and biases (un-folded when BATCH_NORM=true)."""
+        if self._owner is not None and self.bn is None:      # a BN model is never trained here: the host copy is the truth
             ctx, net = self._owner
             self._host_blob = ctx.get_weights(net).cpu().numpy()
         return self._host_blob.copy()
+
+    def device_blob(self) -> np.ndarray:
+        """What the kernels see: the Dense weights, with the BatchNormalization inference affine folded in."""
+        if self.bn is None:
+            return self._host_blob
+        parts, off = [], 0
+        for role, fi, fo in self.shapes:
+            W = self._host_blob[off:off + fi * fo].reshape(fi, fo); off += fi * fo
+            b = self._host_blob[off:off + fo]; off += fo
+            if role in self.bn:
+                st = self.bn[role]
+                sc = (st["gamma"].astype(np.float64) / np.sqrt(st["var"].astype(np.float64) + self.BN_EPS))
+                W = (W.astype(np.float64) * sc[None, :]).astype(np.float32)
+                b = ((b.astype(np.float64) - st["mean"]) * sc + st["beta"]).astype(np.float32)
+            parts += [W.reshape(-1), b]
+        return np.concatenate(parts)
+
+    def _push(self):
+        blob = torch.from_numpy(np.ascontiguousarray(self.device_blob()))
+        if self._owner is not None:
+            ctx, net = self._owner
+            ctx.set_weights(net, blob)
+        if self._own_ctx is not None:
+            self._own_ctx.set_weights(0, blob)
 
     def set_flat_weights(self, blob):
         blob = np.asarray(blob, dtype=np.float32).reshape(-1)
         if blob.size != self._host_blob.size:
             raise ValueError(f"expected {self._host_blob.size} floats, got {blob.size}")
         self._host_blob = blob.copy()
-        if self._owner is not None:
-            ctx, net = self._owner
-            ctx.set_weights(net, torch.from_numpy(self._host_blob))
-        if self._own_ctx is not None:
-            self._own_ctx.set_weights(0, torch.from_numpy(self._host_blob))
+        self._push()
+
+    def get_bn_params(self) -> Optional[Dict[str, Dict[str, np.ndarray]]]:
+        return None if self.bn is None else {r: {k: v.copy() for k, v in st.items()} for r, st in self.bn.items()}
+
+    def set_bn_params(self, params: Dict[str, Dict[str, np.ndarray]]):
+        """role -> {gamma, beta, mean, var} (Keras order: gamma, beta, moving_mean, moving_variance)."""
+        if self.bn is None:
+            raise ValueError("the model was created with bn=False")
+        for role, st in self.bn.items():
+            for k in ("gamma", "beta", "mean", "var"):
+                v = np.asarray(params[role][k], dtype=np.float32)
+                if v.shape != st[k].shape:
+                    raise ValueError(f"bad shape for {role}/{k}")
+                st[k] = v.copy()
+        self._push()
 
     def get_weights(self) -> Dict[str, Dict[str, np.ndarray]]:
         blob, out, off = self.get_flat_weights(), {}, 0
@@ -194,6 +239,8 @@ class NerfModel:
 
     # -- call -------------------------------------------------------------------------------------
     def __call__(self, inputs, training=False):
+        if training and self.bn is not None:
+            raise NotImplementedError("BATCH_NORM=true is inference-only on the B200 path (batch statistics are not computed)")
         rays_enc, dirs_enc = inputs
         x, dd = _f32(rays_enc), _f32(dirs_enc)
         ex, ed = 3 + 6 * self.arch["lxyz"], 3 + 6 * self.arch["ldir"]
@@ -204,7 +251,7 @@ class NerfModel:
         else:
             if self._own_ctx is None:
                 self._own_ctx = _Ctx(self.arch, 2, 1, 1, False, 0.0)
-                self._own_ctx.set_weights(0, torch.from_numpy(self._host_blob))
+                self._own_ctx.set_weights(0, torch.from_numpy(np.ascontiguousarray(self.device_blob())))
             ctx, net = self._own_ctx, 0
         n = x.numel() // ex
         out = torch.empty(x.shape[:-1] + (4,), device=x.device, dtype=torch.float32)
@@ -249,6 +296,10 @@ class NeRFTrainer:
         """models.py:80-86."""
         if not isinstance(optimizer, Adam):
             raise TypeError("optimizer must be nerf_keras_b200.models.Adam")
+        if self.coarse_model.bn is not None or self.fine_model.bn is not None:
+            raise NotImplementedError("training with BATCH_NORM=true is not supported by the B200 path: batch statistics "
+                                      "over all samples of a batch need a layer-by-layer kernel (DESIGN.md); "
+                                      "BN checkpoints can be rendered (inference folds the moving statistics)")
         self.optimizer, self.loss_fn = optimizer, loss_fn
         self._rebuild_ctx()
 
@@ -257,7 +308,9 @@ class NeRFTrainer:
             self._rebuild_ctx()
 
     def _rebuild_ctx(self, max_rays=None):
-        blobs = [self.coarse_model.get_flat_weights(), self.fine_model.get_flat_weights()]
+        for m in (self.coarse_model, self.fine_model):
+            m.get_flat_weights()                              # refresh the host copies from the old ctx
+        blobs = [np.ascontiguousarray(self.coarse_model.device_blob()), np.ascontiguousarray(self.fine_model.device_blob())]
         if self._ctx is not None:
             self._ctx.close()
         training = self.optimizer is not None
@@ -296,6 +349,8 @@ class NeRFTrainer:
         maps_only=True skips the per-sample outputs (their pairs are (None, None)): what a renderer needs."""
         if (l_xyz not in (None, self.l_xyz)) or (l_dir not in (None, self.l_dir)):
             raise ValueError("l_xyz / l_dir differ from the trainer's configuration")
+        if training and (self.coarse_model.bn is not None or self.fine_model.bn is not None):
+            raise NotImplementedError("BATCH_NORM=true is inference-only on the B200 path")
         if self._ctx is None:
             self._rebuild_ctx()
         o, d, t = _f32(ray_origins), _f32(ray_directions), _f32(t_vals)
@@ -435,6 +490,9 @@ class NeRFTrainer:
             for role, wb in m.get_weights().items():
                 data[f"{name}/{role}/W"] = wb["W"]
                 data[f"{name}/{role}/b"] = wb["b"]
+            for role, st in (m.get_bn_params() or {}).items():
+                for k, v in st.items():
+                    data[f"{name}/{role}/bn_{k}"] = v
         np.savez(path, **data)
 
     def load_weights(self, path: str):
@@ -442,3 +500,6 @@ class NeRFTrainer:
         for name, m in (("coarse", self.coarse_model), ("fine", self.fine_model)):
             m.set_weights({role: {"W": data[f"{name}/{role}/W"], "b": data[f"{name}/{role}/b"]}
                            for role, _, _ in m.shapes})
+            if m.bn is not None:
+                m.set_bn_params({role: {k: data[f"{name}/{role}/bn_{k}"] for k in ("gamma", "beta", "mean", "var")}
+                                 for role in m.bn})

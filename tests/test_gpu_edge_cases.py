@@ -5,6 +5,7 @@ import pytest
 import torch
 
 import oracle as O
+from oracle import models_ref as MR
 from tests.util import golden_weights, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -113,8 +114,6 @@ def test_error_behaviour(nk):
         nk.sample_pdf(np.zeros((4, 8), np.float32), np.zeros((4, 8), np.float32), 4)
     with pytest.raises(TypeError):
         nk.NeRFTrainer("not a model", nk.create_nerf_complete_model(8, 256, 4, 10, 4), 8, 4, 8, 10, 4)
-    with pytest.raises(ValueError):
-        nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
     tr = _trainer(nk, wc, wf, 8, 16, 32)
     with pytest.raises(RuntimeError):
         tr.train_step((g["img"][:8], (g["o"][:8], g["d"][:8], g["t"][:8])))       # compile() not called
@@ -145,3 +144,63 @@ def test_weights_roundtrip_and_save_load(nk, tmp_path):
     after = tr2.forward_pass(g["o"], g["d"], g["t"], u_pdf=g["u_pdf"])[0][1]
     assert (before - after).abs().max().item() <= 1e-6
     assert np.abs(tr.coarse_model.get_weights()["d0"]["W"] - wc["d0"]["W"].numpy()).max() > 0
+
+
+def test_batch_norm_checkpoints_render_by_folding(nk, tmp_path):
+    """BATCH_NORM=true (models.py:30-33, 49-52; three of the reference's six configs): inference folds the moving
+    statistics into the Dense weights.  fp32 model call vs the oracle's BN forward <= 2e-4; bf16 render within the
+    north_star bounds of the oracle's; training raises; save/load keeps the BN parameters."""
+    rng = np.random.default_rng(11)
+    wc, wf = O.init_weights(seed=5, bias_range=0.1), O.init_weights(seed=6, bias_range=0.1)
+    bns = []
+    for s in (1, 2):
+        bn = MR.init_bn()
+        for st in bn.values():
+            n = st["gamma"].numel()
+            st["gamma"] = torch.from_numpy(rng.uniform(0.5, 1.5, n).astype(np.float32))
+            st["beta"] = torch.from_numpy(rng.uniform(-0.2, 0.2, n).astype(np.float32))
+            st["mean"] = torch.from_numpy(rng.uniform(-0.3, 0.3, n).astype(np.float32))
+            st["var"] = torch.from_numpy(rng.uniform(0.2, 2.0, n).astype(np.float32))
+        bns.append(bn)
+    to_np = lambda bn: {r: {k: v.numpy() for k, v in st.items()} for r, st in bn.items()}
+    mc = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+    mf = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+    mc.set_flat_weights(O.flatten_weights(wc)); mf.set_flat_weights(O.flatten_weights(wf))
+    mc.set_bn_params(to_np(bns[0])); mf.set_bn_params(to_np(bns[1]))
+    # the Keras-style model call (fp32 kernels) against the oracle's BN forward, inference mode
+    x = torch.from_numpy(rng.uniform(-1, 1, (300, 63)).astype(np.float32))
+    dd = torch.from_numpy(rng.uniform(-1, 1, (300, 27)).astype(np.float32))
+    ref = O.nerf_mlp(wc, x, dd, bn=bns[0], training=False)
+    got = mc([x.cuda(), dd.cuda()])
+    assert np.abs(got.cpu().numpy() - ref.numpy()).max() <= 2e-4
+    with pytest.raises(NotImplementedError):
+        mc([x.cuda(), dd.cuda()], training=True)
+    # trainer: render on the tcgen05 path vs the oracle's forward pass with the same BN parameters
+    B, Nc, Nf = 200, 32, 64
+    o, d = O.get_rays(20, 20, 25.0, torch.from_numpy(np.asarray(O.pose_spherical(30.0, -30.0, 4.0))))
+    o, d = o.reshape(-1, 3)[:B], d.reshape(-1, 3)[:B]
+    t = O.generate_t_vals(2.0, 6.0, B, Nc, False)
+    u = torch.from_numpy(rng.random((B, Nf), dtype=np.float32))
+    rgbs, depths, ws, preds = O.forward_pass(wc, wf, o, d, t, 10, 4, Nf, u, bn_coarse=bns[0], bn_fine=bns[1])[:4]
+    tr = nk.NeRFTrainer(mc, mf, B, Nc, Nf, 10, 4)
+    tr.build()
+    got = tr.forward_pass(o.cuda(), d.cuda(), t.cuda(), u_pdf=u.cuda())
+    assert np.abs(got[3][0].cpu().numpy() - preds[0].numpy()).max() <= 5e-2       # coarse raw predictions, bf16 MLP
+    stable = np.abs(preds[0].numpy()[:, -1, 3]) > 0.06
+    assert stable.mean() > 0.5
+    assert np.abs(got[0][0].cpu().numpy() - rgbs[0].numpy())[stable].max() <= 2e-3
+    with pytest.raises(NotImplementedError):
+        tr.compile(nk.Adam(5e-4), nk.MeanSquaredError())
+    with pytest.raises(NotImplementedError):
+        tr.forward_pass(o.cuda(), d.cuda(), t.cuda(), u_pdf=u.cuda(), training=True)
+    # weights + BN parameters survive save / load
+    path = str(tmp_path / "bn.npz")
+    tr.save_weights(path)
+    m2c = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+    m2f = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+    tr2 = nk.NeRFTrainer(m2c, m2f, B, Nc, Nf, 10, 4)
+    tr2.build()
+    tr2.load_weights(path)
+    again = tr2.forward_pass(o.cuda(), d.cuda(), t.cuda(), u_pdf=u.cuda())
+    assert torch.equal(again[0][1], got[0][1])
+    np.testing.assert_array_equal(m2f.get_bn_params()["ddir"]["var"], bns[1]["ddir"]["var"].numpy())

@@ -40,10 +40,22 @@ def expected_shapes(conf):
     return roles, shapes
 
 
-def dense_layers_in_creation_order(model):
-    dense = [l for l in model.layers if l.__class__.__name__ == "Dense"]
+def layers_in_creation_order(model, cls="Dense"):
+    found = [l for l in model.layers if l.__class__.__name__ == cls]
     suffix = lambda l: int(m.group(1)) if (m := re.search(r"_(\d+)$", l.name)) else 0
-    return sorted(dense, key=suffix)
+    return sorted(found, key=suffix)
+
+
+def dense_layers_in_creation_order(model):
+    return layers_in_creation_order(model, "Dense")
+
+
+def bn_roles(conf):
+    """BATCH_NORM=true: one BatchNormalization after every trunk Dense and after the direction Dense (models.py:30-33,49-52)."""
+    return ["d%d" % i for i in range(conf["NUM_LAYERS"])] + ["ddir"]
+
+
+BN_KEYS = ("gamma", "beta", "mean", "var")          # Keras weight order: gamma, beta, moving_mean, moving_variance
 
 
 def build_trainer(conf):
@@ -64,8 +76,7 @@ def main():
     ap.add_argument("--npz", required=True)
     args = ap.parse_args()
     conf = json.load(open(args.config))
-    if conf.get("BATCH_NORM", False):
-        raise SystemExit("BatchNorm checkpoints are not supported by the B200 path (DESIGN.md, known divergences)")
+    use_bn = bool(conf.get("BATCH_NORM", False))     # the B200 path renders BN checkpoints (folded), it does not train them
     roles, shapes = expected_shapes(conf)
     trainer = build_trainer(conf)
     nets = (("coarse", trainer.coarse_model), ("fine", trainer.fine_model))
@@ -79,6 +90,12 @@ def main():
                 W, b = layer.get_weights()
                 assert W.shape == shape, (name, role, W.shape, shape)
                 out[f"{name}/{role}/W"], out[f"{name}/{role}/b"] = W.astype(np.float32), b.astype(np.float32)
+            if use_bn:
+                bns = layers_in_creation_order(model, "BatchNormalization")
+                assert len(bns) == len(bn_roles(conf)), (name, len(bns))
+                for role, layer in zip(bn_roles(conf), bns):
+                    for key, arr in zip(BN_KEYS, layer.get_weights()):
+                        out[f"{name}/{role}/bn_{key}"] = arr.astype(np.float32)
         np.savez(args.npz, **out)
         print("wrote", args.npz, "with", len(out), "arrays")
     else:
@@ -88,6 +105,9 @@ def main():
                 W, b = data[f"{name}/{role}/W"], data[f"{name}/{role}/b"]
                 assert W.shape == shape, (name, role, W.shape, shape)
                 layer.set_weights([W, b])
+            if use_bn:
+                for role, layer in zip(bn_roles(conf), layers_in_creation_order(model, "BatchNormalization")):
+                    layer.set_weights([data[f"{name}/{role}/bn_{key}"] for key in BN_KEYS])
         trainer.save_weights(args.h5)
         print("wrote", args.h5)
 
