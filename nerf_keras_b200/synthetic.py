@@ -90,3 +90,51 @@ class BatchedRayDataset:
             idx = idx[self.rank * self.local:(self.rank + 1) * self.local]
             t = self.t_row.expand(idx.shape[0], -1).contiguous()
             yield self.img[idx], (self.o[idx], self.d[idx], t)
+
+
+class HostPrefetcher:
+    """Feeds batches that live in (pinned) host memory to the device with the copy of batch i+1 overlapped with the work
+    on batch i: a second CUDA stream and two device staging slots.  `host_batches` is any iterable of tuples of CPU
+    tensors (pin them for truly asynchronous copies); the iterator yields tuples of device tensors that stay valid
+    until the next-but-one `next()`.  This is what replaces tf.data's prefetch (data_utils.py:166-167) when the ray set
+    does not fit in HBM."""
+
+    def __init__(self, host_batches, device=None):
+        self.src = host_batches
+        self.device = torch.device(device) if device is not None else du._dev()
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def __iter__(self):
+        it = iter(self.src)
+        slots, ready, free = [None, None], [None, None], [None, None]
+        compute = torch.cuda.current_stream(self.device)
+
+        def enqueue(k, batch):
+            if slots[k] is None or any(a.shape != b.shape or a.dtype != b.dtype for a, b in zip(slots[k], batch)):
+                slots[k] = tuple(torch.empty(b.shape, dtype=b.dtype, device=self.device) for b in batch)
+            if free[k] is not None:
+                self.stream.wait_event(free[k])          # the consumer is done with this slot
+            with torch.cuda.stream(self.stream):
+                for dst, b in zip(slots[k], batch):
+                    dst.copy_(b, non_blocking=True)
+                ready[k] = torch.cuda.Event()
+                ready[k].record(self.stream)
+
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        enqueue(0, nxt)
+        k = 0
+        while True:
+            cur = k
+            nxt = next(it, None)
+            if nxt is not None:
+                # slot 1-k was handed out one iteration ago; everything enqueued on the compute stream so far used it
+                free[1 - k] = torch.cuda.Event()
+                free[1 - k].record(compute)
+                enqueue(1 - k, nxt)
+            compute.wait_event(ready[cur])
+            yield slots[cur]
+            if nxt is None:
+                return
+            k = 1 - k

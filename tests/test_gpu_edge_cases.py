@@ -204,3 +204,32 @@ def test_batch_norm_checkpoints_render_by_folding(nk, tmp_path):
     again = tr2.forward_pass(o.cuda(), d.cuda(), t.cuda(), u_pdf=u.cuda())
     assert torch.equal(again[0][1], got[0][1])
     np.testing.assert_array_equal(m2f.get_bn_params()["ddir"]["var"], bns[1]["ddir"]["var"].numpy())
+
+
+def test_host_prefetcher_delivers_batches_in_order(nk):
+    """`HostPrefetcher`: pinned-host batches copied on a side stream one step ahead; values, order, slot reuse."""
+    from nerf_keras_b200.synthetic import HostPrefetcher
+    rng = np.random.default_rng(0)
+    host = [tuple(torch.from_numpy(rng.random(shape, dtype=np.float32)).pin_memory() for shape in ((64, 3), (64, 7)))
+            for _ in range(7)]
+    seen = []
+    acc = torch.zeros((), device="cuda")
+    for a, b in HostPrefetcher(host):
+        assert a.is_cuda and b.shape == (64, 7)
+        acc = acc + a.sum() * 1e-3            # some work on the compute stream that reads the slot
+        seen.append((a.clone(), b.clone()))
+    assert len(seen) == 7
+    for (a, b), (ha, hb) in zip(seen, host):
+        assert torch.equal(a.cpu(), ha) and torch.equal(b.cpu(), hb)
+    assert list(HostPrefetcher([])) == []
+    # feeds train_step like any other batch source
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    tr = _trainer(nk, wc, wf, 32, int(g["Nc"]), int(g["Nf"]), compile_=True)
+    assert g["o"].shape[0] >= 96
+    hb = [tuple(torch.from_numpy(np.ascontiguousarray(g[k][i * 32:(i + 1) * 32])).pin_memory() for k in ("img", "o", "d", "t", "u_pdf"))
+          for i in range(3)]
+    losses = []
+    for img, o, d, t, u in HostPrefetcher(hb):
+        losses.append(float(tr.train_step((img, (o, d, t)), u_pdf=u)["loss"]))
+    assert len(losses) == 3 and all(np.isfinite(losses))
