@@ -170,6 +170,20 @@ def resample_merge(t_vals, weights, ns_fine, u=None, return_index=False):
     return (out, idx) if return_index else out
 
 
+def create_batched_dataset_pipeline(images_s, ray_oris_s, ray_dirs_s, num_samples, batch_size, auto=None, near=2.0, far=6.0,
+                                    shuffle=True, rand_sampling=True):
+    """data_utils.py:140-170 without tf.data: an iterable of (images, (ray_origins, ray_directions, t_vals)) batches.
+    Same arguments (`auto`, tf.data.AUTOTUNE in the reference, is ignored); every ray once per epoch, drop_remainder, a
+    local shuffle equivalent to the 5 * batch_size shuffle buffer, ONE jitter vector shared by all rays (the reference
+    materialises the (n_rays, num_samples) t-value array; here each batch expands the shared row).  The data stays on
+    the device; see synthetic.HostPrefetcher for host-resident ray sets."""
+    from .synthetic import BatchedRayDataset
+    dev = _dev()
+    to_dev = lambda x: _f32(x).reshape(-1, x.shape[-1]).to(dev).contiguous()
+    return BatchedRayDataset(to_dev(images_s), to_dev(ray_oris_s), to_dev(ray_dirs_s), num_samples, batch_size, near, far,
+                             shuffle=shuffle, rand_sampling=rand_sampling, order="windowed")
+
+
 # ---- host 4x4 camera helpers (data_utils.py:225-267); negligible work, stays on the host ----
 def get_translation_t(t):
     return np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, t], [0, 0, 0, 1]], dtype=np.float32)

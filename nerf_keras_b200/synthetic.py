@@ -66,7 +66,11 @@ class BatchedRayDataset:
     (images, (ray_origins, ray_directions, t_vals)).  rank/world shard each global batch for data parallelism."""
 
     def __init__(self, images_s, ray_oris_s, ray_dirs_s, num_samples, batch_size, near=2.0, far=6.0, shuffle=True,
-                 rand_sampling=True, steps_per_epoch=None, rank=0, world=1, seed=0):
+                 rand_sampling=True, steps_per_epoch=None, rank=0, world=1, seed=0, order="random"):
+        # order="random": uniformly random rays (with replacement) per batch.  order="windowed": the reference's epoch
+        # semantics -- every ray exactly once per epoch, drop_remainder, shuffled like tf.data's shuffle buffer of
+        # 5 * batch_size elements (data_utils.py:162-164), i.e. a LOCAL shuffle: sort by (position + window * u).
+        self.order = order
         self.img, self.o, self.d = images_s, ray_oris_s, ray_dirs_s
         self.n = self.o.shape[0]
         self.batch = int(batch_size)
@@ -82,8 +86,16 @@ class BatchedRayDataset:
         return self.steps
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]]:
+        perm = None
+        if self.order == "windowed" and self.shuffle:
+            window = float(5 * self.batch if self.batch else 1024)
+            keys = torch.arange(self.n, device=self.o.device, dtype=torch.float32) + \
+                window * torch.rand(self.n, device=self.o.device, generator=self.gen)
+            perm = torch.argsort(keys)
         for s in range(self.steps):
-            if self.shuffle:
+            if perm is not None:
+                idx = perm[s * self.batch:(s + 1) * self.batch]
+            elif self.shuffle:
                 idx = torch.randint(0, self.n, (self.batch,), device=self.o.device, generator=self.gen)
             else:
                 idx = (torch.arange(self.batch, device=self.o.device) + s * self.batch) % self.n

@@ -233,3 +233,28 @@ def test_host_prefetcher_delivers_batches_in_order(nk):
     for img, o, d, t, u in HostPrefetcher(hb):
         losses.append(float(tr.train_step((img, (o, d, t)), u_pdf=u)["loss"]))
     assert len(losses) == 3 and all(np.isfinite(losses))
+
+
+def test_create_batched_dataset_pipeline_epoch_semantics(nk):
+    """data_utils.py:140-170: every ray once per epoch (drop_remainder), locally shuffled, one shared jitter vector."""
+    n, B, N = 10_000, 512, 16
+    img = np.arange(n * 3, dtype=np.float32).reshape(n, 3)
+    o = np.stack([np.arange(n, dtype=np.float32)] * 3, 1)
+    d = np.ones((n, 3), np.float32)
+    ds = nk.create_batched_dataset_pipeline(img, o, d, N, B, None, near=2.0, far=6.0, shuffle=True, rand_sampling=True)
+    assert len(ds) == n // B
+    ids, first_t = [], None
+    for images, (ro, rd, t) in ds:
+        assert images.shape == (B, 3) and ro.shape == (B, 3) and t.shape == (B, N)
+        assert torch.equal(images[:, 0], ro[:, 0] * 3)                  # pixels travel with their rays
+        first_t = t[0] if first_t is None else first_t
+        assert torch.equal(t, first_t.expand(B, N))                      # Q1: one jitter vector for the whole dataset
+        ids.append(ro[:, 0].long())
+    ids = torch.cat(ids).cpu().numpy()
+    assert len(np.unique(ids)) == len(ids) == (n // B) * B               # no ray twice
+    pos = np.arange(len(ids))
+    assert np.abs(ids - pos).max() <= 5 * B + B and np.abs(ids - pos).mean() > B / 4   # a local shuffle, not sequential
+    seq = nk.create_batched_dataset_pipeline(img, o, d, N, B, None, shuffle=False, rand_sampling=False)
+    first = next(iter(seq))
+    assert torch.equal(first[1][0][:, 0].cpu(), torch.arange(B, dtype=torch.float32))
+    assert torch.equal(first[1][2][0].cpu(), O.generate_t_vals(2.0, 6.0, 1, N, False)[0])
