@@ -389,6 +389,24 @@ def main():
                     "avg_launch_ms": avg_ms, "launches": k_n.value,
                     "share_of_step": k_ms.value / total_ms}
 
+    # the other two tensor kernels of a training step (same live CUDA-event timers), for the record:
+    #   weight gradient: HBM-bound, reads every saved activation + dZ image once = 1 294 336 B per 128-sample tile
+    #   dX chain: tensor-bound, 557 056 MAC per sample (dZ.W^T of ddir[:256], feature and layers 7..1; heads on CUDA cores)
+    if args.mode == "train" and "wgrad" in kernel_ms:
+        tiles = -(-B * Nc // 128) + -(-B * (Nc + Nf) // 128)
+        wg_bytes = tiles * (655360 + 638976)
+        extra["roofline_wgrad"] = {"bound": "hbm", "kernel": "nerf_wgrad_tc_kernel", "unit": "GB/s", "peak": peaks["hbm"],
+                                   "achieved": wg_bytes / (kernel_ms["wgrad"] * 1e-3) / 1e9,
+                                   "frac": wg_bytes / (kernel_ms["wgrad"] * 1e-3) / 1e9 / peaks["hbm"],
+                                   "traffic": 12.019e9 / 2, "traffic_unit": "bytes/launch (ncu, profiles/r1_*)",
+                                   "share_of_step": kernel_ms["wgrad"] / ms_per_step}
+        chain_flop = samples_per_step * 2 * (256 * 128 + 8 * 256 * 256)
+        extra["roofline_chain"] = {"bound": "tensor", "kernel": "nerf_mlp_bwd_tc_kernel", "unit": "TFLOP/s",
+                                   "peak": peaks["tensor_sustained"],
+                                   "achieved": chain_flop / (kernel_ms["mlp_bwd_chain"] * 1e-3) / 1e12,
+                                   "frac": chain_flop / (kernel_ms["mlp_bwd_chain"] * 1e-3) / 1e12 / peaks["tensor_sustained"],
+                                   "share_of_step": kernel_ms["mlp_bwd_chain"] / ms_per_step}
+
     line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
