@@ -102,7 +102,7 @@ def test_volume_render_golden(nk, name):
     np.testing.assert_allclose(w.cpu().numpy(), g["wt_f"], atol=1e-5)
 
 
-@pytest.mark.parametrize("B,N", [(4096, 64), (513, 192), (9, 16), (3, 48), (2, 1), (5, 33)])
+@pytest.mark.parametrize("B,N", [(4096, 64), (513, 192), (9, 16), (3, 48), (2, 1), (5, 33), (7, 256), (6, 257), (5, 512)])
 def test_volume_render_random_and_edge_cases(nk, B, N):
     gen = torch.Generator().manual_seed(B * 1000 + N)
     preds = torch.randn(B, N, 4, generator=gen) * 3.0
@@ -118,9 +118,17 @@ def test_volume_render_random_and_edge_cases(nk, B, N):
     assert float(w.sum(-1).max()) <= 1.0 + 1e-5
 
 
+def test_volume_render_maximum_sample_count(nk):
+    """512 samples per ray is the compositing kernels' limit (whole ray in registers); beyond it they refuse loudly."""
+    preds = torch.zeros(2, 513, 4)
+    t = O.generate_t_vals(2.0, 6.0, 2, 513, False)
+    with pytest.raises(ValueError):
+        nk.volume_render(preds, t)
+
+
 def test_volume_render_backward_matches_autograd(nk):
     from nerf_keras_b200 import _lib
-    for B, N in [(257, 64), (31, 192), (5, 16)]:
+    for B, N in [(257, 64), (31, 192), (5, 16), (3, 512), (4, 300)]:
         gen = torch.Generator().manual_seed(N)
         preds = (torch.randn(B, N, 4, generator=gen) * 2.0).requires_grad_(True)
         t = O.generate_t_vals(2.0, 6.0, B, N, False) + torch.rand(B, 1, generator=gen) * 0.01
