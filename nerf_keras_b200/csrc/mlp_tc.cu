@@ -165,6 +165,7 @@ __device__ __forceinline__ uint32_t signs_to_mask(uint32_t neg) { return ~__brev
 // forward of both nets per 4096-ray step: bulk stores 1.85 ms, 256-bit register stores 2.06 ms, 128-bit register
 // stores 2.44 ms -- the LSU path loses to the TMA engine even though it spares the shared-memory reads.
 constexpr bool kDirectSave = false;
+constexpr bool kSplitImageStore = true;   // bulk-store K-blocks 0,1 as soon as they are written (two 32 KB stores per phase)
 __device__ __forceinline__ void st_global_v4(uint64_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -517,6 +518,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     tc_fence_before();
                     fence_async();
                     arrive(bar_lo);                                    // next phase may start on K-blocks 0,1
+                    if (SAVE && !kDirectSave && kSplitImageStore) {
+                        // first half of the image (K-blocks 0,1) leaves now, under the second half of the epilogue
+                        named_bar_sync(1 + s, TILE_M);
+                        if (elected) {
+                            int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
+                            bulk_s2g(save_tile + off, act_base, 32768);
+                            bulk_commit();
+                        }
+                    }
                     if (ph == 8) trunk_part2<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
                     else if (relu) trunk_part2<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
                     else trunk_part2<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
@@ -537,7 +547,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                             named_bar_sync(1 + s, TILE_M);
                             if (elected) {
                                 int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
-                                bulk_s2g(save_tile + off, act_base, 65536);
+                                if (kSplitImageStore) bulk_s2g(save_tile + off + 32768, act_base + 32768, 32768);
+                                else bulk_s2g(save_tile + off, act_base, 65536);
                                 bulk_commit();
                             }
                         }
