@@ -399,6 +399,8 @@ def main():
                                    "achieved": wg_bytes / (kernel_ms["wgrad"] * 1e-3) / 1e9,
                                    "frac": wg_bytes / (kernel_ms["wgrad"] * 1e-3) / 1e9 / peaks["hbm"],
                                    "traffic": 12.019e9 / 2, "traffic_unit": "bytes/launch (ncu, profiles/r1_*)",
+                                   "peak_source": peaks["source"] + " (HBM copy)",
+                                   "avg_launch_ms": kernel_ms["wgrad"] / 2, "launches": 2 * args.steps,
                                    "share_of_step": kernel_ms["wgrad"] / ms_per_step}
         chain_flop = samples_per_step * 2 * (256 * 128 + 8 * 256 * 256)
         extra["roofline_chain"] = {"bound": "tensor", "kernel": "nerf_mlp_bwd_tc_kernel", "unit": "TFLOP/s",
@@ -406,6 +408,14 @@ def main():
                                    "achieved": chain_flop / (kernel_ms["mlp_bwd_chain"] * 1e-3) / 1e12,
                                    "frac": chain_flop / (kernel_ms["mlp_bwd_chain"] * 1e-3) / 1e12 / peaks["tensor_sustained"],
                                    "share_of_step": kernel_ms["mlp_bwd_chain"] / ms_per_step}
+
+    # `roofline` is the kernel with the largest share of the step; the others keep their own keys
+    if roofline is not None and "roofline_wgrad" in extra:
+        cands = {"roofline_fwd": roofline, "roofline_wgrad": extra["roofline_wgrad"], "roofline_chain": extra["roofline_chain"]}
+        top = max(cands, key=lambda k: cands[k]["share_of_step"])
+        extra.pop("roofline_wgrad"); extra.pop("roofline_chain")
+        roofline = cands.pop(top)
+        extra.update(cands)
 
     line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -288,12 +288,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
 // ------------------------------------------------------------------------------------------------
 // 2. weight gradients: dW[k_in][n_out] = sum over samples  X[m][k_in] * dZ[m][n_out]
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_THREADS = 192;            // 4 worker warps + loader warp + MMA warp
+constexpr int WG_THREADS = 320;            // warps 0-3: side jobs + final reduction, 4: loader, 5: MMA issuer, 6-9: side jobs
+constexpr int WG_SIDE_WARPS = 8;
 constexpr int WG_STAGES = 3;
 constexpr int WG_SLOT = 65536;             // A half-blocks (4 x 8 KB) + B half-blocks (4 x 8 KB)
 constexpr int WG_SM_BAR = WG_STAGES * WG_SLOT;
 constexpr int WG_SMEM = WG_SM_BAR + 128 + 1024;
-constexpr int WG_NJOBS = 14;
+constexpr int WG_NJOBS = 13;
 
 struct WgJob {
     int64_t a_off;       // byte offset of the X image inside a saved-activation tile
@@ -305,10 +306,12 @@ struct WgJob {
     int rows;            // valid rows of dW produced by this job
     int col_lo, col_hi;  // valid columns [col_lo, col_hi) of the accumulator that are written to dW
     int64_t bias_dst;    // float offset of the bias gradient (column sums of dZ), or -1
+    int64_t sig_dst;     // float offset of dW_sigma (256,1): column sums of the X image weighted by d sigma per sample, or -1
 };
 struct WgParams {
     int debug;              // bit0: skip side jobs, bit1: skip MMAs, bit2: skip final reduction (timing experiments)
     WgJob jobs[WG_NJOBS];
+    int cta_first[WG_NJOBS + 1];   // 1-D grid: job j owns CTAs [cta_first[j], cta_first[j+1]) and splits its samples among them
     const uint8_t* act_save;
     const uint8_t* dz_save;
     const float4* dpreds;
@@ -327,14 +330,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw_addr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const WgJob& J = P.jobs[blockIdx.y];
+    int job_id = 0;
+    while (job_id + 1 < WG_NJOBS && (int)blockIdx.x >= P.cta_first[job_id + 1]) ++job_id;
+    const WgJob& J = P.jobs[job_id];
+    const int job_ctas = P.cta_first[job_id + 1] - P.cta_first[job_id], job_cta = (int)blockIdx.x - P.cta_first[job_id];
     const uint32_t bar_full = base + WG_SM_BAR, bar_empty = bar_full + 8 * WG_STAGES, bar_done = bar_empty + 8 * WG_STAGES;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_SM_BAR + 8 * (2 * WG_STAGES + 1));
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < WG_STAGES; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1 + 128);   // tcgen05.commit + the 128 side-job threads
+            mbar_init(bar_empty + 8 * i, 1 + 32 * WG_SIDE_WARPS);   // tcgen05.commit + the side-job threads
         }
         mbar_init(bar_done, 1);
         fence_barrier_init();
@@ -346,8 +352,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     const uint32_t tmem_base = *tmem_slot;
 
     // this CTA's slab of half-tiles (64 samples each)
-    const int64_t per = (P.n_half_tiles + gridDim.x - 1) / gridDim.x;
-    const int64_t ht0 = (int64_t)blockIdx.x * per;
+    const int64_t per = (P.n_half_tiles + job_ctas - 1) / job_ctas;
+    const int64_t ht0 = (int64_t)job_cta * per;
     const int64_t ht1 = (ht0 + per < P.n_half_tiles) ? ht0 + per : P.n_half_tiles;
     const int n_ht = (ht1 > ht0) ? (int)(ht1 - ht0) : 0;
     const int n_a_load = (J.n_a == 1) ? 2 : J.n_a;   // a single 64-feature block is loaded twice (M = 128 MMA)
@@ -399,28 +405,40 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
         }
     } else {
         // ===================== side jobs + final reduction =====================
+        // Eight side warps (one single warp per scheduler is latency-bound: a dependent-issue chain of ~1.1 K instructions
+        // per half-tile made the job's CTAs the stragglers); side warp sw takes rows [8 sw, 8 sw + 8) of each 64-sample
+        // half-tile, lane <-> (64-column block, 16-byte chunk) = 8 columns.
+        const int sw = (warp < 4) ? warp : warp - 2;
+        const int cb = lane >> 3, ch = lane & 7;
         float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias: partial column sums (8 columns per lane)
+        float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sigma head: column sums of X weighted by d sigma
+        auto accum = [&](uint32_t img, float wgt, float (&acc)[8], int rr) {
+            const uint32_t addr = img + cb * 8192 + sw * 1024 + rr * 128 + ((ch ^ rr) << 4);
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
+            acc[0] = fmaf(wgt, __uint_as_float(w0 << 16), acc[0]); acc[1] = fmaf(wgt, __uint_as_float(w0 & 0xFFFF0000u), acc[1]);
+            acc[2] = fmaf(wgt, __uint_as_float(w1 << 16), acc[2]); acc[3] = fmaf(wgt, __uint_as_float(w1 & 0xFFFF0000u), acc[3]);
+            acc[4] = fmaf(wgt, __uint_as_float(w2 << 16), acc[4]); acc[5] = fmaf(wgt, __uint_as_float(w2 & 0xFFFF0000u), acc[5]);
+            acc[6] = fmaf(wgt, __uint_as_float(w3 << 16), acc[6]); acc[7] = fmaf(wgt, __uint_as_float(w3 & 0xFFFF0000u), acc[7]);
+        };
         int slot = 0;
         uint32_t par = 0;
         for (int i = 0; i < n_ht; ++i) {
+            // d sigma of this warp's 8 samples: one load per lane, issued before the wait so that its latency is hidden
+            float my_ds = 0.f;
+            if (J.sig_dst >= 0 && lane < 8) my_ds = __ldg(&P.dpreds[(ht0 + i) * 64 + sw * 8 + lane].w);
             mbar_wait(bar_full + 8 * slot, par, 13);
-            const uint32_t b0 = base + slot * WG_SLOT + 32768;
-            if (J.bias_dst >= 0 && !(P.debug & (1 | 8))) {
-                // column sums of the dZ half-tile: lane <-> (64-col block, 16-byte chunk), each warp takes 16 rows
-                const int cb = lane >> 3, ch = lane & 7;
-                if (cb < J.n_b) {
-#pragma unroll 4
-                    for (int rr = 0; rr < 16; ++rr) {
-                        const int r = warp * 16 + rr;
-                        const uint32_t addr = b0 + cb * 8192 + (r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4);
-                        uint32_t w0, w1, w2, w3;
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
-                        cs[0] += __uint_as_float(w0 << 16); cs[1] += __uint_as_float(w0 & 0xFFFF0000u);
-                        cs[2] += __uint_as_float(w1 << 16); cs[3] += __uint_as_float(w1 & 0xFFFF0000u);
-                        cs[4] += __uint_as_float(w2 << 16); cs[5] += __uint_as_float(w2 & 0xFFFF0000u);
-                        cs[6] += __uint_as_float(w3 << 16); cs[7] += __uint_as_float(w3 & 0xFFFF0000u);
-                    }
-                }
+            const uint32_t a0 = base + slot * WG_SLOT, b0 = a0 + 32768;
+            if (J.sig_dst >= 0 && !(P.debug & (1 | 8))) {
+                // dW_sigma[f] += sum over the half-tile's samples of h8[sample][f] * d sigma[sample]  (models.py:42): the
+                // X image of this job IS h8, so the sigma head costs no extra HBM traffic (it used to be a job of its own)
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) accum(a0, __shfl_sync(0xffffffffu, my_ds, rr), sg, rr);
+            }
+            if (J.bias_dst >= 0 && !(P.debug & (1 | 8)) && cb < J.n_b) {
+                // bias gradient: column sums of the dZ half-tile
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) accum(b0, 1.0f, cs, rr);
             }
             mbar_arrive(bar_empty + 8 * slot);
             if (++slot == WG_STAGES) { slot = 0; par ^= 1; }
@@ -430,7 +448,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
 #pragma unroll
                 for (int q = 0; q < 8; ++q) atomicAdd(P.grads + J.bias_dst + (lane >> 3) * 64 + (lane & 7) * 8 + q, cs[q]);
             }
-            if (n_mh > 0 && !(P.debug & 4)) {
+            if (J.sig_dst >= 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) atomicAdd(P.grads + J.sig_dst + (lane >> 3) * 64 + (lane & 7) * 8 + q, sg[q]);
+            }
+            if (n_mh > 0 && !(P.debug & 4) && warp < 4) {     // TMEM lane quarters belong to warps 0-3
                 mbar_wait(bar_done, 0, 14);
                 tc_fence_after();
                 const int N = 64 * J.n_b;
@@ -837,8 +859,8 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     W.n_half_tiles = n_pairs * 4;
     W.grads = grads;
     auto job = [&](int i, int64_t a_off, int n_a, int64_t b_off, int n_b, int64_t w_dst, int ld, int rows, int col_lo,
-                   int col_hi, int64_t bias) {
-        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, col_lo, col_hi, bias};
+                   int col_hi, int64_t bias, int64_t sig = -1) {
+        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, col_lo, col_hi, bias, sig};
     };
     job(0, SAVE_ENC, 1, DZ_Z, 4, off.w[0], H, ENC_X, 0, H, off.b[0]);
     for (int l = 1; l <= 4; ++l)
@@ -847,14 +869,13 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     job(6, SAVE_ENC, 1, DZ_Z + 65536 * 5, 4, off.w[5] + (int64_t)H * H, H, ENC_X, 0, H, -1);
     job(7, SAVE_H + 65536 * 5, 4, DZ_Z + 65536 * 6, 4, off.w[6], H, H, 0, H, off.b[6]);
     job(8, SAVE_H + 65536 * 6, 4, DZ_Z + 65536 * 7, 4, off.w[7], H, H, 0, H, off.b[7]);
-    job(9, SAVE_H + 65536 * 7, 4, DZ_FEAT, 4, off.w[9], H, H, 0, H, off.b[9]);
+    // feature layer; its X image is h8, so the same job also produces dW_sigma = h8^T d sigma as a side job
+    job(9, SAVE_H + 65536 * 7, 4, DZ_FEAT, 4, off.w[9], H, H, 0, H, off.b[9], off.w[8]);
     job(10, SAVE_FEAT, 4, DZ_DDIR, 2, off.w[10], H / 2, H, 0, H / 2, off.b[10]);
-    // sigma head: h8^T [.., d sigma] -> column 3 of the accumulator is dW_sigma (256,1)
-    job(11, SAVE_H + 65536 * 7, 4, DZ_HEAD, 1, off.w[8] - 3, 1, H, 3, 4, -1);
     // rgb head: hd^T [d rgb, ..] -> columns 0..2 are dW_rgb (128,3)
-    job(12, SAVE_HD, 2, DZ_HEAD, 1, off.w[11], 3, H / 2, 0, 3, -1);
+    job(11, SAVE_HD, 2, DZ_HEAD, 1, off.w[11], 3, H / 2, 0, 3, -1);
     // direction rows of Wddir: dirimg^T dZ_ddir -> rows 256..282 of dW_ddir
-    job(13, SAVE_DIR, 1, DZ_DDIR, 2, off.w[10] + (int64_t)H * (H / 2), H / 2, ENC_D, 0, H / 2, -1);
+    job(12, SAVE_DIR, 1, DZ_DDIR, 2, off.w[10] + (int64_t)H * (H / 2), H / 2, ENC_D, 0, H / 2, -1);
     head_bias_kernel<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4*>(d_preds), M, grads + off.b[11],
                                                 grads + off.b[8]);
     NERF_LAUNCHED();
@@ -863,8 +884,13 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     int slabs = num_sms() / WG_NJOBS;
     if (slabs < 1) slabs = 1;
     if (slabs > W.n_half_tiles) slabs = (int)W.n_half_tiles;
+    // CTAs per job: equal shares, the spare SMs go to the feature job (its side warps also compute the sigma head)
+    int spare = num_sms() - slabs * WG_NJOBS;
+    if (slabs >= W.n_half_tiles) spare = 0;
+    W.cta_first[0] = 0;
+    for (int j = 0; j < WG_NJOBS; ++j) W.cta_first[j + 1] = W.cta_first[j] + slabs + ((j == 9 && spare > 0) ? spare : 0);
     timing_begin(2, st);
-    nerf_wgrad_tc_kernel<<<dim3(slabs, WG_NJOBS), WG_THREADS, WG_SMEM, st>>>(W);
+    nerf_wgrad_tc_kernel<<<W.cta_first[WG_NJOBS], WG_THREADS, WG_SMEM, st>>>(W);
     timing_end(2, st);
     NERF_LAUNCHED();
     return NERF_OK;
