@@ -33,7 +33,7 @@ FLOP_PER_SAMPLE_FWD = 1186816          # BASELINE.md section 3 (un-padded, both 
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused forward kernel per launch (mean of the coarse and fine
 # launches of one step) from the committed `ncu --set full` captures: profiles/r1_train_kernels_ncu_summary.txt
 # (training variant, writes the saved operand images) and profiles/r1_render_fwd_ncu_summary.txt (render variant)
-NCU_TRAFFIC_PER_LAUNCH = {"train": (0.025934e9 + 1.348226e9 + 0.073420e9 + 4.165228e9) / 2,
+NCU_TRAFFIC_PER_LAUNCH = {"train": (0.030137e9 + 1.353939e9 + 0.085956e9 + 4.178626e9) / 2,
                           "render": (4.590592e6 + 6.688768e6 + 1.280e3) / 2}
 CPU_SAMPLE_RAYS = 256                  # bounded CPU sample (rays per CPU step)
 
@@ -398,7 +398,7 @@ def main():
         extra["roofline_wgrad"] = {"bound": "hbm", "kernel": "nerf_wgrad_tc_kernel", "unit": "GB/s", "peak": peaks["hbm"],
                                    "achieved": wg_bytes / (kernel_ms["wgrad"] * 1e-3) / 1e9,
                                    "frac": wg_bytes / (kernel_ms["wgrad"] * 1e-3) / 1e9 / peaks["hbm"],
-                                   "traffic": 12.019e9 / 2, "traffic_unit": "bytes/launch (ncu, profiles/r1_*)",
+                                   "traffic": (8.589644e9 + 2.817732e9) / 2, "traffic_unit": "bytes/launch (ncu, profiles/r1_*)",
                                    "peak_source": peaks["source"] + " (HBM copy)",
                                    "avg_launch_ms": kernel_ms["wgrad"] / 2, "launches": 2 * args.steps,
                                    "share_of_step": kernel_ms["wgrad"] / ms_per_step}
