@@ -165,7 +165,9 @@ __device__ __forceinline__ uint32_t signs_to_mask(uint32_t neg) { return ~__brev
 // forward of both nets per 4096-ray step: bulk stores 1.85 ms, 256-bit register stores 2.06 ms, 128-bit register
 // stores 2.44 ms -- the LSU path loses to the TMA engine even though it spares the shared-memory reads.
 constexpr bool kDirectSave = false;
-constexpr bool kSplitImageStore = true;   // bulk-store K-blocks 0,1 as soon as they are written (two 32 KB stores per phase)
+constexpr bool kSplitImageStore = true;
+constexpr bool kHybridSave = false;       // K-blocks 0,1 by 256-bit register stores during the first epilogue half, K-blocks 2,3 by
+                                          // one bulk store: measured 1.90 ms per step vs 1.65 with two bulk stores -- off   // bulk-store K-blocks 0,1 as soon as they are written (two 32 KB stores per phase)
 __device__ __forceinline__ void st_global_v4(uint64_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -221,7 +223,7 @@ __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float
 #pragma unroll
         for (int q = 0; q < 16; ++q) held[CG * 16 + q] = pk[q];
     }
-    if (SAVE && kDirectSave) {
+    if (SAVE && (kDirectSave || (kHybridSave && !STORE))) {
         const bool odd = (rs.off[0] >> 7) & 1;                 // row parity (bit 7 of the row's shared-memory address)
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -518,7 +520,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     tc_fence_before();
                     fence_async();
                     arrive(bar_lo);                                    // next phase may start on K-blocks 0,1
-                    if (SAVE && !kDirectSave && kSplitImageStore) {
+                    if (SAVE && !kDirectSave && kSplitImageStore && !kHybridSave) {
                         // first half of the image (K-blocks 0,1) leaves now, under the second half of the epilogue
                         named_bar_sync(1 + s, TILE_M);
                         if (elected) {
