@@ -258,3 +258,32 @@ def test_create_batched_dataset_pipeline_epoch_semantics(nk):
     first = next(iter(seq))
     assert torch.equal(first[1][0][:, 0].cpu(), torch.arange(B, dtype=torch.float32))
     assert torch.equal(first[1][2][0].cpu(), O.generate_t_vals(2.0, 6.0, 1, N, False)[0])
+
+
+def test_randomised_shapes_against_the_oracle(nk):
+    """Seeded fuzz over ragged sizes: ray generation (bit-exact), compositing (<= 1e-5) and resample + merge (== sort of
+    the concatenation) on 40 random shape combinations, including 1-row / 1-sample / non-multiple-of-32 cases."""
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        H, W = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        focal = float(rng.uniform(0.5, 900.0))
+        pose = np.asarray(O.pose_spherical(float(rng.uniform(-180, 180)), float(rng.uniform(-90, 0)), float(rng.uniform(1, 6))))
+        o, d = nk.get_rays(H, W, focal, pose)
+        o_ref, d_ref = O.get_rays(H, W, float(np.float32(focal)), torch.from_numpy(pose.astype(np.float32)))
+        assert np.array_equal(o.cpu().numpy(), o_ref.numpy()) and np.array_equal(d.cpu().numpy(), d_ref.numpy()), (case, H, W)
+        B, N = int(rng.integers(1, 300)), int(rng.integers(1, 260))
+        preds = torch.from_numpy(rng.normal(0, 2.5, (B, N, 4)).astype(np.float32))
+        t = torch.from_numpy(np.sort(rng.uniform(0.5, 9.0, (B, N)).astype(np.float32), axis=1))
+        rgb_r, dep_r, w_r = O.volume_render(preds, t)
+        rgb, dep, w = nk.volume_render(preds, t)
+        assert np.abs(rgb.cpu().numpy() - rgb_r.numpy()).max() <= 1e-5, (case, B, N)
+        assert np.abs(w.cpu().numpy() - w_r.numpy()).max() <= 1e-5, (case, B, N)
+        Nc, Nf = int(rng.integers(2, 130)), int(rng.integers(1, 270))
+        tc = torch.from_numpy(np.sort(rng.uniform(2.0, 6.0, (B, Nc)).astype(np.float32), axis=1)).cuda()
+        wc = torch.from_numpy(rng.random((B, Nc), dtype=np.float32) ** 3).cuda()
+        u = torch.from_numpy(rng.random((B, Nf), dtype=np.float32)).cuda()
+        t_all, src = nk.resample_merge(tc, wc, Nf, u=u, return_index=True)
+        fine = nk.sample_pdf(0.5 * (tc[:, 1:] + tc[:, :-1]), wc, Nf, u=u) if Nc >= 2 else None
+        cat = torch.cat([tc, fine], dim=1)
+        assert torch.equal(t_all, torch.sort(cat, dim=1).values), (case, B, Nc, Nf)
+        assert torch.equal(torch.gather(cat, 1, src.long()), t_all), (case, B, Nc, Nf)
