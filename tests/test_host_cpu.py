@@ -173,3 +173,11 @@ def test_keras_bridge_role_table_matches_layer_shapes():
         want = layer_shapes(conf["NUM_LAYERS"], conf["HIDDEN_DIM"], conf["SKIP_LAYER"], conf["L_XYZ"], conf["L_DIR"])
         assert roles == [r for r, _, _ in want]
         assert shapes == [(fi, fo) for _, fi, fo in want]
+
+
+def test_callback_image_scaling_matches_array_to_img():
+    """keras.utils.array_to_img(scale=True): (x - min) / (max - min) * 255, constant images stay 0 (train_lego.py:216-220)."""
+    from nerf_keras_b200.callbacks import array_to_uint8
+    x = np.array([[0.25, 0.5], [0.75, 1.25]], dtype=np.float32)
+    np.testing.assert_array_equal(array_to_uint8(x), np.array([[0, 63], [127, 255]], dtype=np.uint8))
+    assert array_to_uint8(np.full((2, 2), 3.0, np.float32)).max() == 0
