@@ -126,6 +126,24 @@ int nerf_train_forward_backward(nerf_ctx* ctx, const float* images, const float*
 /* keras.optimizers.Adam.apply_gradients (train_lego.py:149-151, models.py:107) on the ctx gradient
  * buffer scaled by grad_scale (1/world_size after a sum all-reduce); bumps the step count. */
 int nerf_adam_step(nerf_ctx* ctx, float grad_scale, void* stream);
+/* ---- BATCH_NORM=true training (models.py:30-33, 49-52 with training=True) --------------------------------------------
+ * Batch statistics couple all samples of a batch between consecutive layers, so this is a separate, layer-by-layer fp32
+ * path (cuBLAS sgemm between hand-written statistics / normalise / backward kernels; cuBLAS is bound at first use).  It
+ * serves the reference's small-batch BN configs and does not use a nerf_ctx: every buffer is the caller's.
+ *   params   [coarse | fine], nerf_param_count() floats each: Dense kernels and biases, un-folded
+ *   bn       [coarse | fine] x [gamma | beta | moving_mean | moving_variance], nerf_bn_param_count() floats each, layers in
+ *            the order d0..d(L-1), ddir; the moving statistics are updated in place (momentum 0.99, epsilon 1e-3)
+ *   grads    like params, overwritten;  bn_grads [coarse | fine] x [dgamma | dbeta], overwritten
+ *   metrics  3 device floats: loss_coarse, loss (fine), psnr
+ * Gradient semantics: stop-gradient on the fine sample positions. */
+int64_t nerf_bn_param_count(const nerf_config* cfg);
+int64_t nerf_bn_workspace_bytes(const nerf_config* cfg, int64_t batch);
+int nerf_bn_forward_backward(const nerf_config* cfg, const float* params, float* bn, const float* images, const float* o,
+                             const float* d, const float* t, const float* u_pdf, int64_t batch, float* grads, float* bn_grads,
+                             float* metrics, void* workspace, int64_t workspace_bytes, void* stream);
+/* The Adam update of nerf_adam_step on caller-owned flat buffers (step counts from 1). */
+int nerf_adam_flat(float* params, const float* grads, float* m, float* v, int64_t n, int64_t step, float learning_rate,
+                   float grad_scale, void* stream);
 /* NeRFTrainer.test_step metrics (models.py:122-145): mse_c, mse_f, psnr from rgb_c, rgb_f, images. */
 int nerf_metrics(const float* images, const float* rgb_c, const float* rgb_f, int64_t batch, float* metrics_dev,
                  void* stream);

@@ -7,7 +7,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr)
 OBJS=()
 PIDS=()
-for f in ops mlp_fp32 ctx mlp_tc mlp_tc_bwd; do
+for f in ops mlp_fp32 ctx mlp_tc mlp_tc_bwd bn_train; do
   src="$HERE/$f.cu"; obj="$HERE/$f.o"
   stale=0
   [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/../../include/nerf_b200.h" -nt "$obj" ]] && stale=1
@@ -19,5 +19,5 @@ for f in ops mlp_fp32 ctx mlp_tc mlp_tc_bwd; do
   OBJS+=("$obj")
 done
 for pid in "${PIDS[@]:-}"; do [[ -n "$pid" ]] && wait "$pid"; done
-"$NVCC" -shared -o "$OUT" "${OBJS[@]}" -lcudart
+"$NVCC" -shared -o "$OUT" "${OBJS[@]}" -lcudart -ldl
 echo "built $OUT"

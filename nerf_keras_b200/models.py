@@ -296,16 +296,87 @@ class NeRFTrainer:
         """models.py:80-86."""
         if not isinstance(optimizer, Adam):
             raise TypeError("optimizer must be nerf_keras_b200.models.Adam")
-        if self.coarse_model.bn is not None or self.fine_model.bn is not None:
-            raise NotImplementedError("training with BATCH_NORM=true is not supported by the B200 path: batch statistics "
-                                      "over all samples of a batch need a layer-by-layer kernel (DESIGN.md); "
-                                      "BN checkpoints can be rendered (inference folds the moving statistics)")
+        if (self.coarse_model.bn is None) != (self.fine_model.bn is None):
+            raise ValueError("coarse and fine model must both be created with the same bn flag")
         self.optimizer, self.loss_fn = optimizer, loss_fn
+        self._bn_state = None
+        if self.coarse_model.bn is not None:
+            # BATCH_NORM=true: batch statistics couple all samples of a batch between consecutive layers, so training
+            # runs on the layer-by-layer fp32 path (csrc/bn_train.cu); rendering keeps the fused kernels (folded BN).
+            if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                                  and torch.distributed.get_world_size() > 1):
+                raise NotImplementedError("data-parallel training with BATCH_NORM=true is not supported")
+            self.optimizer = optimizer
+            self._rebuild_ctx_inference_only()
+            self._bn_init_state()
+            return
         self._rebuild_ctx()
 
     def build(self, input_shape=None):
         if self._ctx is None:
             self._rebuild_ctx()
+
+    # -- BATCH_NORM=true training state (csrc/bn_train.cu) -----------------------------------------------------------
+    def _rebuild_ctx_inference_only(self):
+        opt, self.optimizer = self.optimizer, None           # the ctx of a BN trainer is a render-only ctx
+        try:
+            self._rebuild_ctx()
+        finally:
+            self.optimizer = opt
+
+    def _bn_init_state(self):
+        dev = _dev()
+        models = (self.coarse_model, self.fine_model)
+        n = self.coarse_model.count_params()
+        roles = list(self.coarse_model.bn.keys())
+        pack = lambda m, k: np.concatenate([m.bn[r][k] for r in roles]).astype(np.float32)
+        params = torch.from_numpy(np.concatenate([m._host_blob for m in models])).to(dev)
+        bn = torch.from_numpy(np.concatenate([np.concatenate([pack(m, k) for k in ("gamma", "beta", "mean", "var")])
+                                              for m in models])).to(dev)
+        nbn = bn.numel() // 8
+        z = lambda k: torch.zeros(k, device=dev, dtype=torch.float32)
+        self._bn_state = dict(params=params, bn=bn, n=n, nbn=nbn, roles=roles, grads=z(2 * n), bn_grads=z(4 * nbn),
+                              m=z(2 * n), v=z(2 * n), bm=z(8 * nbn), bv=z(8 * nbn), step=0, ws=None, ws_rays=0, dirty=False)
+
+    def _bn_sync_models(self):
+        """Device training state -> the two models (un-folded weights + BN parameters) -> folded weights of the render ctx."""
+        st = getattr(self, "_bn_state", None)
+        if not st or not st["dirty"]:
+            return
+        st["dirty"] = False
+        params, bn = st["params"].cpu().numpy(), st["bn"].cpu().numpy()
+        n, nbn = st["n"], st["nbn"]
+        for i, m in enumerate((self.coarse_model, self.fine_model)):
+            blk = bn[i * 4 * nbn:(i + 1) * 4 * nbn]
+            off, out = 0, {}
+            for r in st["roles"]:
+                c = m.bn[r]["gamma"].shape[0]
+                out[r] = {k: blk[j * nbn + off: j * nbn + off + c].copy() for j, k in enumerate(("gamma", "beta", "mean", "var"))}
+                off += c
+            m.bn = out
+            m.set_flat_weights(params[i * n:(i + 1) * n])      # pushes the folded blob to the ctx
+
+    def _bn_train_step(self, images, o, d, t, u):
+        st = self._bn_state
+        B = o.shape[0]
+        L = _lib.lib()
+        cfg = self._ctx.cfg
+        if st["ws"] is None or st["ws_rays"] < B:
+            st["ws"] = torch.empty(int(L.nerf_bn_workspace_bytes(C.byref(cfg), B)), dtype=torch.uint8, device=o.device)
+            st["ws_rays"] = B
+        metrics = torch.empty((3,), device=o.device, dtype=torch.float32)
+        _lib.check(L.nerf_bn_forward_backward(C.byref(cfg), _ptr(st["params"]), _ptr(st["bn"]), _ptr(images), _ptr(o), _ptr(d),
+                                              _ptr(t), _ptr(u), B, _ptr(st["grads"]), _ptr(st["bn_grads"]), _ptr(metrics),
+                                              _ptr(st["ws"]), st["ws"].numel(), _stream()), "bn train_step")
+        st["step"] += 1
+        lr, n, nbn = float(self.optimizer.learning_rate), st["n"], st["nbn"]
+        adam = lambda p, g, m, v, k: _lib.check(L.nerf_adam_flat(p, g, m, v, k, st["step"], lr, 1.0, _stream()), "adam")
+        adam(_ptr(st["params"]), _ptr(st["grads"]), _ptr(st["m"]), _ptr(st["v"]), 2 * n)
+        for i in range(2):      # gamma | beta of each net are the first 2 nbn floats of its [gamma | beta | mean | var] block
+            e = 4 * i * nbn * 4
+            adam(_ptr(st["bn"]) + e, _ptr(st["bn_grads"]) + 2 * i * nbn * 4, _ptr(st["bm"]) + e, _ptr(st["bv"]) + e, 2 * nbn)
+        st["dirty"] = True
+        return self._update_metrics(metrics)
 
     def _rebuild_ctx(self, max_rays=None):
         for m in (self.coarse_model, self.fine_model):
@@ -353,6 +424,7 @@ class NeRFTrainer:
             raise NotImplementedError("BATCH_NORM=true is inference-only on the B200 path")
         if self._ctx is None:
             self._rebuild_ctx()
+        self._bn_sync_models()
         o, d, t = _f32(ray_origins), _f32(ray_directions), _f32(t_vals)
         if t.shape != (o.shape[0], self.ns_coarse):
             raise ValueError(f"t_vals must have shape (n_rays, {self.ns_coarse})")
@@ -426,6 +498,9 @@ class NeRFTrainer:
         images, (o, d, t) = inputs
         images, o, d, t = _f32(images), _f32(o), _f32(d), _f32(t)
         B = o.shape[0]
+        if getattr(self, "_bn_state", None) is not None:
+            u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
+            return self._bn_train_step(images, o, d, t, u)
         if B > self._ctx.max_rays:
             self._rebuild_ctx(max_rays=B)
         u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
@@ -485,6 +560,7 @@ class NeRFTrainer:
 
     # -- weights I/O (train_lego.py:199-213, inference.py:170) ------------------------------------
     def save_weights(self, path: str):
+        self._bn_sync_models()
         data = {}
         for name, m in (("coarse", self.coarse_model), ("fine", self.fine_model)):
             for role, wb in m.get_weights().items():

@@ -50,3 +50,21 @@ def test_train_fern_script_with_callback(tmp_path):
     for e in range(conf["EPOCHS"]):
         im = Image.open(tmp_path / "images" / "ckpt" / f"{e:03d}.png")
         assert im.size == (2 * conf["WIDTH"], conf["HEIGHT"])            # predicted image | depth map
+
+
+def test_train_script_with_batch_norm_config(tmp_path):
+    """The reference's BN configs (fern_batch_debug / fern_batch_h256 / lego_batch_debug have BATCH_NORM=true) train on the
+    layer-by-layer path and validate / save through the fused kernels with the moving statistics folded in."""
+    import json
+    conf = json.load(open(os.path.join(ROOT, "config", "lego_batch_debug.json")))
+    conf.update(BATCH_NORM=True, EPOCHS=2)
+    cfg = tmp_path / "lego_bn_debug.json"
+    json.dump(conf, open(cfg, "w"))
+    out = _run([os.path.join(ROOT, "train_lego.py"), "--config", str(cfg), "--steps-per-epoch", "30", "--views", "5"], str(tmp_path))
+    lines = [l for l in out.splitlines() if l.startswith("Epoch")]
+    assert len(lines) == 2 and "nan" not in out.lower()
+    loss = [float(l.split("loss: ")[1].split()[0]) for l in lines]
+    assert loss[1] < loss[0]
+    saved = [f for f in os.listdir(tmp_path / "models") if f.endswith(".npz")]
+    data = np.load(tmp_path / "models" / saved[0])
+    assert "coarse/d0/bn_gamma" in data and "fine/ddir/bn_var" in data

@@ -72,7 +72,7 @@ def test_models_host_logic():
     w["rgb"]["b"][:] = [1, 2, 3]
     m.set_weights(w)
     assert np.array_equal(m.get_weights()["rgb"]["b"], [1, 2, 3])
-    # BATCH_NORM=true: inference folds gamma / sqrt(var + eps) into the Dense weights on the host; training raises
+    # BATCH_NORM=true: inference folds gamma / sqrt(var + eps) into the Dense weights on the host
     mb = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
     assert sorted(mb.get_bn_params()) == sorted([f"d{i}" for i in range(8)] + ["ddir"])
     bn = mb.get_bn_params()
@@ -81,9 +81,6 @@ def test_models_host_logic():
     raw, dev = mb.get_weights()["d0"], mb.device_blob()
     np.testing.assert_allclose(dev[:63 * 256].reshape(63, 256), raw["W"], rtol=1e-6)           # s = 2 / sqrt(4) = 1
     np.testing.assert_allclose(dev[63 * 256:63 * 256 + 256], raw["b"] - 1.0 + 0.5, atol=1e-6)    # (b - mean) s + beta
-    with pytest.raises(NotImplementedError):
-        nk.NeRFTrainer(mb, nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True), 8, 4, 8, 10, 4).compile(
-            nk.Adam(5e-4), nk.MeanSquaredError())
     with pytest.raises(TypeError):
         nk.NeRFTrainer(object(), m, 8, 4, 8, 10, 4)
     oracle_like = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
