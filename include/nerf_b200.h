@@ -44,7 +44,7 @@ typedef struct nerf_config {
     int32_t l_xyz;       /* L_XYZ       (10)  */
     int32_t l_dir;       /* L_DIR       (4)   */
     int32_t ns_coarse;   /* NS_COARSE         */
-    int32_t ns_fine;     /* NS_FINE           */
+    int32_t ns_fine;     /* NS_FINE; 0 = single-net benchmark shape (coarse net only, SURVEY 8(d) sweep) */
     int32_t max_rays;    /* largest ray batch any call will pass (workspace is sized for it) */
     int32_t batch_norm;  /* BATCH_NORM: must be 0 here; the host mirror folds BN inference into W, b   */
     int32_t training;    /* 1: allocate gradient / Adam / saved-activation storage            */
@@ -110,7 +110,9 @@ int nerf_mlp_forward_encoded(nerf_ctx* ctx, int net, const float* rays_enc, cons
  * o,d (B,3), t (B,N) -> preds (B,N,4).  precision selects the tcgen05 or the fp32 path. */
 int nerf_mlp_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t batch,
                           int num_samples, int precision, float* preds, void* stream);
-/* NeRFTrainer.forward_pass (models.py:151-176), inference mode.  u_pdf (B,Nf) explicit uniforms.
+/* NeRFTrainer.forward_pass (models.py:151-176), inference mode.  u_pdf (B,Nf) explicit uniforms, or NULL: the
+ * draws of tf.random.uniform (data_utils.py:196) are generated inside the resampling kernel (Philox4x32-10 keyed by
+ * nerf_set_seed, a per-call counter, the ray and the draw index -- no (B,Nf) buffer in HBM).
  * Outputs (any may be NULL): rgb_c/f (B,3), depth_c/f (B), w_c (B,Nc), w_f (B,Nc+Nf),
  * pred_c (B,Nc,4), pred_f (B,Nc+Nf,4), t_all (B,Nc+Nf). */
 typedef struct nerf_forward_out {
@@ -123,6 +125,28 @@ int nerf_forward_pass(nerf_ctx* ctx, const float* o, const float* d, const float
  * loss_coarse, loss (fine), psnr (models.py:110-120).  images (B,3). */
 int nerf_train_forward_backward(nerf_ctx* ctx, const float* images, const float* o, const float* d, const float* t,
                                 const float* u_pdf, int64_t batch, float* metrics_dev, void* stream);
+/* The same step in two halves so that a data-parallel caller can all-reduce the fine net's half of the gradient buffer
+ * while the coarse net's backward still runs: phases bit 0 = forward of both nets, loss, metrics and the
+ * fine net's backward (fills grads[n_params, 2 n_params)); bit 1 = the coarse net's backward, including the term through
+ * the fine sample positions (fills grads[0, n_params)).  phases = 3 is nerf_train_forward_backward.  u_pdf may be NULL
+ * (in-kernel Philox draws keyed by the optimiser step).  No host synchronisation; safe to capture in a CUDA graph. */
+#define NERF_PHASE_FORWARD_FINE 1
+#define NERF_PHASE_COARSE 2
+int nerf_train_phases(nerf_ctx* ctx, const float* images, const float* o, const float* d, const float* t,
+                      const float* u_pdf, int64_t batch, float* metrics_dev, int phases, void* stream);
+/* Seed of the in-kernel uniform draws (keras.utils.set_random_seed, train_lego.py:22). */
+int nerf_set_seed(nerf_ctx* ctx, uint64_t seed);
+/* LEARNING_RATE lives in device memory (the step may be replayed from a CUDA graph): change it between steps. */
+int nerf_set_learning_rate(nerf_ctx* ctx, float learning_rate, void* stream);
+/* Optimiser state [coarse | fine] (2 * param_count floats each) and the number of applied updates: read / restore it when a
+ * trainer moves to a context with a larger workspace.  Device pointers; `step` is a host value. */
+int nerf_get_optimizer_state(nerf_ctx* ctx, float* m, float* v, int64_t* step, void* stream);
+int nerf_set_optimizer_state(nerf_ctx* ctx, const float* m, const float* v, int64_t step, void* stream);
+/* Running sums kept by the context for keras.metrics.Mean (models.py:113-120): device float[4] = sum of loss_coarse,
+ * sum of loss (fine), sum of psnr, number of steps; every train phase-0 call and nerf_metrics_accumulate add to it. */
+int nerf_metric_sums(nerf_ctx* ctx, float** sums_dev);
+int nerf_metrics_accumulate(nerf_ctx* ctx, const float* images, const float* rgb_c, const float* rgb_f, int64_t batch,
+                            float* metrics_dev, void* stream);
 /* keras.optimizers.Adam.apply_gradients (train_lego.py:149-151, models.py:107) on the ctx gradient
  * buffer scaled by grad_scale (1/world_size after a sum all-reduce); bumps the step count. */
 int nerf_adam_step(nerf_ctx* ctx, float grad_scale, void* stream);
@@ -168,6 +192,9 @@ int nerf_debug_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d
                           int num_samples, float* dtp, void* stream);
 int nerf_sample_pdf_bwd(const float* t, const float* weights, const float* u, const int32_t* src_idx,
                         const float* dtp, const float* d_delta, int64_t batch, int nc, int nf, float* d_w, void* stream);
+/* Test hook: out (batch, nf) = the uniforms the in-kernel generator gives sample_pdf for (seed, counter); a training step
+ * uses counter = number of optimiser updates applied so far, an inference pass 2^62 + its call index since nerf_set_seed. */
+int nerf_debug_pdf_draws(uint64_t seed, uint64_t counter, int64_t batch, int nf, float* out, void* stream);
 /* Timing experiments only: bit0 skip the CUDA-core side jobs, bit1 skip the MMAs, bit2 skip the final
  * reduction of the weight-gradient kernel (results are then wrong by construction). */
 int nerf_debug_flags(int flags);

@@ -59,7 +59,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    dt = time.time() - t0           # wall time of the slowest rank's render loop
+    dt_render = time.time() - t0    # wall time of the slowest rank's render loop
     local_frames = torch.stack(frames) if frames else torch.empty((0, H, W, 3), dtype=torch.uint8, device="cuda")
     if world > 1:
         per = -(-args.frames // world)
@@ -70,11 +70,14 @@ def main():
             chunks = [allf[r * per: r * per + (shard_range(args.frames, r, world)[1] - shard_range(args.frames, r, world)[0])]
                       for r in range(world)]
             local_frames = torch.cat(chunks)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+    dt = time.time() - t0           # ... including the only collective of the sweep, the gather of the frames to rank 0
     if rank == 0:
         np.save(args.out, local_frames.cpu().numpy())
         n_rays = args.frames * H * W
-        print(f"rendered {local_frames.shape[0]} frames {H}x{W} on {world} GPU(s) in {dt:.3f} s: "
-              f"{n_rays / dt:.3e} rays/s aggregate -> {args.out}")
+        print(f"rendered {local_frames.shape[0]} frames {H}x{W} on {world} GPU(s) in {dt:.3f} s including the gather "
+              f"({dt_render:.3f} s render only): {n_rays / dt:.3e} rays/s aggregate -> {args.out}")
 
 
 if __name__ == "__main__":

@@ -50,7 +50,14 @@ SIGNATURES = {
     "nerf_mlp_forward_rays": (_I, [_P, _I, _P, _P, _P, _L, _I, _I, _P, _P]),
     "nerf_forward_pass": (_I, [_P, _P, _P, _P, _P, _L, _I, C.POINTER(ForwardOut), _P]),
     "nerf_train_forward_backward": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _P]),
+    "nerf_train_phases": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _I, _P]),
     "nerf_adam_step": (_I, [_P, _F, _P]),
+    "nerf_set_seed": (_I, [_P, C.c_uint64]),
+    "nerf_set_learning_rate": (_I, [_P, _F, _P]),
+    "nerf_get_optimizer_state": (_I, [_P, _P, _P, C.POINTER(_L), _P]),
+    "nerf_set_optimizer_state": (_I, [_P, _P, _P, _L, _P]),
+    "nerf_metric_sums": (_I, [_P, C.POINTER(_P)]),
+    "nerf_metrics_accumulate": (_I, [_P, _P, _P, _P, _L, _P, _P]),
     "nerf_metrics": (_I, [_P, _P, _P, _L, _P, _P]),
     "nerf_launch_count": (_L, []),
     "nerf_timing_enable": (_I, [_I]),
@@ -59,6 +66,7 @@ SIGNATURES = {
     "nerf_selftest_mma_rate": (_I, [_I, _I, _I, _P, _P]),
     "nerf_debug_input_grad": (_I, [_P, _I, _P, _P, _P, _L, _I, _P, _P]),
     "nerf_sample_pdf_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _P]),
+    "nerf_debug_pdf_draws": (_I, [C.c_uint64, C.c_uint64, _L, _I, _P, _P]),
     "nerf_debug_flags": (_I, [_I]),
     "nerf_debug_pair_mode": (_I, [_I]),
     "nerf_debug_trace": (_I, [_P]),

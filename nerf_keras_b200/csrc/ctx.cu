@@ -3,16 +3,19 @@
 
 using namespace nerf;
 
-extern "C" int nerf_volume_render_bwd(const float*, const float*, const float*, const float*, int64_t, int, float*,
-                                      float*, void*);
-extern "C" int nerf_metrics_grad(const float*, const float*, const float*, int64_t, float*, float*, float*, void*);
+extern "C" int nerf_volume_render_bwd_heads(const float*, const float*, const float*, const float*, int64_t, int, float*,
+                                            float*, float*, float*, void*);
+extern "C" int nerf_metrics_grad_sums(const float*, const float*, const float*, int64_t, float*, float*, float*, float*,
+                                      void*);
 extern "C" int nerf_adam_flat(float*, const float*, float*, float*, int64_t, int64_t, float, float, void*);
 
 namespace nerf {
 int64_t tc_save_bytes_per_tile();
 int tc_train_alloc(nerf_ctx* ctx);
 int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
-                const float* d_preds, cudaStream_t st);
+                const float* d_preds, cudaStream_t st, int flags);
+int adam_from_dev_state(float* params, const float* grads, float* m, float* v, int64_t n, const nerf_dev_state* ds,
+                        float grad_scale, cudaStream_t st);
 }  // namespace nerf
 
 static int build_layers(const nerf_config& c, std::vector<LayerInfo>& layers, int64_t& n_params) {
@@ -46,7 +49,7 @@ static int validate_cfg(const nerf_config* c) {
     NERF_CHECK_ARG(c->hidden_dim >= 2 && c->hidden_dim <= 1024 && c->hidden_dim % 2 == 0, "HIDDEN_DIM out of range");
     NERF_CHECK_ARG(c->skip_layer >= 1, "SKIP_LAYER must be >= 1");
     NERF_CHECK_ARG(c->l_xyz >= 0 && c->l_xyz <= 16 && c->l_dir >= 0 && c->l_dir <= 16, "L_XYZ/L_DIR out of range");
-    NERF_CHECK_ARG(c->ns_coarse >= 2 && c->ns_fine >= 1, "NS_COARSE must be >= 2 and NS_FINE >= 1");
+    NERF_CHECK_ARG(c->ns_coarse >= 2 && c->ns_fine >= 0, "NS_COARSE must be >= 2 and NS_FINE >= 0");
     NERF_CHECK_ARG(c->max_rays >= 1, "max_rays must be >= 1");
     NERF_CHECK_ARG(c->batch_norm == 0, "BATCH_NORM=true is not supported by the B200 path (see DESIGN.md)");
     // the skip concat after the LAST trunk layer would change the head fan-in; the reference configs never do this
@@ -95,7 +98,16 @@ extern "C" int nerf_create(const nerf_config* cfg, nerf_ctx** out) {
     ALLOC(ctx->fw_src_idx, R * Na * 4);
     ALLOC(ctx->fw_rgb_c, R * 12);
     ALLOC(ctx->fw_rgb_f, R * 12);
-    ALLOC(ctx->fw_dirbias, R * (cfg->hidden_dim / 2) * 4);
+    ALLOC(ctx->fw_dirbias[0], R * (cfg->hidden_dim / 2) * 4);
+    ALLOC(ctx->fw_dirbias[1], R * (cfg->hidden_dim / 2) * 4);
+    ALLOC(ctx->dev_state, sizeof(nerf_dev_state));
+    ALLOC(ctx->metric_sums, 4 * sizeof(float));
+    cudaMemset(ctx->metric_sums, 0, 4 * sizeof(float));
+    {
+        nerf_dev_state h = {};
+        h.lr = cfg->learning_rate;
+        cudaMemcpy(ctx->dev_state, &h, sizeof(h), cudaMemcpyHostToDevice);
+    }
     if (cfg->training) {
         ALLOC(ctx->grads, np2 * 4);
         ALLOC(ctx->adam_m, np2 * 4);
@@ -133,7 +145,7 @@ extern "C" int nerf_destroy(nerf_ctx* ctx) {
     cudaFree(ctx->ws_a); cudaFree(ctx->ws_b); cudaFree(ctx->ws_c); cudaFree(ctx->ws_encx); cudaFree(ctx->ws_encd);
     cudaFree(ctx->fw_pred_c); cudaFree(ctx->fw_pred_f); cudaFree(ctx->fw_w_c); cudaFree(ctx->fw_w_f);
     cudaFree(ctx->fw_t_all); cudaFree(ctx->fw_src_idx); cudaFree(ctx->fw_rgb_c); cudaFree(ctx->fw_rgb_f);
-    cudaFree(ctx->fw_dirbias);
+    cudaFree(ctx->fw_dirbias[0]); cudaFree(ctx->fw_dirbias[1]); cudaFree(ctx->dev_state); cudaFree(ctx->metric_sums);
     cudaFree(ctx->tr_dpred_c); cudaFree(ctx->tr_dpred_f); cudaFree(ctx->tr_drgb_c); cudaFree(ctx->tr_drgb_f);
     cudaFree(ctx->tr_ddirbias); cudaFree(ctx->tr_ddelta_f); cudaFree(ctx->tr_dtp_f); cudaFree(ctx->tr_dw_extra);
     cudaFree(ctx->w_ig);
@@ -151,6 +163,7 @@ extern "C" int nerf_set_weights(nerf_ctx* ctx, int net, const float* blob, int64
                               (cudaStream_t)stream));
     ctx->weights_set[net] = true;
     ctx->packed_valid[net] = false;
+    ctx->bwd_packed_valid = false;
     return NERF_OK;
 }
 
@@ -217,8 +230,8 @@ extern "C" int nerf_mlp_forward_rays(nerf_ctx* ctx, int net, const float* o, con
     return tc_forward_rays(ctx, net, o, d, t, batch, num_samples, preds, false, (cudaStream_t)stream);
 }
 
-// NeRFTrainer.forward_pass (models.py:151-176)
-static int forward_pass_impl(nerf_ctx* ctx, const float* o, const float* d, const float* t, const float* u_pdf,
+// NeRFTrainer.forward_pass (models.py:151-176).  NS_FINE = 0 (single-net benchmark shape) stops after the coarse net.
+static int forward_pass_impl(nerf_ctx* ctx, const float* o, const float* d, const float* t, const PdfDraws& draws,
                              int64_t B, int precision, bool save, const nerf_forward_out* out, cudaStream_t st) {
     const nerf_config& c = ctx->cfg;
     const int Nc = c.ns_coarse, Nf = c.ns_fine, Na = Nc + Nf;
@@ -232,13 +245,17 @@ static int forward_pass_impl(nerf_ctx* ctx, const float* o, const float* d, cons
     float* rgb_c = z.rgb_c ? z.rgb_c : ctx->fw_rgb_c;
     float* rgb_f = z.rgb_f ? z.rgb_f : ctx->fw_rgb_f;
     int rc;
+    const bool tc = precision != NERF_PRECISION_FP32;
+    if (tc && (rc = tc_dirbias(ctx, d, B, Nf > 0 ? 3 : 1, st))) return rc;     // ddir biases of both nets, one launch
     auto mlp = [&](int net, const float* tt, int N, float* preds) -> int {
-        if (precision == NERF_PRECISION_FP32) return mlp_fp32_forward_rays(ctx, net, o, d, tt, B, N, preds, st);
-        return tc_forward_rays(ctx, net, o, d, tt, B, N, preds, save, st);
+        if (!tc) return mlp_fp32_forward_rays(ctx, net, o, d, tt, B, N, preds, st);
+        return tc_forward_rays(ctx, net, o, d, tt, B, N, preds, save, st, true);
     };
     if ((rc = mlp(NERF_NET_COARSE, t, Nc, pred_c))) return rc;                                       // :152-157
+    // the coarse weights are only needed by the resampling: skip the store when nobody asked for them
     if ((rc = nerf_volume_render(pred_c, t, B, Nc, rgb_c, z.depth_c, w_c, z.acc_c, st))) return rc;  // :164
-    if ((rc = nerf_resample_merge(t, w_c, u_pdf, B, Nc, Nf, t_all, ctx->fw_src_idx, st))) return rc; // :165-167
+    if (Nf == 0) return NERF_OK;
+    if ((rc = resample_merge(t, w_c, draws, B, Nc, Nf, t_all, ctx->fw_src_idx, st))) return rc;      // :165-167
     if ((rc = mlp(NERF_NET_FINE, t_all, Na, pred_f))) return rc;                                     // :169-173
     if ((rc = nerf_volume_render(pred_f, t_all, B, Na, rgb_f, z.depth_f, w_f, z.acc_f, st))) return rc;  // :175
     return NERF_OK;
@@ -246,67 +263,161 @@ static int forward_pass_impl(nerf_ctx* ctx, const float* o, const float* d, cons
 
 extern "C" int nerf_forward_pass(nerf_ctx* ctx, const float* o, const float* d, const float* t, const float* u_pdf,
                                  int64_t batch, int precision, const nerf_forward_out* out, void* stream) {
-    NERF_CHECK_ARG(ctx && o && d && t && u_pdf && batch >= 0, "bad arguments");
+    NERF_CHECK_ARG(ctx && o && d && t && batch >= 0, "bad arguments");
     NERF_CHECK_ARG(batch <= ctx->cfg.max_rays, "batch exceeds cfg.max_rays");
     NERF_CHECK_ARG(precision == NERF_PRECISION_FP32 || precision == NERF_PRECISION_BF16_TC, "unknown precision");
     int rc = check_ready(ctx, 0);
     if (rc) return rc;
-    if ((rc = check_ready(ctx, 1))) return rc;
+    if (ctx->cfg.ns_fine > 0 && (rc = check_ready(ctx, 1))) return rc;
     if (precision == NERF_PRECISION_BF16_TC) {
         std::string why;
         if (!tc_supported(ctx->cfg, &why)) return fail(NERF_ERR_INVALID, why);
     }
     if (batch == 0) return NERF_OK;
-    return forward_pass_impl(ctx, o, d, t, u_pdf, batch, precision, false, out, (cudaStream_t)stream);
+    // in-kernel draws of an inference pass: keyed by a per-call counter in its own half of the counter space
+    PdfDraws dr = {u_pdf, ctx->seed, u_pdf ? 0ull : ((1ull << 62) + ctx->render_draws++), nullptr};
+    return forward_pass_impl(ctx, o, d, t, dr, batch, precision, false, out, (cudaStream_t)stream);
 }
 
 // NeRFTrainer.train_step up to (not including) apply_gradients  (models.py:88-106)
-extern "C" int nerf_train_forward_backward(nerf_ctx* ctx, const float* images, const float* o, const float* d,
-                                           const float* t, const float* u_pdf, int64_t batch, float* metrics_dev,
-                                           void* stream) {
-    NERF_CHECK_ARG(ctx && images && o && d && t && u_pdf && metrics_dev && batch >= 1, "bad arguments");
+extern "C" int nerf_train_phases(nerf_ctx* ctx, const float* images, const float* o, const float* d, const float* t,
+                                 const float* u_pdf, int64_t batch, float* metrics_dev, int phases, void* stream) {
+    NERF_CHECK_ARG(ctx && images && o && d && t && metrics_dev && batch >= 1, "bad arguments");
     NERF_CHECK_ARG(batch <= ctx->cfg.max_rays, "batch exceeds cfg.max_rays");
+    NERF_CHECK_ARG((phases & 3) != 0 && (phases & ~7) == 0, "phases: bit 0 forward + fine backward, bit 1 coarse backward, bit 2 accumulate");
     if (!ctx->cfg.training || !ctx->grads) return fail(NERF_ERR_STATE, "ctx was not created with training=1");
     std::string why;
     if (!tc_supported(ctx->cfg, &why)) return fail(NERF_ERR_INVALID, why);
+    const bool single = ctx->cfg.ns_fine == 0;
     int rc = check_ready(ctx, 0);
     if (rc) return rc;
-    if ((rc = check_ready(ctx, 1))) return rc;
+    if (!single && (rc = check_ready(ctx, 1))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int Nc = ctx->cfg.ns_coarse, Na = Nc + ctx->cfg.ns_fine;
-    if ((rc = forward_pass_impl(ctx, o, d, t, u_pdf, batch, NERF_PRECISION_BF16_TC, true, nullptr, st))) return rc;
-    if ((rc = nerf_metrics_grad(images, ctx->fw_rgb_c, ctx->fw_rgb_f, batch, metrics_dev, ctx->tr_drgb_c,
-                                ctx->tr_drgb_f, st)))
-        return rc;
-    const bool q5 = !ctx->cfg.stop_grad_samples;   // reference semantics: gradient flows through the fine sample positions
-    NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * ctx->n_params * 4, st));
-    // fine net first: its input gradient feeds the coarse net through sort + sample_pdf (models.py:165-175)
-    if ((rc = nerf_volume_render_bwd(ctx->fw_pred_f, ctx->fw_t_all, ctx->tr_drgb_f, nullptr, batch, Na, ctx->tr_dpred_f,
-                                     q5 ? ctx->tr_ddelta_f : nullptr, st)))
-        return rc;
-    if ((rc = tc_backward(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dpred_f, st))) return rc;
-    const float* d_w_extra = nullptr;
-    if (q5) {
-        if ((rc = tc_input_grad(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dtp_f, st))) return rc;
-        if ((rc = sample_pdf_backward(t, ctx->fw_w_c, u_pdf, ctx->fw_src_idx, ctx->tr_dtp_f, ctx->tr_ddelta_f, batch, Nc,
-                                      ctx->cfg.ns_fine, ctx->tr_dw_extra, st)))
+    const int64_t np = ctx->n_params;
+    const bool q5 = !ctx->cfg.stop_grad_samples && !single;   // reference semantics: gradient flows through the fine sample positions
+    // uniform draws of sample_pdf: explicit, or Philox keyed by the optimiser step held in device memory
+    const PdfDraws dr = {u_pdf, ctx->seed, 0ull, u_pdf ? nullptr : &ctx->dev_state->step};
+    const LayerInfo& Lrgb = ctx->layers[ctx->cfg.num_layers + 3];
+    const LayerInfo& Lsig = ctx->layers[ctx->cfg.num_layers];
+    if (phases & NERF_PHASE_FORWARD_FINE) {
+        if ((rc = forward_pass_impl(ctx, o, d, t, dr, batch, NERF_PRECISION_BF16_TC, true, nullptr, st))) return rc;
+        if ((rc = nerf_metrics_grad_sums(images, ctx->fw_rgb_c, single ? ctx->fw_rgb_c : ctx->fw_rgb_f, batch, metrics_dev,
+                                         ctx->tr_drgb_c, single ? nullptr : ctx->tr_drgb_f, ctx->metric_sums, st)))
             return rc;
-        d_w_extra = ctx->tr_dw_extra;
+        if (!(phases & 4)) NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * np * 4, st));
+        if ((rc = tc_dir_images(ctx, d, batch, Nc, single ? 0 : Na, st))) return rc;
+        if (!single) {
+            // fine net first: its input gradient feeds the coarse net through sort + sample_pdf (models.py:165-175)
+            float* gf = ctx->grads + np;
+            if ((rc = nerf_volume_render_bwd_heads(ctx->fw_pred_f, ctx->fw_t_all, ctx->tr_drgb_f, nullptr, batch, Na,
+                                                   ctx->tr_dpred_f, q5 ? ctx->tr_ddelta_f : nullptr, gf + Lrgb.b_off,
+                                                   gf + Lsig.b_off, st)))
+                return rc;
+            if ((rc = tc_backward(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dpred_f, st, 3))) return rc;
+        }
     }
-    if ((rc = nerf_volume_render_bwd(ctx->fw_pred_c, t, ctx->tr_drgb_c, d_w_extra, batch, Nc, ctx->tr_dpred_c, nullptr, st)))
-        return rc;
-    if ((rc = tc_backward(ctx, NERF_NET_COARSE, o, d, t, batch, Nc, ctx->tr_dpred_c, st))) return rc;
+    if (phases & NERF_PHASE_COARSE) {
+        const float* d_w_extra = nullptr;
+        if (q5) {
+            if ((rc = tc_input_grad(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dtp_f, st))) return rc;
+            if ((rc = sample_pdf_backward(t, ctx->fw_w_c, dr, ctx->fw_src_idx, ctx->tr_dtp_f, ctx->tr_ddelta_f, batch, Nc,
+                                          ctx->cfg.ns_fine, ctx->tr_dw_extra, st)))
+                return rc;
+            d_w_extra = ctx->tr_dw_extra;
+        }
+        float* gc = ctx->grads;
+        if ((rc = nerf_volume_render_bwd_heads(ctx->fw_pred_c, t, ctx->tr_drgb_c, d_w_extra, batch, Nc, ctx->tr_dpred_c,
+                                               nullptr, gc + Lrgb.b_off, gc + Lsig.b_off, st)))
+            return rc;
+        if ((rc = tc_backward(ctx, NERF_NET_COARSE, o, d, t, batch, Nc, ctx->tr_dpred_c, st, 3))) return rc;
+    }
     return NERF_OK;
 }
 
+extern "C" int nerf_train_forward_backward(nerf_ctx* ctx, const float* images, const float* o, const float* d,
+                                           const float* t, const float* u_pdf, int64_t batch, float* metrics_dev,
+                                           void* stream) {
+    return nerf_train_phases(ctx, images, o, d, t, u_pdf, batch, metrics_dev, 3, stream);
+}
+
+// keras Adam.apply_gradients on [coarse | fine]; t and the learning rate come from device memory, the step counter is
+// bumped by the re-pack launch that follows (forward images of both nets), then the transposed images are rebuilt:
+// every operand image is current when the next step starts and no later call has to pack anything.
 extern "C" int nerf_adam_step(nerf_ctx* ctx, float grad_scale, void* stream) {
     NERF_CHECK_ARG(ctx != nullptr, "null ctx");
     if (!ctx->grads) return fail(NERF_ERR_STATE, "nerf_adam_step: ctx was not created with training=1");
+    cudaStream_t st = (cudaStream_t)stream;
     ctx->adam_step += 1;
-    int rc = nerf_adam_flat(ctx->params, ctx->grads, ctx->adam_m, ctx->adam_v, 2 * ctx->n_params, ctx->adam_step,
-                            ctx->cfg.learning_rate, grad_scale, stream);
-    ctx->packed_valid[0] = ctx->packed_valid[1] = false;
-    return rc;
+    int rc = adam_from_dev_state(ctx->params, ctx->grads, ctx->adam_m, ctx->adam_v, 2 * ctx->n_params, ctx->dev_state,
+                                 grad_scale, st);
+    if (rc) return rc;
+    if (tc_supported(ctx->cfg, nullptr)) {
+        if ((rc = tc_pack_all(ctx, true, st))) return rc;
+        if ((rc = tc_pack_backward(ctx, st))) return rc;
+    } else {
+        return fail(NERF_ERR_STATE, "nerf_adam_step: training runs on the tcgen05 path only (8x256, skip 4, L 10/4)");
+    }
+    return NERF_OK;
+}
+
+extern "C" int nerf_set_seed(nerf_ctx* ctx, uint64_t seed) {
+    NERF_CHECK_ARG(ctx != nullptr, "null ctx");
+    ctx->seed = seed;
+    ctx->render_draws = 0;
+    NERF_CUDA(cudaMemcpy(&ctx->dev_state->seed, &seed, sizeof(seed), cudaMemcpyHostToDevice));
+    return NERF_OK;
+}
+
+extern "C" int nerf_set_learning_rate(nerf_ctx* ctx, float lr, void* stream) {
+    NERF_CHECK_ARG(ctx != nullptr && lr >= 0.f, "bad arguments");
+    ctx->cfg.learning_rate = lr;
+    // the value is read from pageable host memory: synchronous with respect to the host, ordered on `stream`
+    NERF_CUDA(cudaMemcpyAsync(&ctx->dev_state->lr, &ctx->cfg.learning_rate, sizeof(float), cudaMemcpyHostToDevice,
+                              (cudaStream_t)stream));
+    NERF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return NERF_OK;
+}
+
+extern "C" int nerf_get_optimizer_state(nerf_ctx* ctx, float* m, float* v, int64_t* step, void* stream) {
+    NERF_CHECK_ARG(ctx && m && v && step, "null pointer");
+    if (!ctx->grads) return fail(NERF_ERR_STATE, "ctx was not created with training=1");
+    cudaStream_t st = (cudaStream_t)stream;
+    NERF_CUDA(cudaMemcpyAsync(m, ctx->adam_m, 2 * ctx->n_params * 4, cudaMemcpyDefault, st));
+    NERF_CUDA(cudaMemcpyAsync(v, ctx->adam_v, 2 * ctx->n_params * 4, cudaMemcpyDefault, st));
+    // the authoritative count is the device one (graph replays do not pass through nerf_adam_step on the host)
+    unsigned long long s = 0;
+    NERF_CUDA(cudaMemcpyAsync(&s, &ctx->dev_state->step, sizeof(s), cudaMemcpyDeviceToHost, st));
+    NERF_CUDA(cudaStreamSynchronize(st));
+    ctx->adam_step = (int64_t)s;
+    *step = ctx->adam_step;
+    return NERF_OK;
+}
+
+extern "C" int nerf_set_optimizer_state(nerf_ctx* ctx, const float* m, const float* v, int64_t step, void* stream) {
+    NERF_CHECK_ARG(ctx && m && v && step >= 0, "bad arguments");
+    if (!ctx->grads) return fail(NERF_ERR_STATE, "ctx was not created with training=1");
+    cudaStream_t st = (cudaStream_t)stream;
+    NERF_CUDA(cudaMemcpyAsync(ctx->adam_m, m, 2 * ctx->n_params * 4, cudaMemcpyDefault, st));
+    NERF_CUDA(cudaMemcpyAsync(ctx->adam_v, v, 2 * ctx->n_params * 4, cudaMemcpyDefault, st));
+    ctx->adam_step = step;
+    const unsigned long long s = (unsigned long long)step;
+    NERF_CUDA(cudaMemcpyAsync(&ctx->dev_state->step, &s, sizeof(s), cudaMemcpyHostToDevice, st));
+    NERF_CUDA(cudaStreamSynchronize(st));
+    return NERF_OK;
+}
+
+extern "C" int nerf_metric_sums(nerf_ctx* ctx, float** sums_dev) {
+    NERF_CHECK_ARG(ctx && sums_dev, "null pointer");
+    *sums_dev = ctx->metric_sums;
+    return NERF_OK;
+}
+
+// NeRFTrainer.test_step (models.py:122-145): metrics of one batch, added to the running sums of the context
+extern "C" int nerf_metrics_accumulate(nerf_ctx* ctx, const float* images, const float* rgb_c, const float* rgb_f,
+                                       int64_t batch, float* metrics_dev, void* stream) {
+    NERF_CHECK_ARG(ctx != nullptr, "null ctx");
+    return nerf_metrics_grad_sums(images, rgb_c, rgb_f, batch, metrics_dev, nullptr, nullptr, ctx->metric_sums, stream);
 }
 
 // Diagnostics: gradients of sum(preds * d_preds) wrt one net's weights for given rays / t-values
@@ -326,7 +437,7 @@ extern "C" int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, cons
     NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * ctx->n_params * 4, st));
     float* dp = net == 0 ? ctx->tr_dpred_c : ctx->tr_dpred_f;   // tile-padded staging buffer
     NERF_CUDA(cudaMemcpyAsync(dp, d_preds, (size_t)batch * num_samples * 16, cudaMemcpyDeviceToDevice, st));
-    return tc_backward(ctx, net, o, d, t, batch, num_samples, dp, st);
+    return tc_backward(ctx, net, o, d, t, batch, num_samples, dp, st, 0);
 }
 
 // Diagnostics: after nerf_debug_mlp_grads(net, ...) -- dtp[m] = < d_ray, d(sum(preds * d_preds)) / d pts[m] >.

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "rng.cuh"
 
 namespace nerf {
 
@@ -15,6 +16,15 @@ struct LayerInfo {
 };
 
 }  // namespace nerf
+
+// Step state that kernels read from device memory, so that a captured CUDA graph of the training step stays valid
+// from one replay to the next (kernel arguments are frozen at capture time).
+struct nerf_dev_state {
+    unsigned long long step;   // optimiser updates applied so far (Adam's t - 1); also keys the in-kernel uniform draws
+    unsigned long long seed;   // nerf_set_seed
+    float lr;                  // LEARNING_RATE
+    float pad;
+};
 
 struct nerf_ctx {
     nerf_config cfg;
@@ -27,7 +37,11 @@ struct nerf_ctx {
     float* grads = nullptr;
     float* adam_m = nullptr;
     float* adam_v = nullptr;
-    int64_t adam_step = 0;
+    int64_t adam_step = 0;                // host mirror of dev_state->step
+    nerf_dev_state* dev_state = nullptr;
+    uint64_t seed = 0;
+    uint64_t render_draws = 0;            // counter keying the in-kernel draws of inference forward passes
+    float* metric_sums = nullptr;         // device float[4]: running sums of loss_coarse, loss, psnr + step count
     bool weights_set[2] = {false, false};
 
     // tcgen05 operand images (bf16, 128B-swizzled 16 KB chunks) + fp32 side tables, per net
@@ -35,6 +49,7 @@ struct nerf_ctx {
     __nv_bfloat16* w_bwd[2] = {nullptr, nullptr};  // backward (transposed) chunk stream
     float* side[2] = {nullptr, nullptr};           // biases + fp32 head weights (see mlp_tc.cu)
     bool packed_valid[2] = {false, false};
+    bool bwd_packed_valid = false;                 // w_bwd[0], w_bwd[1] and w_ig match the current weights
 
     // fp32 path workspace (allocated on first use)
     int64_t fp32_chunk = 0;
@@ -42,7 +57,8 @@ struct nerf_ctx {
 
     // forward_pass / train workspace, sized for cfg.max_rays
     float *fw_pred_c = nullptr, *fw_pred_f = nullptr, *fw_w_c = nullptr, *fw_w_f = nullptr, *fw_t_all = nullptr;
-    float *fw_rgb_c = nullptr, *fw_rgb_f = nullptr, *fw_dirbias = nullptr;
+    float *fw_rgb_c = nullptr, *fw_rgb_f = nullptr;
+    float* fw_dirbias[2] = {nullptr, nullptr};     // per-ray ddir bias of each net
     int32_t* fw_src_idx = nullptr;
 
     // training workspace (cfg.training): saved activation images and gradient images, per net
@@ -69,11 +85,18 @@ int tc_supported(const nerf_config& cfg, std::string* why);
 int tc_alloc(nerf_ctx* ctx);
 void tc_free(nerf_ctx* ctx);
 int tc_pack_weights(nerf_ctx* ctx, int net, cudaStream_t st);
+int tc_pack_all(nerf_ctx* ctx, bool tick_step, cudaStream_t st);     // forward images of both nets (+ step counter tick)
+int tc_pack_backward(nerf_ctx* ctx, cudaStream_t st);                // transposed images of both nets + input-gradient image
+int tc_dirbias(nerf_ctx* ctx, const float* d, int64_t B, int nets_mask, cudaStream_t st);
+int tc_dir_images(nerf_ctx* ctx, const float* d, int64_t B, int nc, int na, cudaStream_t st);
+bool stream_is_capturing(cudaStream_t st);
 int tc_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N, float* dtp,
                   cudaStream_t st);
-int sample_pdf_backward(const float* t, const float* weights, const float* u, const int32_t* src_idx, const float* dtp,
+int sample_pdf_backward(const float* t, const float* weights, const PdfDraws& dr, const int32_t* src_idx, const float* dtp,
                         const float* d_delta, int64_t B, int nc, int nf, float* d_w, cudaStream_t st);
 int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
-                    float* preds, bool save_acts, cudaStream_t st);
+                    float* preds, bool save_acts, cudaStream_t st, bool dirbias_ready = false);
+int resample_merge(const float* t, const float* weights, PdfDraws dr, int64_t B, int nc, int nf, float* t_all,
+                   int32_t* src_idx, cudaStream_t st);
 
 }  // namespace nerf

@@ -82,8 +82,17 @@ __device__ __forceinline__ float fwd_weight_at(const float* __restrict__ blob, c
     }
 }
 
-__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ blob, BlobOffsets off,
-                                                       __nv_bfloat16* __restrict__ chunks, float* __restrict__ side) {
+struct PackFwdArgs {
+    const float* blob[2];
+    __nv_bfloat16* chunks[2];
+    float* side[2];
+    nerf_dev_state* tick;      // optional: the optimiser step counter is bumped here (this launch follows the Adam kernel)
+};
+__global__ void __launch_bounds__(256) pack_fwd_kernel(const PackFwdArgs A, BlobOffsets off) {
+    const float* __restrict__ blob = A.blob[blockIdx.y];
+    __nv_bfloat16* __restrict__ chunks = A.chunks[blockIdx.y];
+    float* __restrict__ side = A.side[blockIdx.y];
+    if (A.tick && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) A.tick->step += 1ull;
     // one thread per 16-byte group: chunk g, row n (0..127), k-group kg (0..7)
     const int total = N_CHUNKS * 128 * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -120,10 +129,15 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
 }
 
 // per-ray fp32 bias of the ddir layer: dirbias[ray][j] = sum_k enc_dir(d_ray)[k] * Wddir[256+k][j]
-__global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ d, int64_t rays,
-                                                      const float* __restrict__ wddir /* (283,128) */,
-                                                      const float* __restrict__ bddir /* (128) */,
-                                                      float* __restrict__ dirbias) {
+struct DirbiasArgs {
+    const float* wddir[2];   // (283,128)
+    const float* bddir[2];   // (128)
+    float* out[2];           // (rays,128)
+};
+__global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ d, int64_t rays, const DirbiasArgs A) {
+    const float* __restrict__ wddir = A.wddir[blockIdx.y];
+    const float* __restrict__ bddir = A.bddir[blockIdx.y];
+    float* __restrict__ dirbias = A.out[blockIdx.y];
     __shared__ float enc[ENC_D];
     for (int64_t ray = blockIdx.x; ray < rays; ray += gridDim.x) {
         if (threadIdx.x < ENC_D) {
@@ -1383,33 +1397,61 @@ void tc_free(nerf_ctx* ctx) {
     }
 }
 
-int tc_pack_weights(nerf_ctx* ctx, int net, cudaStream_t st) {
+static int launch_pack_fwd(nerf_ctx* ctx, int first, int count, bool tick, cudaStream_t st) {
     BlobOffsets off = make_offsets(ctx);
-    pack_fwd_kernel<<<num_sms(), 256, 0, st>>>(ctx->params + (int64_t)net * ctx->n_params, off, ctx->w_fwd[net],
-                                               ctx->side[net]);
+    PackFwdArgs A = {};
+    for (int i = 0; i < count; ++i) {
+        const int net = first + i;
+        A.blob[i] = ctx->params + (int64_t)net * ctx->n_params;
+        A.chunks[i] = ctx->w_fwd[net];
+        A.side[i] = ctx->side[net];
+    }
+    A.tick = tick ? ctx->dev_state : nullptr;
+    pack_fwd_kernel<<<dim3(num_sms() / 2, count), 256, 0, st>>>(A, off);
     NERF_LAUNCHED();
-    ctx->packed_valid[net] = true;
+    for (int i = 0; i < count; ++i) ctx->packed_valid[first + i] = true;
+    return NERF_OK;
+}
+
+int tc_pack_weights(nerf_ctx* ctx, int net, cudaStream_t st) { return launch_pack_fwd(ctx, net, 1, false, st); }
+int tc_pack_all(nerf_ctx* ctx, bool tick_step, cudaStream_t st) { return launch_pack_fwd(ctx, 0, 2, tick_step, st); }
+
+// per-ray ddir biases of the nets in `nets_mask` (bit 0 coarse, bit 1 fine), one launch
+int tc_dirbias(nerf_ctx* ctx, const float* d, int64_t B, int nets_mask, cudaStream_t st) {
+    DirbiasArgs A = {};
+    int count = 0;
+    for (int net = 0; net < 2; ++net) {
+        if (!(nets_mask & (1 << net))) continue;
+        const float* blob = ctx->params + (int64_t)net * ctx->n_params;
+        A.wddir[count] = blob + ctx->layers[10].w_off;
+        A.bddir[count] = blob + ctx->layers[10].b_off;
+        A.out[count] = ctx->fw_dirbias[net];
+        ++count;
+    }
+    if (count == 0 || B == 0) return NERF_OK;
+    dirbias_kernel<<<dim3((unsigned)(B < 4 * num_sms() ? B : 4 * num_sms()), count), 128, 0, st>>>(d, B, A);
+    NERF_LAUNCHED();
     return NERF_OK;
 }
 
 int tc_forward_rays(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
-                    float* preds, bool save_acts, cudaStream_t st) {
+                    float* preds, bool save_acts, cudaStream_t st, bool dirbias_ready) {
     if (!ctx->packed_valid[net]) {
         int rc = tc_pack_weights(ctx, net, st);
         if (rc) return rc;
     }
     if (B > ctx->cfg.max_rays) return fail(NERF_ERR_INVALID, "tc_forward_rays: batch exceeds cfg.max_rays");
-    const float* blob = ctx->params + (int64_t)net * ctx->n_params;
-    dirbias_kernel<<<(unsigned)(B < 4 * num_sms() ? B : 4 * num_sms()), 128, 0, st>>>(
-        d, B, blob + ctx->layers[10].w_off, blob + ctx->layers[10].b_off, ctx->fw_dirbias);
-    NERF_LAUNCHED();
+    if (!dirbias_ready) {
+        int rc = tc_dirbias(ctx, d, B, 1 << net, st);
+        if (rc) return rc;
+    }
     FwdParams P;
     P.o = o; P.d = d; P.t = t; P.N = N;
     P.M = B * (int64_t)N;
     P.n_pairs = ceil_div(P.M, 2 * TILE_M);
     P.w_chunks = ctx->w_fwd[net];
     P.side = ctx->side[net];
-    P.dirbias = ctx->fw_dirbias;
+    P.dirbias = ctx->fw_dirbias[net];
     P.preds = reinterpret_cast<float4*>(preds);
     P.act_save = save_acts ? reinterpret_cast<uint8_t*>(ctx->act_save[net]) : nullptr;
     P.mask_save = save_acts ? ctx->mask_save[net] : nullptr;

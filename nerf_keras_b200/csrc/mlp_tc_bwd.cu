@@ -47,8 +47,22 @@ __device__ __forceinline__ float bwd_weight_at(const float* __restrict__ blob, c
     return blob[off.w[l] + (int64_t)n * H + k];                          // rows 0..255 (h part for l = 5)
 }
 
-__global__ void __launch_bounds__(256) pack_bwd_kernel(const float* __restrict__ blob, BlobOffsets off,
-                                                       __nv_bfloat16* __restrict__ chunks) {
+struct PackBwdArgs {
+    const float* blob[2];
+    __nv_bfloat16* chunks[2];
+    const float* ig_blob;            // weights whose W0^T / W5b^T image is packed by grid row 2 (the fine net), or null
+    __nv_bfloat16* ig_img;
+};
+__device__ void pack_ig_rows(const float* __restrict__ blob, const BlobOffsets& off, __nv_bfloat16* __restrict__ img);
+
+__global__ void __launch_bounds__(256) pack_bwd_kernel(const PackBwdArgs A, BlobOffsets off) {
+    if (blockIdx.y == 2) {
+        if (A.ig_blob) pack_ig_rows(A.ig_blob, off, A.ig_img);
+        return;
+    }
+    const float* __restrict__ blob = A.blob[blockIdx.y];
+    __nv_bfloat16* __restrict__ chunks = A.chunks[blockIdx.y];
+    if (!blob) return;
     const int total = B_CHUNKS * 128 * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int g = i / (128 * 8);
@@ -491,8 +505,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
 // kernel hoists that product into a per-ray bias, the backward wants it as a GEMM operand again.
 // One warp per ray writes the ray's N rows ([27 values | zeros], 128 bytes each) into the tiles' images.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) dir_image_kernel(const float* __restrict__ d, int64_t rays, int N,
-                                                        uint8_t* __restrict__ act_save) {
+struct DirImageArgs {
+    int N[2];
+    uint8_t* act_save[2];
+};
+__global__ void __launch_bounds__(128) dir_image_kernel(const float* __restrict__ d, int64_t rays, const DirImageArgs A) {
+    const int N = A.N[blockIdx.y];
+    uint8_t* __restrict__ act_save = A.act_save[blockIdx.y];
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < rays; ray += warps_total) {
@@ -552,8 +571,7 @@ constexpr int IG_SM_A = IG_W_BYTES;                    // 2 stages x 64 KB (one 
 constexpr int IG_SM_BAR = IG_SM_A + 2 * 65536;
 constexpr int IG_SMEM = IG_SM_BAR + 128 + 1024;
 
-__global__ void __launch_bounds__(256) pack_ig_kernel(const float* __restrict__ blob, BlobOffsets off,
-                                                      __nv_bfloat16* __restrict__ img) {
+__device__ void pack_ig_rows(const float* __restrict__ blob, const BlobOffsets& off, __nv_bfloat16* __restrict__ img) {
     // img[w][kb][n (64) x k (64)]: B[n][k] = W0[n][kb*64+k] (w=0) or W5[256+n][kb*64+k] (w=1); rows n >= 63 are zero
     const int total = 2 * 4 * 64 * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -718,7 +736,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 
 __global__ void __launch_bounds__(128) sample_pdf_bwd_kernel(const float* __restrict__ t, const float* __restrict__ weights,
-                                                             const float* __restrict__ u, const int32_t* __restrict__ src_idx,
+                                                             const PdfDraws dr, const int32_t* __restrict__ src_idx,
                                                              const float* __restrict__ dtp, const float* __restrict__ d_delta,
                                                              int64_t B, int nc, int nf, float* __restrict__ d_w) {
     extern __shared__ float smem_pb[];
@@ -729,6 +747,7 @@ __global__ void __launch_bounds__(128) sample_pdf_bwd_kernel(const float* __rest
     float* dcdf = tm + nc + 1;                          // nc + 1
     float* pdf = dcdf + nc + 1;                         // nc
     const int na = nc + nf;
+    const unsigned long long dstep = pdf_step(dr);
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < B; ray += warps_total) {
         const float* w = weights + ray * nc;
@@ -758,7 +777,7 @@ __global__ void __launch_bounds__(128) sample_pdf_bwd_kernel(const float* __rest
             float g = dtp[ray * na + pos];
             if (pos > 0) g += d_delta[ray * na + pos - 1];
             if (pos < na - 1) g -= d_delta[ray * na + pos];
-            const float uu = u[ray * nf + j];
+            const float uu = pdf_draw(dr, dstep, ray, nf, j);
             int lo = 0, hi = nc + 1;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] > uu) hi = mid; else lo = mid + 1; }
             const int below = max(0, lo - 1), above = min(nc, lo);
@@ -804,8 +823,8 @@ int tc_train_alloc(nerf_ctx* ctx) {
     const nerf_config& c = ctx->cfg;
     // the CTA-pair forward kernel works on 512-row quads: size the per-tile storage for whole quads
     const int64_t tiles[2] = {ceil_div((int64_t)c.max_rays * c.ns_coarse, 512) * 4,
-                              ceil_div((int64_t)c.max_rays * (c.ns_coarse + c.ns_fine), 512) * 4};
-    for (int net = 0; net < 2; ++net) {
+                              c.ns_fine > 0 ? ceil_div((int64_t)c.max_rays * (c.ns_coarse + c.ns_fine), 512) * 4 : 0};
+    for (int net = 0; net < (c.ns_fine > 0 ? 2 : 1); ++net) {
         NERF_CUDA(cudaMalloc((void**)&ctx->act_save[net], (size_t)(tiles[net] * SAVE_TILE_BYTES)));
         // rows of a ragged last tile are read by the weight-gradient GEMMs (times zero gradients): keep them finite
         NERF_CUDA(cudaMemset(ctx->act_save[net], 0, (size_t)(tiles[net] * SAVE_TILE_BYTES)));
@@ -820,9 +839,41 @@ int tc_train_alloc(nerf_ctx* ctx) {
     return NERF_OK;
 }
 
-// gradients of one net given dL/dpreds; the forward must have run with save_acts on the same batch
+// transposed weight images of both nets and the input-gradient image of the fine net, one launch
+int tc_pack_backward(nerf_ctx* ctx, cudaStream_t st) {
+    BlobOffsets off = make_offsets(ctx);
+    PackBwdArgs A = {};
+    const bool single = ctx->cfg.ns_fine == 0;
+    for (int net = 0; net < (single ? 1 : 2); ++net) {
+        A.blob[net] = ctx->params + (int64_t)net * ctx->n_params;
+        A.chunks[net] = ctx->w_bwd[net];
+    }
+    if (!single) {      // 64 KB: also packed for stop_grad_samples contexts (diagnostic entry points use it)
+        A.ig_blob = ctx->params + ctx->n_params;
+        A.ig_img = ctx->w_ig;
+    }
+    pack_bwd_kernel<<<dim3(num_sms() / 3, 3), 256, 0, st>>>(A, off);
+    NERF_LAUNCHED();
+    ctx->bwd_packed_valid = true;
+    return NERF_OK;
+}
+
+// direction-encoding operand images of both nets (rows of Wddir below the feature part), one launch
+int tc_dir_images(nerf_ctx* ctx, const float* d, int64_t B, int nc, int na, cudaStream_t st) {
+    DirImageArgs A = {};
+    A.N[0] = nc; A.act_save[0] = reinterpret_cast<uint8_t*>(ctx->act_save[0]);
+    A.N[1] = na; A.act_save[1] = reinterpret_cast<uint8_t*>(ctx->act_save[1]);
+    const int nets = (na > 0) ? 2 : 1;
+    dir_image_kernel<<<dim3(stream_grid(B * 32, 128, 4), nets), 128, 0, st>>>(d, B, A);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+
+// gradients of one net given dL/dpreds; the forward must have run with save_acts on the same batch.
+// flags bit 0: the head bias gradients were already accumulated by volume_render_bwd; bit 1: the direction images of
+// this net are already in place (tc_dir_images)
 int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
-                const float* d_preds, cudaStream_t st) {
+                const float* d_preds, cudaStream_t st, int flags) {
     (void)o; (void)t;
     const int64_t M = B * (int64_t)N;
     const int64_t n_pairs = ceil_div(M, 2 * TILE_M);
@@ -830,11 +881,12 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     if (n_pairs * 2 * TILE_M > M)
         NERF_CUDA(cudaMemsetAsync(const_cast<float*>(d_preds) + M * 4, 0, (size_t)(n_pairs * 2 * TILE_M - M) * 16, st));
     BlobOffsets off = make_offsets(ctx);
-    const float* blob = ctx->params + (int64_t)net * ctx->n_params;
     float* grads = ctx->grads + (int64_t)net * ctx->n_params;
 
-    pack_bwd_kernel<<<num_sms(), 256, 0, st>>>(blob, off, ctx->w_bwd[net]);
-    NERF_LAUNCHED();
+    if (!ctx->bwd_packed_valid) {
+        int rc = tc_pack_backward(ctx, st);
+        if (rc) return rc;
+    }
 
     BwdParams P;
     P.dpreds = reinterpret_cast<const float4*>(d_preds);
@@ -876,11 +928,17 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     job(11, SAVE_HD, 2, DZ_HEAD, 1, off.w[11], 3, H / 2, 0, 3, -1);
     // direction rows of Wddir: dirimg^T dZ_ddir -> rows 256..282 of dW_ddir
     job(12, SAVE_DIR, 1, DZ_DDIR, 2, off.w[10] + (int64_t)H * (H / 2), H / 2, ENC_D, 0, H / 2, -1);
-    head_bias_kernel<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4*>(d_preds), M, grads + off.b[11],
-                                                grads + off.b[8]);
-    NERF_LAUNCHED();
-    dir_image_kernel<<<stream_grid(B * 32, 128), 128, 0, st>>>(d, B, N, reinterpret_cast<uint8_t*>(ctx->act_save[net]));
-    NERF_LAUNCHED();
+    if (!(flags & 1)) {
+        head_bias_kernel<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4*>(d_preds), M, grads + off.b[11],
+                                                    grads + off.b[8]);
+        NERF_LAUNCHED();
+    }
+    if (!(flags & 2)) {
+        DirImageArgs A = {};
+        A.N[0] = N; A.act_save[0] = reinterpret_cast<uint8_t*>(ctx->act_save[net]);
+        dir_image_kernel<<<dim3(stream_grid(B * 32, 128), 1), 128, 0, st>>>(d, B, A);
+        NERF_LAUNCHED();
+    }
     int slabs = num_sms() / WG_NJOBS;
     if (slabs < 1) slabs = 1;
     if (slabs > W.n_half_tiles) slabs = (int)W.n_half_tiles;
@@ -904,9 +962,11 @@ namespace nerf {
 int tc_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N, float* dtp,
                   cudaStream_t st) {
     const int64_t M = B * (int64_t)N;
-    BlobOffsets off = make_offsets(ctx);
-    pack_ig_kernel<<<16, 256, 0, st>>>(ctx->params + (int64_t)net * ctx->n_params, off, ctx->w_ig);
-    NERF_LAUNCHED();
+    if (net != 1) return fail(NERF_ERR_INVALID, "tc_input_grad: the input-gradient image is packed for the fine net only");
+    if (!ctx->bwd_packed_valid) {
+        int rc = tc_pack_backward(ctx, st);
+        if (rc) return rc;
+    }
     IgParams P;
     P.dz_save = reinterpret_cast<const uint8_t*>(ctx->dz_save[net]);
     P.w_img = ctx->w_ig;
@@ -919,12 +979,12 @@ int tc_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const 
     return NERF_OK;
 }
 
-int sample_pdf_backward(const float* t, const float* weights, const float* u, const int32_t* src_idx, const float* dtp,
+int sample_pdf_backward(const float* t, const float* weights, const PdfDraws& dr, const int32_t* src_idx, const float* dtp,
                         const float* d_delta, int64_t B, int nc, int nf, float* d_w, cudaStream_t st) {
     const int threads = 128;
     const size_t smem = (size_t)(threads / 32) * (3 * (nc + 1) + nc) * sizeof(float);
     if (smem > 48 * 1024) return fail(NERF_ERR_INVALID, "sample_pdf_backward: nc too large");
-    sample_pdf_bwd_kernel<<<stream_grid(B * 32, threads), threads, smem, st>>>(t, weights, u, src_idx, dtp, d_delta, B, nc, nf, d_w);
+    sample_pdf_bwd_kernel<<<stream_grid(B * 32, threads), threads, smem, st>>>(t, weights, dr, src_idx, dtp, d_delta, B, nc, nf, d_w);
     NERF_LAUNCHED();
     return NERF_OK;
 }
@@ -939,8 +999,8 @@ extern "C" int nerf_sample_pdf_bwd(const float* t, const float* weights, const f
     float* zeros = nullptr;
     NERF_CUDA(cudaMalloc(&zeros, (size_t)batch * (nc + nf) * 4));
     NERF_CUDA(cudaMemsetAsync(zeros, 0, (size_t)batch * (nc + nf) * 4, (cudaStream_t)stream));
-    int rc = nerf::sample_pdf_backward(t, weights, u, src_idx, dtp ? dtp : zeros, d_delta ? d_delta : zeros, batch, nc, nf,
-                                       d_w, (cudaStream_t)stream);
+    int rc = nerf::sample_pdf_backward(t, weights, nerf::PdfDraws{u, 0ull, 0ull, nullptr}, src_idx, dtp ? dtp : zeros,
+                                       d_delta ? d_delta : zeros, batch, nc, nf, d_w, (cudaStream_t)stream);
     cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(zeros);
     return rc;

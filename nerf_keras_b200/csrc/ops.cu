@@ -4,6 +4,7 @@
 // entry point in include/nerf_b200.h).  Ray and t-value generation is BIT-EXACT with respect to the
 // reference's op order: separately rounded __f*_rn intrinsics, no FMA contraction, true division.
 #include "common.cuh"
+#include "ctx.cuh"
 
 namespace nerf {
 thread_local std::string g_last_error;
@@ -419,12 +420,14 @@ __global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __
                                                                 const float* __restrict__ d_rgb,
                                                                 const float* __restrict__ d_w_extra, int64_t B,
                                                                 int N, float4* __restrict__ d_preds,
-                                                                float* __restrict__ d_delta) {
+                                                                float* __restrict__ d_delta,
+                                                                float* __restrict__ g_brgb, float* __restrict__ g_bsig) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     float4 cp[NCH], np_[NCH];
     float ct[NCH], nt[NCH];
+    float4 hb = make_float4(0.f, 0.f, 0.f, 0.f);     // bias gradients of the rgb / sigma heads: sums of d_preds
     auto load = [&](int64_t r, float4 (&p)[NCH], float (&tt)[NCH]) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -500,8 +503,10 @@ __global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __
             const float dsig = dLdalpha * delta * e;
             const float ds_raw = (pr.w > 0.0f) ? dsig : 0.0f;
             if (ok) {
-                d_preds[ray * N + n] =
+                const float4 dpv =
                     make_float4(w * dr * cr * (1.0f - cr), w * dg * cg * (1.0f - cg), w * db * cb * (1.0f - cb), ds_raw);
+                d_preds[ray * N + n] = dpv;
+                hb.x += dpv.x; hb.y += dpv.y; hb.z += dpv.z; hb.w += dpv.w;
                 if (d_delta) d_delta[ray * N + n] = (n == N - 1) ? 0.0f : dLdalpha * sigma * e;
             }
             Rcarry = b0 + a0 * Rcarry;
@@ -509,10 +514,32 @@ __global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __
 #pragma unroll
         for (int c = 0; c < NCH; ++c) { cp[c] = np_[c]; ct[c] = nt[c]; }
     }
+    if (g_brgb) {
+        // one atomic per block and component (block reduce through shared memory)
+        __shared__ float4 s_hb[8];
+        hb.x = warp_sum(hb.x); hb.y = warp_sum(hb.y); hb.z = warp_sum(hb.z); hb.w = warp_sum(hb.w);
+        if (lane == 0) s_hb[threadIdx.x >> 5] = hb;
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            float a = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += reinterpret_cast<const float*>(&s_hb[w])[threadIdx.x];
+            atomicAdd(threadIdx.x < 3 ? g_brgb + threadIdx.x : g_bsig, a);
+        }
+    }
 }
 
+// g_brgb (3 floats) / g_bsig (1 float), optional: the bias gradients of the rgb and sigma heads are ACCUMULATED there
+extern "C" int nerf_volume_render_bwd_heads(const float* preds, const float* t, const float* d_rgb, const float* d_w_extra,
+                                            int64_t batch, int num_samples, float* d_preds, float* d_delta, float* g_brgb,
+                                            float* g_bsig, void* stream);
 extern "C" int nerf_volume_render_bwd(const float* preds, const float* t, const float* d_rgb, const float* d_w_extra,
                                       int64_t batch, int num_samples, float* d_preds, float* d_delta, void* stream) {
+    return nerf_volume_render_bwd_heads(preds, t, d_rgb, d_w_extra, batch, num_samples, d_preds, d_delta, nullptr, nullptr,
+                                        stream);
+}
+extern "C" int nerf_volume_render_bwd_heads(const float* preds, const float* t, const float* d_rgb, const float* d_w_extra,
+                                            int64_t batch, int num_samples, float* d_preds, float* d_delta, float* g_brgb,
+                                            float* g_bsig, void* stream) {
     NERF_CHECK_ARG(preds && t && d_rgb && d_preds && batch >= 0 && num_samples >= 1, "bad arguments");
     NERF_CHECK_ARG(num_samples <= 512, "num_samples > 512 is not supported by the compositing kernel");
     if (batch == 0) return NERF_OK;
@@ -523,7 +550,7 @@ extern "C" int nerf_volume_render_bwd(const float* preds, const float* t, const 
     cudaStream_t st = (cudaStream_t)stream;
     const int nch = (num_samples + 31) / 32;
 #define NERF_VRB(K) \
-    volume_render_bwd_kernel<K><<<grid, threads, 0, st>>>(p4, t, d_rgb, d_w_extra, batch, num_samples, dp4, d_delta)
+    volume_render_bwd_kernel<K><<<grid, threads, 0, st>>>(p4, t, d_rgb, d_w_extra, batch, num_samples, dp4, d_delta, g_brgb, g_bsig)
     if (nch <= 1) NERF_VRB(1);
     else if (nch == 2) NERF_VRB(2);
     else if (nch == 3) NERF_VRB(3);
@@ -619,9 +646,10 @@ extern "C" int nerf_sample_pdf(const float* t_mid, const float* weights, const f
 // bitonic sort of P = next_pow2(nc+nf) (value, source index) pairs per warp in shared memory.
 __global__ void __launch_bounds__(128) resample_merge_kernel(const float* __restrict__ t,
                                                              const float* __restrict__ weights,
-                                                             const float* __restrict__ u, int64_t B, int nc, int nf,
+                                                             const PdfDraws dr, int64_t B, int nc, int nf,
                                                              int P, float* __restrict__ t_all,
                                                              int32_t* __restrict__ src_idx) {
+    const unsigned long long dstep = pdf_step(dr);
     extern __shared__ float smem_rm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int per_warp = (2 * nc + 2) + 2 * P;
@@ -642,7 +670,7 @@ __global__ void __launch_bounds__(128) resample_merge_kernel(const float* __rest
         }
         __syncwarp();
         for (int j = lane; j < nf; j += 32) {
-            key[nc + j] = invert_cdf(cdf, tm, nc, u[ray * nf + j]);
+            key[nc + j] = invert_cdf(cdf, tm, nc, pdf_draw(dr, dstep, ray, nf, j));
             val[nc + j] = nc + j;
         }
         for (int j = na + lane; j < P; j += 32) {
@@ -684,10 +712,11 @@ __global__ void __launch_bounds__(128) resample_merge_kernel(const float* __rest
 template <int FI>
 __global__ void __launch_bounds__(128) resample_merge_sorted_kernel(const float* __restrict__ t,
                                                                     const float* __restrict__ weights,
-                                                                    const float* __restrict__ u, int64_t B, int nc, int nf,
+                                                                    const PdfDraws dr, int64_t B, int nc, int nf,
                                                                     float* __restrict__ t_all,
                                                                     int32_t* __restrict__ src_idx) {
     constexpr int P = 32 * FI;
+    const unsigned long long dstep = pdf_step(dr);
     extern __shared__ float smem_rm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int per_warp = (2 * nc + 2) + nc + P;
@@ -719,7 +748,7 @@ __global__ void __launch_bounds__(128) resample_merge_sorted_kernel(const float*
 #pragma unroll
         for (int r = 0; r < FI; ++r) {
             const int j = r * 32 + lane;
-            key[r] = (j < nf) ? invert_cdf(cdf, tm, nc, u[ray * nf + j]) : __int_as_float(0x7f800000);
+            key[r] = (j < nf) ? invert_cdf(cdf, tm, nc, pdf_draw(dr, dstep, ray, nf, j)) : __int_as_float(0x7f800000);
             idx[r] = (j < nf) ? nc + j : -1;
         }
         if (!sorted) {
@@ -803,9 +832,9 @@ __global__ void __launch_bounds__(128) resample_merge_sorted_kernel(const float*
     }
 }
 
-extern "C" int nerf_resample_merge(const float* t, const float* weights, const float* u, int64_t batch, int nc, int nf,
-                                   float* t_all, int32_t* src_idx, void* stream) {
-    NERF_CHECK_ARG(t && weights && u && t_all && batch >= 0 && nc >= 2 && nf >= 1, "bad arguments");
+namespace nerf {
+int resample_merge(const float* t, const float* weights, PdfDraws dr, int64_t batch, int nc, int nf, float* t_all,
+                   int32_t* src_idx, cudaStream_t st) {
     if (batch == 0) return NERF_OK;
     int threads = 128;
     if (nf <= 256 && nc <= 1024) {
@@ -813,12 +842,11 @@ extern "C" int nerf_resample_merge(const float* t, const float* weights, const f
         const int fi = nf <= 32 ? 1 : nf <= 64 ? 2 : nf <= 128 ? 4 : 8;
         size_t smem_fast = (size_t)(threads / 32) * ((2 * nc + 2) + nc + 32 * fi) * sizeof(float);
         const int grid = stream_grid(batch * 32, threads);
-        cudaStream_t st = (cudaStream_t)stream;
         if (smem_fast <= 48 * 1024) {
-            if (fi == 1) resample_merge_sorted_kernel<1><<<grid, threads, smem_fast, st>>>(t, weights, u, batch, nc, nf, t_all, src_idx);
-            else if (fi == 2) resample_merge_sorted_kernel<2><<<grid, threads, smem_fast, st>>>(t, weights, u, batch, nc, nf, t_all, src_idx);
-            else if (fi == 4) resample_merge_sorted_kernel<4><<<grid, threads, smem_fast, st>>>(t, weights, u, batch, nc, nf, t_all, src_idx);
-            else resample_merge_sorted_kernel<8><<<grid, threads, smem_fast, st>>>(t, weights, u, batch, nc, nf, t_all, src_idx);
+            if (fi == 1) resample_merge_sorted_kernel<1><<<grid, threads, smem_fast, st>>>(t, weights, dr, batch, nc, nf, t_all, src_idx);
+            else if (fi == 2) resample_merge_sorted_kernel<2><<<grid, threads, smem_fast, st>>>(t, weights, dr, batch, nc, nf, t_all, src_idx);
+            else if (fi == 4) resample_merge_sorted_kernel<4><<<grid, threads, smem_fast, st>>>(t, weights, dr, batch, nc, nf, t_all, src_idx);
+            else resample_merge_sorted_kernel<8><<<grid, threads, smem_fast, st>>>(t, weights, dr, batch, nc, nf, t_all, src_idx);
             NERF_LAUNCHED();
             return NERF_OK;
         }
@@ -829,10 +857,32 @@ extern "C" int nerf_resample_merge(const float* t, const float* weights, const f
     NERF_CHECK_ARG(smem <= 96 * 1024, "nc+nf too large");
     if (smem > 48 * 1024)
         NERF_CUDA(cudaFuncSetAttribute(resample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    resample_merge_kernel<<<stream_grid(batch * 32, threads), threads, smem, (cudaStream_t)stream>>>(
-        t, weights, u, batch, nc, nf, P, t_all, src_idx);
+    resample_merge_kernel<<<stream_grid(batch * 32, threads), threads, smem, st>>>(t, weights, dr, batch, nc, nf, P, t_all,
+                                                                                  src_idx);
     NERF_LAUNCHED();
     return NERF_OK;
+}
+}  // namespace nerf
+
+// test hook: the uniforms the in-kernel generator hands to sample_pdf for (seed, counter)
+__global__ void __launch_bounds__(256) pdf_draws_kernel(PdfDraws dr, int64_t B, int nf, float* __restrict__ out) {
+    const unsigned long long step = pdf_step(dr);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B * nf; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = pdf_draw(dr, step, i / nf, nf, (int)(i % nf));
+}
+extern "C" int nerf_debug_pdf_draws(uint64_t seed, uint64_t counter, int64_t batch, int nf, float* out, void* stream) {
+    NERF_CHECK_ARG(out && batch >= 1 && nf >= 1, "bad arguments");
+    pdf_draws_kernel<<<stream_grid(batch * nf, 256), 256, 0, (cudaStream_t)stream>>>(PdfDraws{nullptr, seed, counter, nullptr},
+                                                                                   batch, nf, out);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+
+extern "C" int nerf_resample_merge(const float* t, const float* weights, const float* u, int64_t batch, int nc, int nf,
+                                   float* t_all, int32_t* src_idx, void* stream) {
+    NERF_CHECK_ARG(t && weights && u && t_all && batch >= 0 && nc >= 2 && nf >= 1, "bad arguments");
+    return nerf::resample_merge(t, weights, PdfDraws{u, 0ull, 0ull, nullptr}, batch, nc, nf, t_all, src_idx,
+                                (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -843,7 +893,7 @@ extern "C" int nerf_resample_merge(const float* t, const float* weights, const f
 __global__ void __launch_bounds__(1024) metrics_kernel(const float* __restrict__ img, const float* __restrict__ rc,
                                                        const float* __restrict__ rf, int64_t n_el,
                                                        float* __restrict__ metrics, float* __restrict__ d_rc,
-                                                       float* __restrict__ d_rf) {
+                                                       float* __restrict__ d_rf, float* __restrict__ sums) {
     __shared__ float sc[32], sf[32];
     float ac = 0.f, af = 0.f;
     const float scale = 2.0f / (float)n_el;
@@ -864,20 +914,27 @@ __global__ void __launch_bounds__(1024) metrics_kernel(const float* __restrict__
         ac = warp_sum(ac); af = warp_sum(af);
         if (lane == 0) {
             float mc = ac / (float)n_el, mf = af / (float)n_el;
+            const float ps = -10.0f * log10f(mf);
             metrics[0] = mc;
             metrics[1] = mf;
-            metrics[2] = -10.0f * log10f(mf);
+            metrics[2] = ps;
+            if (sums) { sums[0] += mc; sums[1] += mf; sums[2] += ps; sums[3] += 1.0f; }   // keras.metrics.Mean (models.py:113-115)
         }
     }
 }
 
-extern "C" int nerf_metrics_grad(const float* images, const float* rgb_c, const float* rgb_f, int64_t batch,
-                                 float* metrics_dev, float* d_rgb_c, float* d_rgb_f, void* stream) {
+// rgb_f == rgb_c is the single-net shape (NS_FINE = 0): loss and psnr then describe the only net there is
+extern "C" int nerf_metrics_grad_sums(const float* images, const float* rgb_c, const float* rgb_f, int64_t batch,
+                                      float* metrics_dev, float* d_rgb_c, float* d_rgb_f, float* sums, void* stream) {
     NERF_CHECK_ARG(images && rgb_c && rgb_f && metrics_dev && batch >= 1, "bad arguments");
     metrics_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(images, rgb_c, rgb_f, batch * 3, metrics_dev, d_rgb_c,
-                                                         d_rgb_f);
+                                                         d_rgb_f, sums);
     NERF_LAUNCHED();
     return NERF_OK;
+}
+extern "C" int nerf_metrics_grad(const float* images, const float* rgb_c, const float* rgb_f, int64_t batch,
+                                 float* metrics_dev, float* d_rgb_c, float* d_rgb_f, void* stream) {
+    return nerf_metrics_grad_sums(images, rgb_c, rgb_f, batch, metrics_dev, d_rgb_c, d_rgb_f, nullptr, stream);
 }
 
 extern "C" int nerf_metrics(const float* images, const float* rgb_c, const float* rgb_f, int64_t batch,
@@ -892,7 +949,17 @@ extern "C" int nerf_metrics(const float* images, const float* rgb_c, const float
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                    float alpha_t, float one_minus_b1, float one_minus_b2, float eps,
-                                                   float grad_scale) {
+                                                   float grad_scale, const nerf_dev_state* __restrict__ ds) {
+    if (ds) {
+        // step count and learning rate live in device memory (CUDA-graph replays): alpha_t of update t = step + 1
+        __shared__ float s_alpha;
+        if (threadIdx.x == 0) {
+            const double tt = (double)(ds->step + 1ull);
+            s_alpha = (float)((double)ds->lr * sqrt(1.0 - pow(0.999, tt)) / (1.0 - pow(0.9, tt)));
+        }
+        __syncthreads();
+        alpha_t = s_alpha;
+    }
     const int64_t n_vec = n >> 2;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
         float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -927,10 +994,26 @@ extern "C" int nerf_adam_flat(float* params, const float* grads, float* m, float
     const double b1 = 0.9, b2 = 0.999;
     double alpha = (double)lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step));
     adam_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
-        params, grads, m, v, n, (float)alpha, (float)(1.0 - b1), (float)(1.0 - b2), 1e-7f, grad_scale);
+        params, grads, m, v, n, (float)alpha, (float)(1.0 - b1), (float)(1.0 - b2), 1e-7f, grad_scale, nullptr);
     NERF_LAUNCHED();
     return NERF_OK;
 }
+
+namespace nerf {
+// the same update with t and the learning rate read from the context's device state (graph-replayable)
+int adam_from_dev_state(float* params, const float* grads, float* m, float* v, int64_t n, const nerf_dev_state* ds,
+                        float grad_scale, cudaStream_t st) {
+    adam_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, st>>>(params, grads, m, v, n, 0.f, (float)(1.0 - 0.9),
+                                                             (float)(1.0 - 0.999), 1e-7f, grad_scale, ds);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+    return cs != cudaStreamCaptureStatusNone;
+}
+}  // namespace nerf
 
 // ------------------------------------------------------------------------------------------------
 // kernel timing hooks
@@ -944,7 +1027,7 @@ struct TimedSpan { int kind; cudaEvent_t a, b; };
 static std::vector<TimedSpan> g_spans;
 static std::vector<cudaEvent_t> g_open[8];
 void timing_begin(int kind, cudaStream_t st) {
-    if (!g_timing_on) return;
+    if (!g_timing_on || stream_is_capturing(st)) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, st);
@@ -952,7 +1035,7 @@ void timing_begin(int kind, cudaStream_t st) {
     g_open[kind & 7].push_back(e);
 }
 void timing_end(int kind, cudaStream_t st) {
-    if (!g_timing_on) return;
+    if (!g_timing_on || stream_is_capturing(st)) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, st);

@@ -2,14 +2,19 @@
 reference's signatures, running on the sm_100a kernels of libnerf_b200.so (no Keras, no TF).
 
 Differences that are forced by the platform and documented in DESIGN.md:
-  * random draws (`u_pdf` for sample_pdf) may be passed explicitly; otherwise torch's CUDA RNG;
-  * BATCH_NORM=true configs are rejected (out of scope this round);
-  * weights are saved as `.npz` keyed by layer role (h5py is not available).
+  * random draws (`u_pdf` for sample_pdf) may be passed explicitly; otherwise they are generated inside the resampling
+    kernel (Philox keyed by `set_random_seed`, the optimiser step / call counter, the ray and the draw index);
+  * BATCH_NORM=true models render on the fused kernels (inference affine folded into the Dense weights) and train on a
+    separate layer-by-layer fp32 path (csrc/bn_train.cu);
+  * weights are saved as `.npz` keyed by layer role (h5py is not available);
+  * the training step is replayed from a CUDA graph once its input buffers have been seen twice (no per-kernel launch
+    cost, no host work between kernels).
 """
 from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from typing import Dict, Iterable, List, Optional, Tuple
 
 import numpy as np
@@ -21,12 +26,13 @@ from .data_utils import _dev, _f32, _ptr, _stream
 PRECISION_BF16_TC = 0
 PRECISION_FP32 = 1
 
-_seed_state = {"rng": np.random.default_rng(42)}
+_seed_state = {"rng": np.random.default_rng(42), "seed": 42}
 
 
 def set_random_seed(seed: int):
     """keras.utils.set_random_seed (train_lego.py:22)."""
     _seed_state["rng"] = np.random.default_rng(seed)
+    _seed_state["seed"] = int(seed)
     torch.manual_seed(seed)
     if torch.cuda.is_available():
         torch.cuda.manual_seed_all(seed)
@@ -56,7 +62,19 @@ class Adam:
     def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
         if (beta_1, beta_2, epsilon) != (0.9, 0.999, 1e-7):
             raise ValueError("the fused Adam kernel implements the Keras defaults beta_1=0.9, beta_2=0.999, epsilon=1e-7")
-        self.learning_rate = float(learning_rate)
+        self._lr = float(learning_rate)
+        self._trainer = None
+
+    @property
+    def learning_rate(self) -> float:
+        return self._lr
+
+    @learning_rate.setter
+    def learning_rate(self, value):
+        self._lr = float(value)
+        tr = self._trainer() if self._trainer is not None else None
+        if tr is not None:
+            tr._learning_rate_changed()
 
 
 class MeanSquaredError:
@@ -67,21 +85,77 @@ class MeanSquaredError:
 
 
 class _Mean:
-    """keras.metrics.Mean stand-in.  Values may be 0-d CUDA tensors: they are accumulated on the device and only
-    read back (one synchronisation) when `result()` is converted to a Python number."""
+    """keras.metrics.Mean stand-in.  With `bind(sums, i)` the sum and the count live in the context's device buffer
+    (float[4]: three sums + step count, updated by the metrics kernel itself), so a step enqueues no extra kernels and
+    `result()` costs one 16-byte read when somebody asks for the number."""
 
     def __init__(self, name):
-        self.name, self.total, self.count = name, 0.0, 0
+        self.name, self.total, self.count, self._sums, self._i = name, 0.0, 0, None, 0
+
+    def bind(self, sums: Optional[torch.Tensor], i: int):
+        self._sums, self._i = sums, i
 
     def update_state(self, v):
         self.total = self.total + v
         self.count += 1
 
     def result(self):
+        if self._sums is not None:
+            h = self._sums.tolist()
+            return h[self._i] / h[3] if h[3] else 0.0
         return self.total / self.count if self.count else 0.0
 
     def reset_state(self):
         self.total, self.count = 0.0, 0
+        if self._sums is not None:
+            self._sums.zero_()
+
+
+class _Lazy:
+    """A metric value that is read back from the device only when it is converted to a number."""
+
+    def __init__(self, mean: _Mean):
+        self._m = mean
+
+    def __float__(self):
+        return float(self._m.result())
+
+    def item(self):
+        return float(self)
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def __repr__(self):
+        return f"{float(self):.6g}"
+
+    # plain-number behaviour for callers that do arithmetic on the logs
+    def __add__(self, o): return float(self) + o
+    def __radd__(self, o): return o + float(self)
+    def __sub__(self, o): return float(self) - o
+    def __rsub__(self, o): return o - float(self)
+    def __mul__(self, o): return float(self) * o
+    def __rmul__(self, o): return o * float(self)
+    def __truediv__(self, o): return float(self) / o
+    def __neg__(self): return -float(self)
+    def __abs__(self): return abs(float(self))
+    def __lt__(self, o): return float(self) < o
+    def __le__(self, o): return float(self) <= o
+    def __gt__(self, o): return float(self) > o
+    def __ge__(self, o): return float(self) >= o
+
+
+def _timing_on() -> bool:
+    """bench.py's per-kernel CUDA-event timers bracket individual launches: such steps run eagerly."""
+    return bool(_timing_state["on"])
+
+
+_timing_state = {"on": False}
+
+
+def set_kernel_timing(on: bool):
+    _timing_state["on"] = bool(on)
+    _lib.check(_lib.lib().nerf_timing_enable(1 if on else 0), "nerf_timing_enable")
 
 
 class _Ctx:
@@ -108,19 +182,42 @@ class _Ctx:
         _lib.check(_lib.lib().nerf_get_weights(self.handle, net, _ptr(out), out.numel(), _stream()), "nerf_get_weights")
         return out
 
+    @staticmethod
+    def _view(ptr: int, n: int) -> torch.Tensor:
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+        return torch.as_tensor(_Raw(), device=_dev())
+
     def grad_tensor(self) -> torch.Tensor:
         """Zero-copy torch view of the ctx-owned flat gradient buffer [coarse | fine]."""
-        p, n = C.c_void_p(), C.c_int64()
-        _lib.check(_lib.lib().nerf_grad_buffer(self.handle, C.byref(p), C.byref(n)), "nerf_grad_buffer")
+        if getattr(self, "_grad_view", None) is None:
+            p, n = C.c_void_p(), C.c_int64()
+            _lib.check(_lib.lib().nerf_grad_buffer(self.handle, C.byref(p), C.byref(n)), "nerf_grad_buffer")
+            self._grad_view = self._view(p.value, n.value)
+        return self._grad_view
 
-        class _Raw:
-            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (p.value, False), "version": 3}
+    def metric_sums(self) -> torch.Tensor:
+        """Zero-copy view of the running metric sums (loss_coarse, loss, psnr, count)."""
+        if getattr(self, "_sums_view", None) is None:
+            p = C.c_void_p()
+            _lib.check(_lib.lib().nerf_metric_sums(self.handle, C.byref(p)), "nerf_metric_sums")
+            self._sums_view = self._view(p.value, 4)
+        return self._sums_view
 
-        self._raw_keepalive = _Raw()
-        return torch.as_tensor(self._raw_keepalive, device=_dev())
+    def optimizer_state(self):
+        m = torch.empty((2 * self.n_params,), device=_dev(), dtype=torch.float32)
+        v = torch.empty_like(m)
+        step = C.c_int64()
+        _lib.check(_lib.lib().nerf_get_optimizer_state(self.handle, _ptr(m), _ptr(v), C.byref(step), _stream()), "optimizer state")
+        return m, v, int(step.value)
+
+    def set_optimizer_state(self, m, v, step):
+        _lib.check(_lib.lib().nerf_set_optimizer_state(self.handle, _ptr(m), _ptr(v), int(step), _stream()), "optimizer state")
 
     def close(self):
         if self.handle:
+            self._grad_view = self._sums_view = None
             _lib.lib().nerf_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -152,10 +249,11 @@ class NerfModel:
         self._host_blob = np.concatenate(parts)
         self._owner: Optional[Tuple[_Ctx, int]] = None
         self._own_ctx: Optional[_Ctx] = None
+        self._bn_trainer = None      # weakref to the NeRFTrainer that holds this model's BATCH_NORM training state
         # BATCH_NORM=true (models.py:30-33, 49-52): one BatchNormalization after every trunk Dense and after the
-        # direction Dense.  INFERENCE only: the moving statistics are folded into the Dense weights on the host,
+        # direction Dense.  For rendering the moving statistics are folded into the Dense weights on the host,
         #   y = ((xW + b) - mean) * gamma / sqrt(var + eps) + beta  =  x (W s) + ((b - mean) s + beta),  s = gamma / sqrt(var + eps)
-        # so the device kernels are unchanged.  Training with batch statistics is not supported.
+        # so the fused kernels are unchanged; training with batch statistics runs in NeRFTrainer (csrc/bn_train.cu).
         self.bn: Optional[Dict[str, Dict[str, np.ndarray]]] = None
         if bn:
             self.bn = {role: {"gamma": np.ones(fo, np.float32), "beta": np.zeros(fo, np.float32),
@@ -166,9 +264,15 @@ class NerfModel:
     def count_params(self) -> int:
         return int(self._host_blob.size)
 
+    def _bn_owner(self):
+        return self._bn_trainer() if self._bn_trainer is not None else None
+
     def get_flat_weights(self) -> np.ndarray:
         """The Dense kernels and biases (un-folded when BATCH_NORM=true)."""
-        if self._owner is not None and self.bn is None:      # a BN model is never trained here: the host copy is the truth
+        tr = self._bn_owner()
+        if tr is not None:
+            tr._bn_sync_models()                             # device training state -> host copies
+        if self._owner is not None and self.bn is None:      # a BN model's device blob is FOLDED: its host copy is the truth
             ctx, net = self._owner
             self._host_blob = ctx.get_weights(net).cpu().numpy()
         return self._host_blob.copy()
@@ -203,8 +307,14 @@ class NerfModel:
             raise ValueError(f"expected {self._host_blob.size} floats, got {blob.size}")
         self._host_blob = blob.copy()
         self._push()
+        tr = self._bn_owner()
+        if tr is not None:
+            tr._bn_mark_stale()                              # the trainer re-uploads its training copy before the next step
 
     def get_bn_params(self) -> Optional[Dict[str, Dict[str, np.ndarray]]]:
+        tr = self._bn_owner()
+        if tr is not None:
+            tr._bn_sync_models()
         return None if self.bn is None else {r: {k: v.copy() for k, v in st.items()} for r, st in self.bn.items()}
 
     def set_bn_params(self, params: Dict[str, Dict[str, np.ndarray]]):
@@ -218,6 +328,9 @@ class NerfModel:
                     raise ValueError(f"bad shape for {role}/{k}")
                 st[k] = v.copy()
         self._push()
+        tr = self._bn_owner()
+        if tr is not None:
+            tr._bn_mark_stale()
 
     def get_weights(self) -> Dict[str, Dict[str, np.ndarray]]:
         blob, out, off = self.get_flat_weights(), {}, 0
@@ -240,7 +353,11 @@ class NerfModel:
     # -- call -------------------------------------------------------------------------------------
     def __call__(self, inputs, training=False):
         if training and self.bn is not None:
-            raise NotImplementedError("BATCH_NORM=true is inference-only on the B200 path (batch statistics are not computed)")
+            raise NotImplementedError("training-mode calls of a BATCH_NORM=true model go through NeRFTrainer.train_step "
+                                      "(batch statistics are computed by the trainer's layer-by-layer path)")
+        tr = self._bn_owner()
+        if tr is not None:
+            tr._bn_sync_models()
         rays_enc, dirs_enc = inputs
         x, dd = _f32(rays_enc), _f32(dirs_enc)
         ex, ed = 3 + 6 * self.arch["lxyz"], 3 + 6 * self.arch["ldir"]
@@ -270,8 +387,11 @@ def create_nerf_complete_model(num_layers, hidden_dim, skip_layer, lxyz, ldir, b
 class NeRFTrainer:
     """models.py:64-225 -- coarse->fine forward pass, train/test steps, minibatched rendering."""
 
+    MAX_GRAPHS = 16          # captured training-step graphs kept per trainer (one per distinct set of input buffers)
+
     def __init__(self, coarse_model, fine_model, batch_size, ns_coarse, ns_fine, l_xyz, l_dir,
-                 precision=PRECISION_BF16_TC, stop_grad_samples=False, process_group=None):
+                 precision=PRECISION_BF16_TC, stop_grad_samples=False, process_group=None, use_cuda_graph=True,
+                 overlap_allreduce=True):
         if not isinstance(coarse_model, NerfModel):
             raise TypeError("coarse_model must be a NerfModel (create_nerf_complete_model) instance")
         if not isinstance(fine_model, NerfModel):
@@ -284,9 +404,16 @@ class NeRFTrainer:
         self.precision = precision
         self.stop_grad_samples = bool(stop_grad_samples)
         self.process_group = process_group
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self.overlap_allreduce = bool(overlap_allreduce)
         self.optimizer = None
         self.loss_fn = None
         self._ctx: Optional[_Ctx] = None
+        self._bn_state = None
+        self._graphs: Dict[tuple, tuple] = {}
+        self._seen: Dict[tuple, int] = {}
+        self._metrics_buf: Optional[torch.Tensor] = None
+        self._seed = _seed_state["seed"]
         self.loss_coarse_tracker = _Mean("loss_coarse")
         self.loss_tracker = _Mean("loss")
         self.psnr_tracker = _Mean("psnr")
@@ -298,9 +425,19 @@ class NeRFTrainer:
             raise TypeError("optimizer must be nerf_keras_b200.models.Adam")
         if (self.coarse_model.bn is None) != (self.fine_model.bn is None):
             raise ValueError("coarse and fine model must both be created with the same bn flag")
+        if not isinstance(loss_fn, MeanSquaredError):
+            raise TypeError("loss_fn must be nerf_keras_b200.models.MeanSquaredError (the kernels compute the reference's "
+                            "MSE(images, rgb_coarse) + MSE(images, rgb_fine), models.py:98-102)")
         self.optimizer, self.loss_fn = optimizer, loss_fn
+        optimizer._trainer = weakref.ref(self)
         self._bn_state = None
         if self.coarse_model.bn is not None:
+            if self.coarse_model.arch["hidden_dim"] % 4:
+                raise ValueError("BATCH_NORM training needs HIDDEN_DIM % 4 == 0 (16-byte aligned parameter blocks)")
+            if not self.stop_grad_samples:
+                import warnings
+                warnings.warn("BATCH_NORM=true training stops the gradient at the fine sample positions: the reference's "
+                              "un-stopped term (models.py:166-175) is not carried through this path (DESIGN.md)")
             # BATCH_NORM=true: batch statistics couple all samples of a batch between consecutive layers, so training
             # runs on the layer-by-layer fp32 path (csrc/bn_train.cu); rendering keeps the fused kernels (folded BN).
             if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -309,6 +446,8 @@ class NeRFTrainer:
             self.optimizer = optimizer
             self._rebuild_ctx_inference_only()
             self._bn_init_state()
+            for m in (self.coarse_model, self.fine_model):
+                m._bn_trainer = weakref.ref(self)
             return
         self._rebuild_ctx()
 
@@ -336,14 +475,39 @@ class NeRFTrainer:
         nbn = bn.numel() // 8
         z = lambda k: torch.zeros(k, device=dev, dtype=torch.float32)
         self._bn_state = dict(params=params, bn=bn, n=n, nbn=nbn, roles=roles, grads=z(2 * n), bn_grads=z(4 * nbn),
-                              m=z(2 * n), v=z(2 * n), bm=z(8 * nbn), bv=z(8 * nbn), step=0, ws=None, ws_rays=0, dirty=False)
+                              m=z(2 * n), v=z(2 * n), bm=z(8 * nbn), bv=z(8 * nbn), step=0, ws=None, ws_rays=0, dirty=False,
+                              stale=False, syncing=False)
+
+    def _bn_mark_stale(self):
+        """A model's weights / BN parameters were set from outside (load_weights, set_weights ...): the device training
+        copy is re-uploaded from the models before the next step (the Adam moments are kept)."""
+        st = getattr(self, "_bn_state", None)
+        if st and not st.get("syncing"):
+            st["stale"] = True
+
+    def _bn_refresh_state(self):
+        st = self._bn_state
+        dev = st["params"].device
+        models = (self.coarse_model, self.fine_model)
+        pack = lambda m, k: np.concatenate([m.bn[r][k] for r in st["roles"]]).astype(np.float32)
+        st["params"].copy_(torch.from_numpy(np.concatenate([m._host_blob for m in models])).to(dev))
+        st["bn"].copy_(torch.from_numpy(np.concatenate([np.concatenate([pack(m, k) for k in ("gamma", "beta", "mean", "var")])
+                                                        for m in models])).to(dev))
+        st["stale"] = False
 
     def _bn_sync_models(self):
         """Device training state -> the two models (un-folded weights + BN parameters) -> folded weights of the render ctx."""
         st = getattr(self, "_bn_state", None)
-        if not st or not st["dirty"]:
+        if not st or not st["dirty"] or st.get("syncing"):
             return
         st["dirty"] = False
+        st["syncing"] = True
+        try:
+            self._bn_sync_models_locked(st)
+        finally:
+            st["syncing"] = False
+
+    def _bn_sync_models_locked(self, st):
         params, bn = st["params"].cpu().numpy(), st["bn"].cpu().numpy()
         n, nbn = st["n"], st["nbn"]
         for i, m in enumerate((self.coarse_model, self.fine_model)):
@@ -358,6 +522,8 @@ class NeRFTrainer:
 
     def _bn_train_step(self, images, o, d, t, u):
         st = self._bn_state
+        if st.get("stale"):
+            self._bn_refresh_state()
         B = o.shape[0]
         L = _lib.lib()
         cfg = self._ctx.cfg
@@ -382,15 +548,32 @@ class NeRFTrainer:
         for m in (self.coarse_model, self.fine_model):
             m.get_flat_weights()                              # refresh the host copies from the old ctx
         blobs = [np.ascontiguousarray(self.coarse_model.device_blob()), np.ascontiguousarray(self.fine_model.device_blob())]
-        if self._ctx is not None:
-            self._ctx.close()
         training = self.optimizer is not None
+        opt_state = None
+        if self._ctx is not None:
+            if training and self._ctx.cfg.training:
+                opt_state = self._ctx.optimizer_state()       # Adam moments and step survive a workspace resize
+                torch.cuda.current_stream().synchronize()
+            self._graphs.clear()
+            self._seen.clear()
+            self._ctx.close()
         lr = self.optimizer.learning_rate if training else 0.0
         self._ctx = _Ctx(self.coarse_model.arch, self.ns_coarse, self.ns_fine, max_rays or self.batch_size, training, lr,
                          self.stop_grad_samples)
+        _lib.check(_lib.lib().nerf_set_seed(self._ctx.handle, int(self._seed) & 0xFFFFFFFFFFFFFFFF), "nerf_set_seed")
         for net, (m, blob) in enumerate(zip((self.coarse_model, self.fine_model), blobs)):
             m._owner = (self._ctx, net)
             self._ctx.set_weights(net, torch.from_numpy(blob))
+        if opt_state is not None:
+            self._ctx.set_optimizer_state(*opt_state)
+        sums = self._ctx.metric_sums() if getattr(self, "_bn_state", None) is None else None
+        for i, tr in enumerate((self.loss_coarse_tracker, self.loss_tracker, self.psnr_tracker)):
+            tr.bind(sums, i)
+
+    def _learning_rate_changed(self):
+        if self._ctx is not None and self._ctx.cfg.training:
+            _lib.check(_lib.lib().nerf_set_learning_rate(self._ctx.handle, float(self.optimizer.learning_rate), _stream()),
+                       "set_learning_rate")
 
     @property
     def metrics(self):
@@ -409,6 +592,9 @@ class NeRFTrainer:
         out = dict(rgb_c=e(B, 3), rgb_f=e(B, 3), depth_c=e(B), depth_f=e(B))
         if not maps_only:   # per-sample outputs (weights, raw predictions, sample positions): 4.6 KB per ray
             out.update(w_c=e(B, Nc), w_f=e(B, Na), pred_c=e(B, Nc, 4), pred_f=e(B, Na, 4), t_all=e(B, Na))
+        if self.ns_fine == 0:       # single-net shape: the "fine" outputs do not exist
+            for k in ("rgb_f", "depth_f", "w_f", "pred_f", "t_all"):
+                out.pop(k, None)
         fo = _lib.ForwardOut(*[_ptr(out.get(k)) for k, _ in _lib.ForwardOut._fields_])
         _lib.check(_lib.lib().nerf_forward_pass(self._ctx.handle, _ptr(o), _ptr(d), _ptr(t), _ptr(u_pdf), B, precision,
                                                 C.byref(fo), _stream()), "forward_pass")
@@ -429,16 +615,18 @@ class NeRFTrainer:
         if t.shape != (o.shape[0], self.ns_coarse):
             raise ValueError(f"t_vals must have shape (n_rays, {self.ns_coarse})")
         B = o.shape[0]
-        u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
+        u = None if u_pdf is None else _f32(u_pdf)      # None: drawn inside the resampling kernel (data_utils.py:196)
+        if u is not None and u.shape != (B, self.ns_fine):
+            raise ValueError(f"u_pdf must have shape (n_rays, {self.ns_fine})")
         precision = self.precision if precision is None else precision
         tile = self._ctx.max_rays
-        outs = [self._forward_tile(o[s:s + tile], d[s:s + tile], t[s:s + tile], u[s:s + tile], precision, maps_only)
+        outs = [self._forward_tile(o[s:s + tile], d[s:s + tile], t[s:s + tile], None if u is None else u[s:s + tile],
+                                   precision, maps_only)
                 for s in range(0, B, tile)]
+        cat = (lambda k: None if k not in outs[0] else
+               (outs[0][k] if len(outs) == 1 else torch.cat([x[k] for x in outs], dim=0)))
         if maps_only:
-            cat = (lambda k: None if k not in outs[0] else
-                   (outs[0][k] if len(outs) == 1 else torch.cat([x[k] for x in outs], dim=0)))
             return ((cat("rgb_c"), cat("rgb_f")), (cat("depth_c"), cat("depth_f")), (None, None), (None, None))
-        cat = (lambda k: outs[0][k]) if len(outs) == 1 else (lambda k: torch.cat([x[k] for x in outs], dim=0))
         res = ((cat("rgb_c"), cat("rgb_f")), (cat("depth_c"), cat("depth_f")), (cat("w_c"), cat("w_f")),
                (cat("pred_c"), cat("pred_f")))
         return res + (cat("t_all"),) if return_t_all else res
@@ -450,13 +638,15 @@ class NeRFTrainer:
             self._rebuild_ctx()
         o, d, t = _f32(ray_origins), _f32(ray_directions), _f32(t_vals)
         B, N = t.shape
-        if B > self._ctx.max_rays:
-            self._rebuild_ctx(max_rays=B)
         idx = {"coarse": 0, "fine": 1}[net]
         precision = self.precision if precision is None else precision
         out = torch.empty((B, N, 4), device=o.device, dtype=torch.float32)
-        _lib.check(_lib.lib().nerf_mlp_forward_rays(self._ctx.handle, idx, _ptr(o), _ptr(d), _ptr(t), B, N, precision,
-                                                    _ptr(out), _stream()), "mlp_forward_rays")
+        tile = self._ctx.max_rays                       # larger inputs are tiled: the context (and Adam's state) stays
+        for s0 in range(0, B, tile):
+            n = min(tile, B - s0)
+            _lib.check(_lib.lib().nerf_mlp_forward_rays(self._ctx.handle, idx, _ptr(o[s0:s0 + n]), _ptr(d[s0:s0 + n]),
+                                                        _ptr(t[s0:s0 + n]), n, N, precision, _ptr(out[s0:s0 + n]),
+                                                        _stream()), "mlp_forward_rays")
         return out
 
     def debug_mlp_grads(self, net, ray_origins, ray_directions, t_vals, d_preds, return_input_grad=False):
@@ -483,16 +673,50 @@ class NeRFTrainer:
         """models.py:178-225 -- ray-tile loop; tiles are `batch_size` rays (capped by the workspace)."""
         o, d, t = _f32(ray_origins), _f32(ray_directions), _f32(t_vals)
         B = o.shape[0]
-        u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
+        u = None if u_pdf is None else _f32(u_pdf)
         outs = [self.forward_pass(o[s:s + batch_size], d[s:s + batch_size], t[s:s + batch_size], l_xyz, l_dir,
-                                  training=training, u_pdf=u[s:s + batch_size], precision=precision, maps_only=maps_only)
+                                  training=training, u_pdf=None if u is None else u[s:s + batch_size], precision=precision,
+                                  maps_only=maps_only)
                 for s in range(0, B, batch_size)]
         cat = lambda i, j: None if outs[0][i][j] is None else torch.cat([x[i][j] for x in outs], dim=0)
         return tuple((cat(i, 0), cat(i, 1)) for i in range(4))
 
     # -- steps ------------------------------------------------------------------------------------
+    def _world(self) -> int:
+        if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            return torch.distributed.get_world_size(self.process_group)
+        return 1
+
+    def _step_body(self, images, o, d, t, u, B, accumulate=False, grad_scale=1.0, apply=True):
+        """One training step enqueued on the current stream: forward, loss, backward, gradient all-reduce, Adam.
+        No host synchronisation and no allocation: this is what the CUDA graph captures."""
+        L, h = _lib.lib(), self._ctx.handle
+        args = (h, _ptr(images), _ptr(o), _ptr(d), _ptr(t), _ptr(u), B, _ptr(self._metrics_buf))
+        acc = 4 if accumulate else 0
+        world = self._world()
+        if world == 1 or not apply:
+            _lib.check(L.nerf_train_phases(*args, 3 | acc, _stream()), "train_step")
+        else:
+            import torch.distributed as dist
+            g, n = self._ctx.grad_tensor(), self._ctx.n_params
+            if self.overlap_allreduce and self.ns_fine > 0:
+                # the fine net's half of the flat gradient buffer is complete after phase 0: reduce it over NVLink while
+                # the coarse net's backward still runs (SURVEY 5.8); the collective runs on NCCL's own stream
+                _lib.check(L.nerf_train_phases(*args, 1 | acc, _stream()), "train_step (forward + fine backward)")
+                w_fine = dist.all_reduce(g[n:], op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+                _lib.check(L.nerf_train_phases(*args, 2 | acc, _stream()), "train_step (coarse backward)")
+                dist.all_reduce(g[:n], op=dist.ReduceOp.SUM, group=self.process_group)
+                w_fine.wait()
+            else:
+                _lib.check(L.nerf_train_phases(*args, 3 | acc, _stream()), "train_step")
+                dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.process_group)
+            grad_scale = grad_scale / world
+        if apply:
+            _lib.check(L.nerf_adam_step(h, float(grad_scale), _stream()), "adam_step")
+
     def train_step(self, inputs, u_pdf=None):
-        """models.py:88-120.  inputs = (images (B,3), (ray_origins, ray_directions, t_vals))."""
+        """models.py:88-120.  inputs = (images (B,3), (ray_origins, ray_directions, t_vals)).
+        u_pdf=None (production): the uniform draws of sample_pdf are generated inside the kernels."""
         if self.optimizer is None:
             raise RuntimeError("call compile(optimizer, loss_fn) before train_step")
         images, (o, d, t) = inputs
@@ -501,31 +725,74 @@ class NeRFTrainer:
         if getattr(self, "_bn_state", None) is not None:
             u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
             return self._bn_train_step(images, o, d, t, u)
-        if B > self._ctx.max_rays:
-            self._rebuild_ctx(max_rays=B)
-        u = torch.rand((B, self.ns_fine), device=o.device, dtype=torch.float32) if u_pdf is None else _f32(u_pdf)
-        metrics = torch.empty((3,), device=o.device, dtype=torch.float32)
-        L = _lib.lib()
-        _lib.check(L.nerf_train_forward_backward(self._ctx.handle, _ptr(images), _ptr(o), _ptr(d), _ptr(t), _ptr(u), B,
-                                                 _ptr(metrics), _stream()), "train_step")
-        scale = 1.0
-        if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                              and torch.distributed.get_world_size() > 1):
-            from .dist import allreduce_sum_
-            world = allreduce_sum_(self._ctx.grad_tensor(), self.process_group)
-            scale = 1.0 / world
-        _lib.check(L.nerf_adam_step(self._ctx.handle, scale, _stream()), "adam_step")
-        return self._update_metrics(metrics)     # stays on the device: no host synchronisation inside the step
+        if t.shape != (B, self.ns_coarse) or images.shape != (B, 3):
+            raise ValueError(f"expected images (n_rays, 3) and t_vals (n_rays, {self.ns_coarse})")
+        u = None if u_pdf is None else _f32(u_pdf)
+        if self._metrics_buf is None or self._metrics_buf.device != o.device:
+            self._metrics_buf = torch.empty((3,), device=o.device, dtype=torch.float32)
+        cap = self._ctx.max_rays
+        if B > cap:
+            # a batch larger than the workspace: equal micro-batches, gradients accumulated in the context, one update.
+            # mean over the batch = mean of the micro-batch means (the metrics are averaged the same way)
+            if B % cap:
+                raise ValueError(f"a batch of {B} rays must be a multiple of the context's {cap}-ray workspace")
+            k = B // cap
+            for i in range(k):
+                sl = slice(i * cap, (i + 1) * cap)
+                self._step_body(images[sl], o[sl], d[sl], t[sl], None if u is None else u[sl], cap, accumulate=i > 0,
+                                grad_scale=1.0 / k, apply=(i == k - 1))
+            return self._logs()
+        key = (images.data_ptr(), o.data_ptr(), d.data_ptr(), t.data_ptr(), 0 if u is None else u.data_ptr(), B)
+        if self.use_cuda_graph and not _timing_on():
+            entry = self._graphs.get(key)
+            if entry is None and self._seen.get(key, 0) >= 1 and len(self._graphs) < self.MAX_GRAPHS:
+                entry = self._capture(key, images, o, d, t, u, B)
+            if entry is not None:
+                entry[0].replay()
+                return self._logs()
+            self._seen[key] = self._seen.get(key, 0) + 1
+            if len(self._seen) > 4096:
+                self._seen.clear()
+        self._step_body(images, o, d, t, u, B)
+        return self._logs()     # stays on the device: no host synchronisation inside the step
+
+    def _capture(self, key, images, o, d, t, u, B):
+        """Capture one training step on these input buffers.  The buffers are kept alive with the graph; the step count,
+        the learning rate and the random draws are read from device memory, so every replay is a fresh step."""
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.current_stream().synchronize()
+        try:
+            with torch.cuda.graph(g):
+                self._step_body(images, o, d, t, u, B)
+        except Exception:
+            # a failed capture leaves no partial update behind (nothing was executed); fall back to eager for this key
+            self._seen[key] = -(1 << 30)
+            torch.cuda.synchronize()
+            return None
+        # capturing does not execute: the host-side mirror of the step count was advanced once by nerf_adam_step
+        self._graphs[key] = (g, (images, o, d, t, u))
+        return self._graphs[key]
 
     def test_step(self, inputs, u_pdf=None):
         """models.py:122-145."""
         images, (o, d, t) = inputs
         images = _f32(images)
-        rgbs, _, _, _ = self.forward_pass(o, d, t, u_pdf=u_pdf)
+        rgbs, _, _, _ = self.forward_pass(o, d, t, u_pdf=u_pdf, maps_only=True)
         metrics = torch.empty((3,), device=images.device, dtype=torch.float32)
-        _lib.check(_lib.lib().nerf_metrics(_ptr(images), _ptr(rgbs[0]), _ptr(rgbs[1]), images.shape[0], _ptr(metrics),
-                                           _stream()), "test_step")
-        return self._update_metrics(metrics)
+        rgb_f = rgbs[1] if rgbs[1] is not None else rgbs[0]
+        if getattr(self, "_bn_state", None) is not None:
+            _lib.check(_lib.lib().nerf_metrics(_ptr(images), _ptr(rgbs[0]), _ptr(rgb_f), images.shape[0], _ptr(metrics),
+                                               _stream()), "test_step")
+            return self._update_metrics(metrics)
+        _lib.check(_lib.lib().nerf_metrics_accumulate(self._ctx.handle, _ptr(images), _ptr(rgbs[0]), _ptr(rgb_f),
+                                                      images.shape[0], _ptr(metrics), _stream()), "test_step")
+        self.last_metrics = metrics
+        return self._logs()
+
+    def _logs(self):
+        """Running means as Keras reports them (models.py:116-120); read back lazily."""
+        return {"loss_coarse": _Lazy(self.loss_coarse_tracker), "loss": _Lazy(self.loss_tracker),
+                "psnr": _Lazy(self.psnr_tracker)}
 
     def _update_metrics(self, m):
         self.loss_coarse_tracker.update_state(m[0])
@@ -542,13 +809,15 @@ class NeRFTrainer:
             logs = {}
             for batch in train_ds:
                 logs = self.train_step(batch)
+            logs = {k: float(v) for k, v in logs.items()}     # read the running means back before they are reset
             for k in ("loss", "psnr", "loss_coarse"):
-                history[k].append(float(logs[k]) if k in logs else None)
+                history[k].append(logs[k] if k in logs else None)
             if validation_data is not None:
                 self.reset_metrics()
                 vlogs = {}
                 for batch in validation_data:
                     vlogs = self.test_step(batch)
+                vlogs = {k: float(v) for k, v in vlogs.items()}
                 history["val_loss"].append(float(vlogs["loss"]) if "loss" in vlogs else None)
                 history["val_psnr"].append(float(vlogs["psnr"]) if "psnr" in vlogs else None)
                 logs = dict(logs, val_loss=vlogs.get("loss"), val_psnr=vlogs.get("psnr"))

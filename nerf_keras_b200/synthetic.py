@@ -92,6 +92,13 @@ class BatchedRayDataset:
             keys = torch.arange(self.n, device=self.o.device, dtype=torch.float32) + \
                 window * torch.rand(self.n, device=self.o.device, generator=self.gen)
             perm = torch.argsort(keys)
+        # two alternating sets of batch buffers with fixed addresses: the trainer replays its step from a CUDA graph
+        # captured on the buffers it was first handed, and a batch stays valid until the next-but-one is produced
+        n_loc = self.local if self.world > 1 else self.batch
+        if getattr(self, "_slots", None) is None or self._slots[0][0].shape[0] != n_loc:
+            mk = lambda src: torch.empty((n_loc,) + tuple(src.shape[1:]), device=src.device, dtype=src.dtype)
+            self._slots = [(mk(self.img), mk(self.o), mk(self.d), self.t_row.expand(n_loc, -1).contiguous())
+                           for _ in range(2)]
         for s in range(self.steps):
             if perm is not None:
                 idx = perm[s * self.batch:(s + 1) * self.batch]
@@ -100,8 +107,14 @@ class BatchedRayDataset:
             else:
                 idx = (torch.arange(self.batch, device=self.o.device) + s * self.batch) % self.n
             idx = idx[self.rank * self.local:(self.rank + 1) * self.local]
-            t = self.t_row.expand(idx.shape[0], -1).contiguous()
-            yield self.img[idx], (self.o[idx], self.d[idx], t)
+            img, o, d, t = self._slots[s & 1]
+            if idx.shape[0] != img.shape[0]:                 # ragged shard: plain gathers
+                yield self.img[idx], (self.o[idx], self.d[idx], self.t_row.expand(idx.shape[0], -1).contiguous())
+                continue
+            torch.index_select(self.img, 0, idx, out=img)
+            torch.index_select(self.o, 0, idx, out=o)
+            torch.index_select(self.d, 0, idx, out=d)
+            yield img, (o, d, t)
 
 
 class HostPrefetcher:
