@@ -134,6 +134,11 @@ int nerf_train_forward_backward(nerf_ctx* ctx, const float* images, const float*
 #define NERF_PHASE_COARSE 2
 int nerf_train_phases(nerf_ctx* ctx, const float* images, const float* o, const float* d, const float* t,
                       const float* u_pdf, int64_t batch, float* metrics_dev, int phases, void* stream);
+/* Rendering option (default off).  The reference sets delta = 1e10 on a ray's LAST sample (data_utils.py:82), so the ray's
+ * colour is discontinuous in that sample's raw sigma at 0 (alpha jumps 0 -> 1).  With this option the bf16 tensor-core
+ * forward re-evaluates the last sample of every ray with the fp32 CUDA-core MLP and uses its sigma, so the sign decision
+ * is the fp32 one (one extra fp32 MLP evaluation per ray and net).  Inference passes only. */
+int nerf_set_exact_far_sigma(nerf_ctx* ctx, int on);
 /* Seed of the in-kernel uniform draws (keras.utils.set_random_seed, train_lego.py:22). */
 int nerf_set_seed(nerf_ctx* ctx, uint64_t seed);
 /* LEARNING_RATE lives in device memory (the step may be replayed from a CUDA graph): change it between steps. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "nerf_train_phases": (_I, [_P, _P, _P, _P, _P, _P, _L, _P, _I, _P]),
     "nerf_adam_step": (_I, [_P, _F, _P]),
     "nerf_set_seed": (_I, [_P, C.c_uint64]),
+    "nerf_set_exact_far_sigma": (_I, [_P, _I]),
     "nerf_set_learning_rate": (_I, [_P, _F, _P]),
     "nerf_get_optimizer_state": (_I, [_P, _P, _P, C.POINTER(_L), _P]),
     "nerf_set_optimizer_state": (_I, [_P, _P, _P, _L, _P]),

@@ -148,7 +148,7 @@ extern "C" int nerf_destroy(nerf_ctx* ctx) {
     cudaFree(ctx->fw_dirbias[0]); cudaFree(ctx->fw_dirbias[1]); cudaFree(ctx->dev_state); cudaFree(ctx->metric_sums);
     cudaFree(ctx->tr_dpred_c); cudaFree(ctx->tr_dpred_f); cudaFree(ctx->tr_drgb_c); cudaFree(ctx->tr_drgb_f);
     cudaFree(ctx->tr_ddirbias); cudaFree(ctx->tr_ddelta_f); cudaFree(ctx->tr_dtp_f); cudaFree(ctx->tr_dw_extra);
-    cudaFree(ctx->w_ig);
+    cudaFree(ctx->w_ig); cudaFree(ctx->far_t); cudaFree(ctx->far_pred);
     for (int n = 0; n < 2; ++n) { cudaFree(ctx->act_save[n]); cudaFree(ctx->dz_save[n]); cudaFree(ctx->mask_save[n]); }
     tc_free(ctx);
     delete ctx;
@@ -205,6 +205,38 @@ static int check_ready(nerf_ctx* ctx, int net) {
     return NERF_OK;
 }
 
+// ---- exact far sigma (nerf_set_exact_far_sigma): last sample of every ray through the fp32 MLP ------------------------
+__global__ void __launch_bounds__(256) far_gather_kernel(const float* __restrict__ t, int64_t B, int N, float* __restrict__ t_last) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x)
+        t_last[r] = t[r * N + (N - 1)];
+}
+__global__ void __launch_bounds__(256) far_patch_kernel(const float4* __restrict__ far_pred, int64_t B, int N,
+                                                        float4* __restrict__ preds) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < B; r += (int64_t)gridDim.x * blockDim.x)
+        preds[r * N + (N - 1)].w = far_pred[r].w;
+}
+static int patch_far_sigma(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
+                           float* preds, cudaStream_t st) {
+    if (!ctx->far_t) {
+        NERF_CUDA(cudaMalloc(&ctx->far_t, (size_t)ctx->cfg.max_rays * 4));
+        NERF_CUDA(cudaMalloc(&ctx->far_pred, (size_t)ctx->cfg.max_rays * 16));
+    }
+    far_gather_kernel<<<stream_grid(B, 256), 256, 0, st>>>(t, B, N, ctx->far_t);
+    NERF_LAUNCHED();
+    int rc = mlp_fp32_forward_rays(ctx, net, o, d, ctx->far_t, B, 1, ctx->far_pred, st);
+    if (rc) return rc;
+    far_patch_kernel<<<stream_grid(B, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(ctx->far_pred), B, N,
+                                                          reinterpret_cast<float4*>(preds));
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+
+extern "C" int nerf_set_exact_far_sigma(nerf_ctx* ctx, int on) {
+    NERF_CHECK_ARG(ctx != nullptr, "null ctx");
+    ctx->exact_far_sigma = on != 0;
+    return NERF_OK;
+}
+
 extern "C" int nerf_mlp_forward_encoded(nerf_ctx* ctx, int net, const float* rays_enc, const float* dirs_enc,
                                         int64_t n, float* preds, void* stream) {
     NERF_CHECK_ARG(ctx && rays_enc && dirs_enc && preds && n >= 0, "bad arguments");
@@ -227,7 +259,10 @@ extern "C" int nerf_mlp_forward_rays(nerf_ctx* ctx, int net, const float* o, con
     NERF_CHECK_ARG(precision == NERF_PRECISION_BF16_TC, "unknown precision");
     std::string why;
     if (!tc_supported(ctx->cfg, &why)) return fail(NERF_ERR_INVALID, why);
-    return tc_forward_rays(ctx, net, o, d, t, batch, num_samples, preds, false, (cudaStream_t)stream);
+    rc = tc_forward_rays(ctx, net, o, d, t, batch, num_samples, preds, false, (cudaStream_t)stream);
+    if (rc == NERF_OK && ctx->exact_far_sigma)
+        rc = patch_far_sigma(ctx, net, o, d, t, batch, num_samples, preds, (cudaStream_t)stream);
+    return rc;
 }
 
 // NeRFTrainer.forward_pass (models.py:151-176).  NS_FINE = 0 (single-net benchmark shape) stops after the coarse net.
@@ -249,7 +284,9 @@ static int forward_pass_impl(nerf_ctx* ctx, const float* o, const float* d, cons
     if (tc && (rc = tc_dirbias(ctx, d, B, Nf > 0 ? 3 : 1, st))) return rc;     // ddir biases of both nets, one launch
     auto mlp = [&](int net, const float* tt, int N, float* preds) -> int {
         if (!tc) return mlp_fp32_forward_rays(ctx, net, o, d, tt, B, N, preds, st);
-        return tc_forward_rays(ctx, net, o, d, tt, B, N, preds, save, st, true);
+        int r = tc_forward_rays(ctx, net, o, d, tt, B, N, preds, save, st, true);
+        if (r == NERF_OK && ctx->exact_far_sigma && !save) r = patch_far_sigma(ctx, net, o, d, tt, B, N, preds, st);
+        return r;
     };
     if ((rc = mlp(NERF_NET_COARSE, t, Nc, pred_c))) return rc;                                       // :152-157
     // the coarse weights are only needed by the resampling: skip the store when nobody asked for them

@@ -40,6 +40,8 @@ struct nerf_ctx {
     int64_t adam_step = 0;                // host mirror of dev_state->step
     nerf_dev_state* dev_state = nullptr;
     uint64_t seed = 0;
+    bool exact_far_sigma = false;         // rendering: last sample's sigma from the fp32 path (nerf_set_exact_far_sigma)
+    float *far_t = nullptr, *far_pred = nullptr;   // (max_rays), (max_rays, 4): workspace of that option
     uint64_t render_draws = 0;            // counter keying the in-kernel draws of inference forward passes
     float* metric_sums = nullptr;         // device float[4]: running sums of loss_coarse, loss, psnr + step count
     bool weights_set[2] = {false, false};

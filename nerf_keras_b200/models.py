@@ -391,7 +391,7 @@ class NeRFTrainer:
 
     def __init__(self, coarse_model, fine_model, batch_size, ns_coarse, ns_fine, l_xyz, l_dir,
                  precision=PRECISION_BF16_TC, stop_grad_samples=False, process_group=None, use_cuda_graph=True,
-                 overlap_allreduce=True):
+                 overlap_allreduce=True, exact_far_sigma=False):
         if not isinstance(coarse_model, NerfModel):
             raise TypeError("coarse_model must be a NerfModel (create_nerf_complete_model) instance")
         if not isinstance(fine_model, NerfModel):
@@ -406,6 +406,9 @@ class NeRFTrainer:
         self.process_group = process_group
         self.use_cuda_graph = bool(use_cuda_graph)
         self.overlap_allreduce = bool(overlap_allreduce)
+        # rendering option: the last sample of every ray (delta = 1e10, data_utils.py:82: colour is discontinuous in its raw
+        # sigma at 0) takes its sigma from the fp32 path, so bf16 rounding cannot flip that decision
+        self.exact_far_sigma = bool(exact_far_sigma)
         self.optimizer = None
         self.loss_fn = None
         self._ctx: Optional[_Ctx] = None
@@ -561,12 +564,14 @@ class NeRFTrainer:
         self._ctx = _Ctx(self.coarse_model.arch, self.ns_coarse, self.ns_fine, max_rays or self.batch_size, training, lr,
                          self.stop_grad_samples)
         _lib.check(_lib.lib().nerf_set_seed(self._ctx.handle, int(self._seed) & 0xFFFFFFFFFFFFFFFF), "nerf_set_seed")
+        _lib.check(_lib.lib().nerf_set_exact_far_sigma(self._ctx.handle, int(self.exact_far_sigma)), "exact_far_sigma")
         for net, (m, blob) in enumerate(zip((self.coarse_model, self.fine_model), blobs)):
             m._owner = (self._ctx, net)
             self._ctx.set_weights(net, torch.from_numpy(blob))
         if opt_state is not None:
             self._ctx.set_optimizer_state(*opt_state)
-        sums = self._ctx.metric_sums() if getattr(self, "_bn_state", None) is None else None
+        # BATCH_NORM trainers keep host-side trackers (their training step does not go through this context)
+        sums = self._ctx.metric_sums() if self.coarse_model.bn is None else None
         for i, tr in enumerate((self.loss_coarse_tracker, self.loss_tracker, self.psnr_tracker)):
             tr.bind(sums, i)
 
@@ -780,7 +785,7 @@ class NeRFTrainer:
         rgbs, _, _, _ = self.forward_pass(o, d, t, u_pdf=u_pdf, maps_only=True)
         metrics = torch.empty((3,), device=images.device, dtype=torch.float32)
         rgb_f = rgbs[1] if rgbs[1] is not None else rgbs[0]
-        if getattr(self, "_bn_state", None) is not None:
+        if self.coarse_model.bn is not None:
             _lib.check(_lib.lib().nerf_metrics(_ptr(images), _ptr(rgbs[0]), _ptr(rgb_f), images.shape[0], _ptr(metrics),
                                                _stream()), "test_step")
             return self._update_metrics(metrics)
