@@ -500,6 +500,7 @@ def main():
                                "train_frac_of_sustained_bf16": Bs / (ms * 1e-3) * 3 * per_ray / (peaks["tensor_sustained"] * 1e12),
                                "render_frac_of_sustained_bf16": Bs / (rms * 1e-3) * per_ray / (peaks["tensor_sustained"] * 1e12),
                                "micro_batches": Bs // cap})
+                tr.release_graphs()
                 del tr, db
                 torch.cuda.empty_cache()
         best = max(points, key=lambda p: p["train_rays_per_sec"])
@@ -511,8 +512,8 @@ def main():
                 "sweep": points}
         if rank == 0:
             print(json.dumps(line), flush=True)
-        if world > 1:
-            torch.distributed.barrier(); torch.distributed.destroy_process_group()
+        from nerf_keras_b200.dist import shutdown
+        shutdown()
         return 0
 
     # ---- model + trainer (random-init weights of the named architecture) -----------------------
@@ -612,6 +613,7 @@ def main():
                            "speedup_vs_weak_step_of_this_run": ms_per_step / s_ms,
                            "efficiency_vs_weak_step_of_this_run": ms_per_step / s_ms / world,
                            "note": "weak step of this run = BATCH_SIZE rays on every GPU (the 1-GPU amount of work + all-reduce)"}
+        tr_s.release_graphs()
         del tr_s
 
     # rooflines of the three tensor kernels of a step (live CUDA-event timers of the eager pass above)
@@ -667,9 +669,9 @@ def main():
             r = cpu_arm(args.mode, conf, 3, 1, CPU_SAMPLE_RAYS)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+    from nerf_keras_b200.dist import shutdown
+    e2e_state["it"] = None
+    shutdown(trainer)
     return 0
 
 

@@ -56,3 +56,27 @@ def gather_rows(local: torch.Tensor, group=None) -> Optional[torch.Tensor]:
     bufs = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
     dist.gather(local, bufs, dst=0, group=group)
     return torch.cat(bufs, dim=0) if rank == 0 else None
+
+
+def shutdown(*trainers, timeout_s: float = 30.0):
+    """End of a torchrun worker: release the trainers' CUDA graphs (they hold NCCL kernels), synchronise, and destroy the
+    process group.  If the teardown itself does not return within `timeout_s` the process exits with status 0 anyway --
+    all results have been produced at this point."""
+    import os
+    import sys
+    import threading
+    for tr in trainers:
+        if tr is not None:
+            tr.release_graphs()
+    if not dist.is_initialized():
+        return
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    guard = threading.Timer(timeout_s, lambda: os._exit(0))
+    guard.daemon = True
+    guard.start()
+    dist.barrier()
+    dist.destroy_process_group()
+    guard.cancel()

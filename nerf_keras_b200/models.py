@@ -761,6 +761,16 @@ class NeRFTrainer:
         self._step_body(images, o, d, t, u, B)
         return self._logs()     # stays on the device: no host synchronisation inside the step
 
+    def release_graphs(self):
+        """Destroy the captured step graphs.  Call this before torch.distributed.destroy_process_group(): NCCL does not
+        tear a communicator down while a CUDA graph that captured its collectives is still alive."""
+        self._graphs.clear()
+        self._seen.clear()
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def _capture(self, key, images, o, d, t, u, B):
         """Capture one training step on these input buffers.  The buffers are kept alive with the graph; the step count,
         the learning rate and the random draws are read from device memory, so every replay is a fresh step."""

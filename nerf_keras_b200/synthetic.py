@@ -23,12 +23,18 @@ def _procedural_rgb(o: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
                         0.5 + 0.5 * torch.sin(p[..., 0] * p[..., 2])], dim=-1).clamp(0, 1).contiguous()
 
 
-def _views(H, W, focal, poses):
+def _views(H, W, focal, poses, ndc_near=None):
+    """Flattened per-pixel (images, origins, directions) of the views.  ndc_near: rays are moved to the near plane and
+    projected to normalised device coordinates (extension) AFTER the target colours were taken from the
+    world-space rays."""
     imgs, oris, dirs = [], [], []
     for pose in poses:
         o, d = du.get_rays(H, W, focal, pose)
         o, d = o.reshape(-1, 3), d.reshape(-1, 3)
-        imgs.append(_procedural_rgb(o, d)); oris.append(o); dirs.append(d)
+        imgs.append(_procedural_rgb(o, d))
+        if ndc_near is not None:
+            o, d = du.ndc_rays(H, W, focal, ndc_near, o, d)
+        oris.append(o); dirs.append(d)
     return torch.cat(imgs), torch.cat(oris), torch.cat(dirs)
 
 
@@ -43,9 +49,10 @@ def prepare_lego_data(H: int, W: int, n_views: int = 20, seed: int = 0):
     return _views(H, W, focal, poses[:k]), _views(H, W, focal, poses[k:]), (2.0, 6.0), focal
 
 
-def prepare_fern_data(H: int, W: int, n_views: int = 20, seed: int = 2):
+def prepare_fern_data(H: int, W: int, n_views: int = 20, seed: int = 2, ndc: bool = False):
     """Forward-facing poses (identity rotation + small yaw/pitch, xy translation), pinhole rays with near/far from
-    the bounds as the reference does (fern_data_utils.py:489-496); one view held out (:499-500)."""
+    the bounds as the reference does (fern_data_utils.py:489-496); one view held out (:499-500).
+    ndc=True (extension, not in the reference): forward-facing NDC rays as in the original NeRF, sampled on t in [0, 1]."""
     rng = np.random.default_rng(seed)
     focal = float(np.float32(407.6 * W / 504.0))
     poses = []
@@ -57,6 +64,8 @@ def prepare_fern_data(H: int, W: int, n_views: int = 20, seed: int = 2):
         pose[:3, :3] = R.astype(np.float32)
         pose[:2, 3] = rng.uniform(-0.3, 0.3, 2).astype(np.float32)
         poses.append(pose)
+    if ndc:
+        return _views(H, W, focal, poses[1:], 1.0), _views(H, W, focal, poses[:1], 1.0), (0.0, 1.0), focal
     return _views(H, W, focal, poses[1:]), _views(H, W, focal, poses[:1]), (1.2, 12.0), focal
 
 

@@ -57,6 +57,7 @@ def main():
     res["grad_max_abs_err"] = float((g_dp - g_full).abs().max())
     res["grad_norm"] = float(g_full.norm())
     # (2) whole steps through NeRFTrainer.train_step (overlapped all-reduce, CUDA graph) vs the single-GPU trainer
+    keep = []
     for tag, kw in (("overlap_graph", dict(use_cuda_graph=True, overlap_allreduce=True)),
                     ("single_allreduce_eager", dict(use_cuda_graph=False, overlap_allreduce=False))):
         a, b = trainer(hi - lo, stop_grad_samples=True, **kw), trainer(Bg, stop_grad_samples=True, use_cuda_graph=False)
@@ -73,10 +74,11 @@ def main():
                     "update_cosine_vs_1gpu": float(torch.dot(wa - w0, wb - w0) / ((wa - w0).norm() * (wb - w0).norm())),
                     "median_abs_diff_vs_1gpu": float((wa - wb).abs().median()),
                     "graphs": len(a._graphs), "steps": a._ctx.optimizer_state()[2]}
+        keep += [a, b]
     if rank == 0:
         print("DP_RESULT " + json.dumps(res), flush=True)
-    torch.distributed.barrier()
-    torch.distributed.destroy_process_group()
+    from nerf_keras_b200.dist import shutdown
+    shutdown(*keep)
 
 
 if __name__ == "__main__":

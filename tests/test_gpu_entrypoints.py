@@ -68,3 +68,22 @@ def test_train_script_with_batch_norm_config(tmp_path):
     saved = [f for f in os.listdir(tmp_path / "models") if f.endswith(".npz")]
     data = np.load(tmp_path / "models" / saved[0])
     assert "coarse/d0/bn_gamma" in data and "fine/ddir/bn_var" in data
+
+
+def test_train_fern_script_with_ndc_rays(tmp_path):
+    """north_star's "pinhole or NDC" rays: train_fern.py --ndc trains on forward-facing NDC rays (t in [0, 1]); the
+    reference's own Fern rays (pinhole, near / far from the bounds) stay the default."""
+    cfg = os.path.join(ROOT, "config", "fern_batch_debug.json")
+    out = _run([os.path.join(ROOT, "train_fern.py"), "--config", cfg, "--steps-per-epoch", "30", "--views", "4", "--ndc"],
+               str(tmp_path))
+    lines = [l for l in out.splitlines() if l.startswith("Epoch")]
+    assert len(lines) == 2 and "nan" not in out.lower()
+    loss = [float(l.split("loss: ")[1].split()[0]) for l in lines]
+    assert loss[1] < loss[0]
+    # the ray set the script trained on: origins on the near plane (z = -1), unit span to the far plane
+    import torch
+    from nerf_keras_b200.synthetic import prepare_fern_data
+    train, val, (near, far), focal = prepare_fern_data(50, 75, n_views=3, ndc=True)
+    assert (near, far) == (0.0, 1.0)
+    assert torch.allclose(train[1][:, 2], torch.full_like(train[1][:, 2], -1.0), atol=1e-5)
+    assert torch.allclose((train[1] + train[2])[:, 2], torch.ones_like(train[1][:, 2]), atol=1e-5)

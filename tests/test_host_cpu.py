@@ -178,3 +178,24 @@ def test_callback_image_scaling_matches_array_to_img():
     x = np.array([[0.25, 0.5], [0.75, 1.25]], dtype=np.float32)
     np.testing.assert_array_equal(array_to_uint8(x), np.array([[0, 63], [127, 255]], dtype=np.uint8))
     assert array_to_uint8(np.full((2, 2), 3.0, np.float32)).max() == 0
+
+
+def test_reference_literal_configs_load_unchanged():
+    """config/ref_*.json hold the LITERAL values of the reference's six config files (the shipped config/*.json without the
+    prefix are the benchmark-shaped variants BASELINE.json names).  They load through the same schema check, build the
+    model kwargs, and -- in the container that has the reference tree -- equal the reference's files value for value."""
+    import glob
+    import json
+    from nerf_keras_b200.config import load_config, model_kwargs
+    files = sorted(glob.glob(os.path.join(ROOT, "config", "ref_*.json")))
+    assert len(files) == 6
+    for f in files:
+        conf = load_config(f)
+        kw = model_kwargs(conf)
+        assert kw["num_layers"] == 8 and kw["hidden_dim"] == 256 and kw["skip_layer"] == 4 and kw["lxyz"] == 10 and kw["ldir"] == 4
+        assert isinstance(conf["BATCH_NORM"], bool) and conf["LEARNING_RATE"] == 0.0005
+        ref = os.path.join("/root/reference/config", os.path.basename(f)[len("ref_"):])
+        if os.path.exists(ref):
+            assert json.load(open(ref)) == conf
+    # the reference's Fern scripts need TEST_BATCH_SIZE, which fern_batch_h256.json lacks (train_fern.py:38 raises KeyError)
+    assert "TEST_BATCH_SIZE" not in load_config(os.path.join(ROOT, "config", "ref_fern_batch_h256.json"))

@@ -19,6 +19,9 @@ def main(dataset="lego"):
     ap.add_argument("--views", type=int, default=10)
     ap.add_argument("--checkpoint-dir", type=str, default=None,
                     help="per-epoch validation render (PNG), weights and history JSON, as the reference's TrainCallback")
+    ap.add_argument("--ndc", action="store_true",
+                    help="fern only: forward-facing NDC rays, t in [0, 1] (extension; the reference's Fern rays are pinhole "
+                         "with near / far from the bounds, fern_data_utils.py:489-496)")
     ap.add_argument("--data", type=str, default=None,
                     help="real data instead of the synthetic scene: tiny_nerf_data.npz or a Blender scene directory "
                          "(lego), an LLFF scene directory with poses_bounds.npy (fern)")
@@ -31,13 +34,22 @@ def main(dataset="lego"):
         from nerf_keras_b200 import real_data
         if dataset == "fern":
             train, val, (near, far), focal = real_data.prepare_fern_data(conf["HEIGHT"], conf["WIDTH"], datadir=args.data)
+            if args.ndc:
+                H_, W_ = conf["HEIGHT"], conf["WIDTH"]
+                train = (train[0],) + tuple(nk.ndc_rays(H_, W_, focal, 1.0, train[1], train[2]))
+                val = (val[0],) + tuple(nk.ndc_rays(H_, W_, focal, 1.0, val[1], val[2]))
+                near, far = 0.0, 1.0
         elif os.path.isdir(args.data):
             train, val, (near, far), focal = real_data.prepare_blender_data(conf["HEIGHT"], conf["WIDTH"], args.data)
         else:
             train, val, (near, far), focal = real_data.prepare_lego_data(conf["HEIGHT"], conf["WIDTH"], npz_path=args.data)
     else:
-        prep = prepare_lego_data if dataset == "lego" else prepare_fern_data
-        train, val, (near, far), focal = prep(conf["HEIGHT"], conf["WIDTH"], n_views=args.views)
+        if args.ndc and dataset != "fern":
+            raise SystemExit("--ndc applies to the forward-facing Fern scene only")
+        if dataset == "lego":
+            train, val, (near, far), focal = prepare_lego_data(conf["HEIGHT"], conf["WIDTH"], n_views=args.views)
+        else:
+            train, val, (near, far), focal = prepare_fern_data(conf["HEIGHT"], conf["WIDTH"], n_views=args.views, ndc=args.ndc)
     B, Nc, Nf = conf["BATCH_SIZE"], conf["NS_COARSE"], conf["NS_FINE"]
     train_ds = BatchedRayDataset(*train, Nc, B, near, far, shuffle=True, steps_per_epoch=args.steps_per_epoch,
                                  rank=rank, world=world)
@@ -61,6 +73,9 @@ def main(dataset="lego"):
         trainer.save_weights(f"models/nerf_{dataset}_l{conf['NUM_LAYERS']}_d{conf['HIDDEN_DIM']}_n{Nc + Nf}_{name}.npz")
         with open(f"models/history_{name}.json", "w") as f:
             json.dump(history, f)
+    if world > 1:
+        from nerf_keras_b200.dist import shutdown
+        shutdown(trainer)       # the step graphs hold NCCL kernels: release them before the process group goes away
 
 
 if __name__ == "__main__":
