@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
     const int n_units_grid = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int64_t n_units = PAIR ? (P.n_pairs + 1) / 2 : P.n_pairs;
     Barriers B;
-    init_barriers(base, B, PAIR);
+    const bool shared_chunks = PAIR && (P.dbg & 2);     // pair mode: one ring fill per chunk, consumed by both sub-tiles
+    init_barriers(base, B, PAIR, shared_chunks);
     float* side = reinterpret_cast<float*>(smem + SM_SIDE);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
     if (warp == 9) {
@@ -393,14 +394,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
 
     if (warp == 8) {
         if (lane == 0) {
-            if (PAIR) producer_loop_pair(base, B, P.w_chunks, c_fwd_prog, rank, my_pairs);
+            if (PAIR) producer_loop_pair(base, B, P.w_chunks, c_fwd_prog, rank, my_pairs, shared_chunks);
             else producer_loop(base, B, P.w_chunks, N_CHUNKS, total_chunks);
         }
     } else if (warp >= 9) {
         if (lane == 0) {
             if (!PAIR) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace);
-            else if (rank == 0) issuer_loop_pair(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace, P.dbg);
-            else if (warp == 9) forwarder_loop_pair(B, my_pairs * steps_per_tile * 2);
+            else if (rank == 0) issuer_loop_pair(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace, P.dbg, shared_chunks);
+            else if (warp == 9) forwarder_loop_pair(B, my_pairs * steps_per_tile * (shared_chunks ? 1 : 2));
         }
     } else {
         // ===================== workers: PE prologue + epilogues =====================

@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     const WgJob& J = P.jobs[job_id];
     const int job_ctas = P.cta_first[job_id + 1] - P.cta_first[job_id], job_cta = (int)blockIdx.x - P.cta_first[job_id];
     const uint32_t bar_full = base + WG_SM_BAR, bar_empty = bar_full + 8 * WG_STAGES, bar_done = bar_empty + 8 * WG_STAGES;
+    const int STG = (P.debug & 16) ? 2 : WG_STAGES;     // experiment: ring depth 2 (16 instead of 24 bulk copies in flight)
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_SM_BAR + 8 * (2 * WG_STAGES + 1));
 
     if (threadIdx.x == 0) {
@@ -386,12 +387,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
                 const uint32_t dst = base + slot * WG_SLOT;
                 mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)(n_a_load + J.n_b) * 8192u);
                 const uint8_t* a_src = P.act_save + tile * SAVE_TILE_BYTES + J.a_off + half * 8192;
+                const uint8_t* b_src = P.dz_save + tile * DZ_TILE_BYTES + J.b_off + half * 8192;
+                if (P.debug & 32) {
+                    // TIMING EXPERIMENT ONLY (wrong operands): the same bytes as two large copies per stage
+                    bulk_g2s(dst, a_src - half * 8192 + half * (n_a_load * 8192), n_a_load * 8192, bar_full + 8 * slot);
+                    bulk_g2s(dst + 32768, b_src - half * 8192 + half * (J.n_b * 8192), J.n_b * 8192, bar_full + 8 * slot);
+                } else {
                 for (int b = 0; b < n_a_load; ++b)
                     bulk_g2s(dst + b * 8192, a_src + (J.n_a == 1 ? 0 : b) * 16384, 8192, bar_full + 8 * slot);
-                const uint8_t* b_src = P.dz_save + tile * DZ_TILE_BYTES + J.b_off + half * 8192;
                 for (int b = 0; b < J.n_b; ++b)
                     bulk_g2s(dst + 32768 + b * 8192, b_src + b * 16384, 8192, bar_full + 8 * slot);
-                if (++slot == WG_STAGES) { slot = 0; par ^= 1; }
+                }
+                if (++slot == STG) { slot = 0; par ^= 1; }
             }
         }
     } else if (warp == 5) {
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
                     }
                 }
                 mma_commit(bar_empty + 8 * slot);
-                if (++slot == WG_STAGES) { slot = 0; par ^= 1; }
+                if (++slot == STG) { slot = 0; par ^= 1; }
             }
             mma_commit(bar_done);
         }
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
                 for (int rr = 0; rr < 8; ++rr) accum(b0, 1.0f, cs, rr);
             }
             mbar_arrive(bar_empty + 8 * slot);
-            if (++slot == WG_STAGES) { slot = 0; par ^= 1; }
+            if (++slot == STG) { slot = 0; par ^= 1; }
         }
         if (n_ht > 0) {
             if (J.bias_dst >= 0 && (lane >> 3) < J.n_b) {

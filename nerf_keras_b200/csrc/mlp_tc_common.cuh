@@ -124,13 +124,13 @@ struct Barriers {
 };
 
 // pair = true: the CTA is one half of a cta_group::2 pair; the leader's A-tile barriers also collect the peer's workers
-__device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B, bool pair = false) {
+__device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B, bool pair = false, bool shared_chunks = false) {
     B.full = base + SM_FULL; B.empty = base + SM_EMPTY; B.accf = base + SM_ACCF; B.actr = base + SM_ACTR;
     B.pfull = base + SM_PFULL;
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(B.full + 8 * i, 1);
-            mbar_init(B.empty + 8 * i, pair ? 1 : 2);   // single-CTA: both sub-tiles consume a chunk; pair: one consumer
+            mbar_init(B.empty + 8 * i, (pair && !shared_chunks) ? 1 : 2);   // consumers of a chunk: both sub-tiles, or (pair, merged order) one
             mbar_init(B.pfull + 8 * i, 1);
         }
         for (int i = 0; i < 4; ++i) {                 // index = sub-tile * 2 + half
@@ -263,8 +263,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
 // Ring order in pair mode ("merged" order): for every phase first the chunks of sub-tile 0, then the same chunks again
 // for sub-tile 1.  Each chunk has exactly one consumer, the two sub-tiles alternate on the tensor pipe phase by
 // phase, and one sub-tile's whole epilogue runs under the other's MMA phase.
+// shared = true: every chunk is loaded ONCE per phase and consumed by sub-tile 0 and then by sub-tile 1 (the slot is released
+// by both commits): half the ring-fill traffic; the next phase's chunks stream in behind sub-tile 1's progress.
 __device__ __forceinline__ void producer_loop_pair(uint32_t base, const Barriers& B, const __nv_bfloat16* chunks,
-                                                   const Program& prog, int rank, int n_tiles) {
+                                                   const Program& prog, int rank, int n_tiles, bool shared = false) {
     int slot = 0;
     uint32_t par = 1;
     for (int tile = 0; tile < n_tiles; ++tile) {
@@ -273,7 +275,7 @@ __device__ __forceinline__ void producer_loop_pair(uint32_t base, const Barriers
             const int n_ch = prog.chunks[ph], kbs = prog.kb[ph];
             const bool single = (n_ch == kbs);                   // one N-half only: split its rows between the CTAs
             const uint32_t bytes = single ? CHUNK_BYTES / 2 : CHUNK_BYTES;
-            for (int sub = 0; sub < 2; ++sub) {
+            for (int sub = 0; sub < (shared ? 1 : 2); ++sub) {
                 for (int kb = 0; kb < kbs; ++kb) {
                     const int c = first + (single ? kb : rank * kbs + kb);
                     const uint8_t* src = reinterpret_cast<const uint8_t*>(chunks) + (size_t)c * CHUNK_BYTES +
@@ -302,7 +304,8 @@ __device__ __forceinline__ void forwarder_loop_pair(const Barriers& B, int steps
 
 // leader CTA: one issuer thread per sub-tile pair; sub-tile s owns merged positions [base + s*kbs, base + (s+1)*kbs)
 __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& B, uint32_t tmem_base, const Program& prog,
-                                                 int s, int n_tiles, long long* trace = nullptr, int dbg = 0) {
+                                                 int s, int n_tiles, long long* trace = nullptr, int dbg = 0,
+                                                 bool shared = false) {
     const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
     const uint32_t lbo_bits = (16u >> 4) << 16;
     const uint32_t a_tile = ((base + SM_ACT + s * 65536) & 0x3FFFF) >> 4;
@@ -314,6 +317,10 @@ __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& 
     uint32_t g_base = 0;          // merged ring position of the current phase's first chunk
     uint32_t actr_par = 0;
     (void)dbg;
+    // shared chunks: the two sub-tiles must ALTERNATE on the tensor pipe (one's epilogue under the other's MMA window).
+    // Both A tiles are ready at the same moment at kernel start, so sub-tile 1 waits once for sub-tile 0's first
+    // accumulator; from then on it trails by one window (it consumes every chunk after sub-tile 0, from the same slot).
+    if (shared && s == 1) mbar_wait_cluster(B.accf + 8, 0, 9);
     for (int tile = 0; tile < n_tiles; ++tile) {
         for (int ph = 0; ph < prog.n_phases; ++ph) {
             const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
@@ -324,7 +331,7 @@ __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& 
             trace_ev(trace, s, tile, ph, 1);
             uint32_t w_full = 0, w_pfull = 0;     // diagnostics: cycles spent waiting for weight chunks
             for (int kb = 0; kb < kbs; ++kb) {
-                const uint32_t g = g_base + s * kbs + kb;
+                const uint32_t g = g_base + (shared ? 0 : s * kbs) + kb;
                 const uint32_t lap = g / STAGES;
                 const uint32_t slot = g - lap * STAGES;
                 const uint32_t ring_par = lap & 1;
@@ -351,7 +358,7 @@ __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& 
             mma_commit_2cta(bar_h0, 0x3);                       // all 256 columns complete at once in pair mode
             mma_commit_2cta(bar_h1, 0x3);
             actr_par ^= 1;
-            g_base += 2 * kbs;
+            g_base += shared ? kbs : 2 * kbs;
             trace_ev(trace, s, tile, ph, 2);
             if (trace && blockIdx.x == 0 && tile < 3)
                 trace[((s * 3 + tile) * 16 + ph) * 4 + 3] = (long long)w_full | ((long long)w_pfull << 32);
