@@ -415,7 +415,7 @@ extern "C" int nerf_volume_render(const float* preds, const float* t, int64_t ba
 // Same register-resident / next-ray-prefetch structure as the forward kernel; the transmittances of the forward
 // sweep stay in registers for the reverse sweep.
 template <int NCH>
-__global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __restrict__ preds,
+__global__ void __launch_bounds__(256, (NCH >= 6 && NCH <= 8) ? 2 : 1) volume_render_bwd_kernel(const float4* __restrict__ preds,
                                                                 const float* __restrict__ t,
                                                                 const float* __restrict__ d_rgb,
                                                                 const float* __restrict__ d_w_extra, int64_t B,
@@ -441,7 +441,10 @@ __global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __
     for (; ray < B; ray += warps_total) {
         load(ray + warps_total, np_, nt);
         const float dr = __ldg(d_rgb + ray * 3), dg = __ldg(d_rgb + ray * 3 + 1), db = __ldg(d_rgb + ray * 3 + 2);
-        float Tc[NCH], dl[NCH];
+        // exp(-sigma delta) of the forward sweep is kept for the reverse sweep when the ray fits in few chunks; long rays
+        // recompute it (six more live registers per lane cost the 192-sample kernel more occupancy than the exp saves)
+        constexpr bool KEEP_E = NCH <= 3;
+        float Tc[NCH], dl[NCH], ec[KEEP_E ? NCH : 1];
         // forward sweep: transmittance
         float carry = 1.0f;
 #pragma unroll
@@ -455,7 +458,9 @@ __global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __
             const float delta = (n == N - 1) ? 1e10f : (tn1 - tn);
             dl[c] = delta;
             const float sigma = fmaxf(cp[c].w, 0.0f);
-            const float alpha = 1.0f - expf(-sigma * delta);
+            const float e_fw = expf(-sigma * delta);
+            if (KEEP_E) ec[c] = e_fw;
+            const float alpha = 1.0f - e_fw;
             const float x = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
             const float incl = warp_incl_scan_mul(x, lane);
             float excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -472,10 +477,11 @@ __global__ void __launch_bounds__(256) volume_render_bwd_kernel(const float4* __
             const float4 pr = cp[c];
             const float delta = dl[c];
             const float sigma = fmaxf(pr.w, 0.0f);
-            const float e = expf(-sigma * delta);
+            const float e = KEEP_E ? ec[KEEP_E ? c : 0] : expf(-sigma * delta);
             const float alpha = 1.0f - e;
             const float x = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
-            const float cr = sigmoidf_acc(pr.x), cg = sigmoidf_acc(pr.y), cb = sigmoidf_acc(pr.z);
+            // colours to ~1e-6 absolute (ex2.approx based), as in the forward kernel: d_preds carries them times w <= 1
+            const float cr = sigmoidf_fast(pr.x), cg = sigmoidf_fast(pr.y), cb = sigmoidf_fast(pr.z);
             float g = dr * cr + dg * cg + db * cb;
             if (d_w_extra && ok) g += d_w_extra[ray * N + n];
             if (!ok) g = 0.f;
