@@ -7,10 +7,10 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr)
 OBJS=()
 PIDS=()
-for f in ops mlp_fp32 ctx mlp_tc mlp_tc_bwd bn_train; do
+for f in ops mlp_fp32 ctx mlp_tc mlp_tc_experimental mlp_tc_bwd bn_train; do
   src="$HERE/$f.cu"; obj="$HERE/$f.o"
   stale=0
-  [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/../../include/nerf_b200.h" -nt "$obj" ]] && stale=1
+  [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/../../include/nerf_b200.h" -nt "$obj" || "$HERE/../../include/nerf_b200_debug.h" -nt "$obj" ]] && stale=1
   for hdr in "$HERE"/*.cuh; do [[ "$hdr" -nt "$obj" ]] && stale=1; done
   if [[ $stale -eq 1 ]]; then
     ( "$NVCC" "${FLAGS[@]}" ${PTXAS_V:+-Xptxas -v} -c "$src" -o "$obj" || { rm -f "$obj"; exit 1; } ) &

@@ -415,7 +415,7 @@ extern "C" int nerf_volume_render(const float* preds, const float* t, int64_t ba
 // Same register-resident / next-ray-prefetch structure as the forward kernel; the transmittances of the forward
 // sweep stay in registers for the reverse sweep.
 template <int NCH>
-__global__ void __launch_bounds__(256, (NCH >= 6 && NCH <= 8) ? 2 : 1) volume_render_bwd_kernel(const float4* __restrict__ preds,
+__global__ void __launch_bounds__(256, NCH <= 2 ? 3 : (NCH <= 6 ? 2 : 1)) volume_render_bwd_kernel(const float4* __restrict__ preds,
                                                                 const float* __restrict__ t,
                                                                 const float* __restrict__ d_rgb,
                                                                 const float* __restrict__ d_w_extra, int64_t B,

@@ -14,10 +14,14 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _header_symbols():
-    text = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", text)))
+def _header_symbols(names=("nerf_b200.h", "nerf_b200_debug.h")):
+    """Every function the public header (the drop-in boundary) and the debug header (tests / tools) declare."""
+    out = set()
+    for name in names:
+        text = open(os.path.join(ROOT, "include", name)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        out |= set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", text))
+    return sorted(out)
 
 
 def test_library_exports_every_header_symbol():
@@ -26,6 +30,8 @@ def test_library_exports_every_header_symbol():
     handle = C.CDLL(_lib.LIB_PATH)
     syms = _header_symbols()
     assert len(syms) >= 20
+    public = _header_symbols(("nerf_b200.h",))
+    assert not [s for s in public if "selftest" in s or "debug" in s], "debug / self-test exports belong in nerf_b200_debug.h"
     for s in syms:
         assert hasattr(handle, s), f"missing export {s}"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in _lib.SIGNATURES"
