@@ -156,3 +156,42 @@ def test_bn_trainer_trains_and_renders(nk, tmp_path):
     a = tr.forward_pass(o.cuda(), d.cuda(), t.cuda(), u_pdf=u.cuda())[0][1]
     b = tr2.forward_pass(o.cuda(), d.cuda(), t.cuda(), u_pdf=u.cuda())[0][1]
     assert torch.equal(a, b)
+
+
+def test_bn_trainer_state_follows_weight_setters_and_getters(nk, tmp_path):
+    """with BATCH_NORM=true the training weights live in a device-side training state.  Setters called
+    after compile() (load_weights, set_weights, set_bn_params) must become the starting point of the next step, and
+    getters / model calls must see the trained values without an explicit save."""
+    wc, wf, bns, o, d, t, u, img, Nc, Nf = _setup(seed=5)
+    to_np = lambda bn: {r: {k: v.numpy() for k, v in st.items()} for r, st in bn.items()}
+
+    def make(wc_, wf_):
+        mc = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+        mf = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+        mc.set_flat_weights(O.flatten_weights(wc_)); mf.set_flat_weights(O.flatten_weights(wf_))
+        mc.set_bn_params(to_np(bns[0])); mf.set_bn_params(to_np(bns[1]))
+        tr = nk.NeRFTrainer(mc, mf, o.shape[0], Nc, Nf, 10, 4, stop_grad_samples=True)
+        tr.compile(nk.Adam(5e-4), nk.MeanSquaredError())
+        return tr
+
+    batch = (img.cuda(), (o.cuda(), d.cuda(), t.cuda()))
+    a = make(wc, wf)
+    path = str(tmp_path / "bn_ckpt.npz")
+    a.save_weights(path)
+    first_a = float(a.train_step(batch, u_pdf=u.cuda())["loss"])
+    # a trainer compiled on DIFFERENT weights, then handed the checkpoint: its first step must equal a's first step
+    other_c, other_f = O.init_weights(991, 0.1), O.init_weights(992, 0.1)
+    b = make(other_c, other_f)
+    b.load_weights(path)
+    first_b = float(b.train_step(batch, u_pdf=u.cuda())["loss"])
+    assert abs(first_a - first_b) <= 1e-6 * max(1.0, abs(first_a)), (first_a, first_b)
+    # ... and the update started from the loaded weights (not from the compile-time ones)
+    wa, wb = a.coarse_model.get_flat_weights(), b.coarse_model.get_flat_weights()       # getters sync the training state
+    assert np.abs(wa - wb).max() <= 1e-6
+    assert np.abs(wa - O.flatten_weights(wc)).max() > 1e-5                               # trained values, not the stale host copy
+    ga, gb = a.coarse_model.get_bn_params(), b.coarse_model.get_bn_params()
+    assert all(np.allclose(ga[r][k], gb[r][k], atol=1e-6) for r in ga for k in ga[r])
+    # a model call after training uses the trained, folded weights
+    enc_x, enc_d = np.zeros((3, 63), np.float32), np.zeros((3, 27), np.float32)
+    ya, yb = a.coarse_model([enc_x, enc_d]).cpu().numpy(), b.coarse_model([enc_x, enc_d]).cpu().numpy()
+    assert np.abs(ya - yb).max() <= 1e-5
