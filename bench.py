@@ -483,7 +483,7 @@ def main():
         for nf in (0, 64, 128):
             for lb in (10, 12, 14, 16, 18, 20):
                 Bs = 1 << lb
-                cap = min(Bs, 65536 if nf else 262144)            # workspace cap: larger batches run as micro-batches
+                cap = min(Bs, 32768 if nf else 131072)            # workspace cap (saved operand images: 10.4 KB per sample, ~90 GB): larger batches run as micro-batches
                 c2 = dict(conf, NS_FINE=nf, BATCH_SIZE=Bs)
                 tr = make_trainer(nk, c2, cap, Nc, nf, True, use_graph=not args.no_graph)
                 db, _ = make_batches(nk, torch, dev, scene, c2, args.rays, Bs, Nc, nf, 2, rank, False)
@@ -535,13 +535,20 @@ def main():
 
     rgb_host = torch.empty((B, 3), dtype=torch.float32).pin_memory()
     from nerf_keras_b200.synthetic import HostPrefetcher
+
+    def endless_host_batches():
+        j = 0
+        while True:
+            yield host_batches[j % R]
+            j += 1
+    prefetcher = HostPrefetcher(endless_host_batches(), dev)     # one instance: its two staging slots keep their addresses
     e2e_state = {"it": None}
 
     def step_e2e(i):
         # every step's inputs come from pinned host memory; the public HostPrefetcher overlaps the copy of step i+1
         # with step i (the first copy of a run is not overlapped: the iterator is created inside step 0)
         if i == 0 or e2e_state["it"] is None:
-            e2e_state["it"] = iter(HostPrefetcher((host_batches[j % R] for j in range(1 << 30)), dev))
+            e2e_state["it"] = iter(prefetcher)
         img, o, d, t = next(e2e_state["it"])[:4]
         if train:
             trainer.train_step((img, (o, d, t)))

@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
     } else if (warp >= 9) {
         if (lane == 0) {
             if (!PAIR) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace);
-            else if (rank == 0) issuer_loop_pair(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace, P.dbg, shared_chunks);
+            else if (rank == 0 && shared_chunks) { if (warp == 9) issuer_loop_pair_shared(base, B, tmem_base, c_fwd_prog, my_pairs, P.trace); }
+            else if (rank == 0) issuer_loop_pair(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace, P.dbg, false);
             else if (warp == 9) forwarder_loop_pair(B, my_pairs * steps_per_tile * (shared_chunks ? 1 : 2));
         }
     } else {

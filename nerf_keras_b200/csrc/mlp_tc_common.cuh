@@ -130,7 +130,8 @@ __device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B, bool p
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(B.full + 8 * i, 1);
-            mbar_init(B.empty + 8 * i, (pair && !shared_chunks) ? 1 : 2);   // consumers of a chunk: both sub-tiles, or (pair, merged order) one
+            (void)shared_chunks;
+            mbar_init(B.empty + 8 * i, pair ? 1 : 2);   // releases per slot: single CTA: both sub-tiles' issuers; pair: one commit
             mbar_init(B.pfull + 8 * i, 1);
         }
         for (int i = 0; i < 4; ++i) {                 // index = sub-tile * 2 + half
@@ -317,10 +318,7 @@ __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& 
     uint32_t g_base = 0;          // merged ring position of the current phase's first chunk
     uint32_t actr_par = 0;
     (void)dbg;
-    // shared chunks: the two sub-tiles must ALTERNATE on the tensor pipe (one's epilogue under the other's MMA window).
-    // Both A tiles are ready at the same moment at kernel start, so sub-tile 1 waits once for sub-tile 0's first
-    // accumulator; from then on it trails by one window (it consumes every chunk after sub-tile 0, from the same slot).
-    if (shared && s == 1) mbar_wait_cluster(B.accf + 8, 0, 9);
+    (void)shared;
     for (int tile = 0; tile < n_tiles; ++tile) {
         for (int ph = 0; ph < prog.n_phases; ++ph) {
             const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
@@ -362,6 +360,66 @@ __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& 
             trace_ev(trace, s, tile, ph, 2);
             if (trace && blockIdx.x == 0 && tile < 3)
                 trace[((s * 3 + tile) * 16 + ph) * 4 + 3] = (long long)w_full | ((long long)w_pfull << 32);
+        }
+    }
+}
+
+// Pair mode with SHARED weight chunks: ONE issuer thread (leader CTA) feeds the tensor pipe for both sub-tiles in strict
+// alternation -- sub-tile 0 phase p, sub-tile 1 phase p, sub-tile 0 phase p+1, ... -- so that the MMA windows of the two
+// sub-tiles never interleave and each sub-tile's epilogue runs under the other's window.  Every chunk of a phase is loaded
+// once per CTA, consumed twice, and released by the commit that follows sub-tile 1's MMAs.  All barriers a window needs
+// (the phase's chunk barriers of both CTAs, then the A tile) are waited for BEFORE its first MMA, while the previous window
+// still executes: the 16 MMAs of a window are issued back to back.
+__device__ __forceinline__ void issuer_loop_pair_shared(uint32_t base, const Barriers& B, uint32_t tmem_base,
+                                                        const Program& prog, int n_tiles, long long* trace = nullptr) {
+    const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
+    const uint32_t lbo_bits = (16u >> 4) << 16;
+    const uint32_t ring0 = ((base + SM_RING) & 0x3FFFF) >> 4;
+    const uint32_t idesc256 = make_idesc_bf16(256, 256, 0, 0), idesc128 = make_idesc_bf16(256, 128, 0, 0);
+    uint32_t g_base = 0;
+    uint32_t actr_par = 0;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        for (int ph = 0; ph < prog.n_phases; ++ph) {
+            const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
+            const uint32_t idesc = (n_ch == kbs) ? idesc128 : idesc256;
+            // the phase's weight chunks in both CTAs (usually long complete: they were prefetched behind sub-tile 1)
+            for (int kb = 0; kb < kbs; ++kb) {
+                const uint32_t g = g_base + kb, lap = g / STAGES, slot = g - lap * STAGES;
+                mbar_wait(B.full + 8 * slot, lap & 1, 4);
+                mbar_wait_cluster(B.pfull + 8 * slot, lap & 1, 8);
+            }
+            for (int s = 0; s < 2; ++s) {
+                const uint32_t a_tile = ((base + SM_ACT + s * 65536) & 0x3FFFF) >> 4;
+                const uint32_t d_tmem = tmem_base + s * 256;
+                const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;
+                const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;
+                trace_ev(trace, s, tile, ph, 0);
+                mbar_wait_cluster(bar_lo, actr_par, 3);
+                mbar_wait_cluster(bar_hi, actr_par, 5);
+                trace_ev(trace, s, tile, ph, 1);
+                tc_fence_after();
+                for (int kb = 0; kb < kbs; ++kb) {
+                    const uint32_t g = g_base + kb, lap = g / STAGES, slot = g - lap * STAGES;
+                    const uint32_t a_lo = (a_tile + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
+                    const uint32_t b_lo = (ring0 + slot * (CHUNK_BYTES >> 4)) | lbo_bits;
+                    const bool acc0 = (kb > 0) || (flags & PH_ACC);
+                    const int n_mma = ((flags & PH_ENC) && kb == 1) ? 1 : 4;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < n_mma) {
+                            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+                            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                            mma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (acc0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    if (s == 1) mma_commit_2cta(B.empty + 8 * slot, 0x3);      // both sub-tiles are done with the chunk
+                }
+                mma_commit_2cta(bar_h0, 0x3);
+                mma_commit_2cta(bar_h1, 0x3);
+                trace_ev(trace, s, tile, ph, 2);
+            }
+            actr_par ^= 1;
+            g_base += kbs;
         }
     }
 }

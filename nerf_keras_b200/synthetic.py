@@ -137,10 +137,12 @@ class HostPrefetcher:
         self.src = host_batches
         self.device = torch.device(device) if device is not None else du._dev()
         self.stream = torch.cuda.Stream(device=self.device)
+        self._slots = [None, None]      # the two device staging slots survive re-iteration: their addresses are what the
+                                        # trainer's captured step graphs are keyed on
 
     def __iter__(self):
         it = iter(self.src)
-        slots, ready, free = [None, None], [None, None], [None, None]
+        slots, ready, free = self._slots, [None, None], [None, None]
         compute = torch.cuda.current_stream(self.device)
 
         def enqueue(k, batch):
