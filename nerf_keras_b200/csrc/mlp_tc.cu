@@ -250,6 +250,38 @@ __device__ __forceinline__ void trunk_part2(uint32_t t_lane, const float* bias, 
     trunk_group<RELU, SIGMA, SAVE, 7, true>(vb, bias, wsig, sig2, mask[7], rs, nullptr, gimg);
 }
 
+// whole accumulator (256 columns) in one pass, TMEM loads pipelined one group ahead, direct stores: for the CTA-pair
+// kernel, where the accumulator is handed over complete (no MMA of the phase still reads the A tile)
+template <bool RELU, bool SIGMA, bool SAVE>
+__device__ __forceinline__ void trunk_full(uint32_t t_lane, const float* bias, const float* wsig, uint64_t& sig2,
+                                           uint32_t (&mask)[8], const RowStore& rs, uint64_t gimg) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(t_lane, va);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 32, vb);
+    trunk_group<RELU, SIGMA, SAVE, 0, true>(va, bias, wsig, sig2, mask[0], rs, nullptr, gimg);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 64, va);
+    trunk_group<RELU, SIGMA, SAVE, 1, true>(vb, bias, wsig, sig2, mask[1], rs, nullptr, gimg);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 96, vb);
+    trunk_group<RELU, SIGMA, SAVE, 2, true>(va, bias, wsig, sig2, mask[2], rs, nullptr, gimg);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 128, va);
+    trunk_group<RELU, SIGMA, SAVE, 3, true>(vb, bias, wsig, sig2, mask[3], rs, nullptr, gimg);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 160, vb);
+    trunk_group<RELU, SIGMA, SAVE, 4, true>(va, bias, wsig, sig2, mask[4], rs, nullptr, gimg);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 192, va);
+    trunk_group<RELU, SIGMA, SAVE, 5, true>(vb, bias, wsig, sig2, mask[5], rs, nullptr, gimg);
+    tmem_ld_wait();
+    tmem_ld32(t_lane + 224, vb);
+    trunk_group<RELU, SIGMA, SAVE, 6, true>(va, bias, wsig, sig2, mask[6], rs, nullptr, gimg);
+    tmem_ld_wait();
+    trunk_group<RELU, SIGMA, SAVE, 7, true>(vb, bias, wsig, sig2, mask[7], rs, nullptr, gimg);
+}
+
 // one 32-column group of the ddir epilogue: + (bias + per-ray direction bias), ReLU, rgb head dot products
 template <bool SAVE, int CG>
 __device__ __forceinline__ void ddir_group(const uint32_t (&v)[32], const float* dbias /* this ray, 128 floats */,
@@ -364,7 +396,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
     } else if (warp >= 9) {
         if (lane == 0) {
             if (!PAIR) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace);
-            else if (rank == 0 && shared_chunks) { if (warp == 9) issuer_loop_pair_shared(base, B, tmem_base, c_fwd_prog, my_pairs, P.trace); }
+            else if (rank == 0 && shared_chunks) issuer_loop_pair_shared(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace);
             else if (rank == 0) issuer_loop_pair(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace, P.dbg, false);
             else if (warp == 9) forwarder_loop_pair(B, my_pairs * steps_per_tile * (shared_chunks ? 1 : 2));
         }
@@ -385,7 +417,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
         uint32_t accf_par = 0;
         uint32_t E[32];     // bf16(enc), 64 channels packed
         uint32_t Elo[2];    // bf16 residuals of the raw x, y, z channels
-        auto fence_async = [&]() { if (PAIR) fence_proxy_async_all(); else fence_proxy_async_smem(); };
+        // pair mode: the writes are read by the async proxy of THIS SM (each SM's tensor core reads its own A rows); the
+        // cross-CTA ordering is carried by the cluster-scope release / acquire of the barrier (P.dbg bit 2: cheaper fence)
+        const bool cheap_fence = PAIR && (P.dbg & 4);
+        auto fence_async = [&]() { if (PAIR && !cheap_fence) fence_proxy_async_all(); else fence_proxy_async_smem(); };
         auto arrive = [&](uint32_t bar) {                                // the peer's workers arrive on the leader's barrier
             if (PAIR && rank != 0) mbar_arrive_cluster(bar); else mbar_arrive(bar);
         };
@@ -486,6 +521,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                     const uint64_t gimg = SAVE ? reinterpret_cast<uint64_t>(save_tile + ((layer < 8) ? SAVE_H + 65536 * layer
                                                                                                     : SAVE_FEAT)) - act_base
                                                : 0ull;
+                    if (PAIR && (P.dbg & 2)) {
+                        // pair kernel with shared chunks: the accumulator arrives complete -> one pass, one fence, one hand-off
+                        mbar_wait(bar_h1, accf_par, 6);
+                        accf_par ^= 1;
+                        tc_fence_after();
+                        if (SAVE && !kDirectSave) {
+                            if (elected) bulk_wait_read0();
+                            named_bar_sync(1 + s, TILE_M);
+                        }
+                        if (ph == 8) trunk_full<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
+                        else if (relu) trunk_full<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
+                        else trunk_full<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, gimg);
+                        if (ph == 8) {
+                            float a, b;
+                            f2_unpack(sig2, a, b);
+                            sig = a + b;
+                        }
+                        tc_fence_before();
+                        fence_async();
+                        if (SAVE) {
+                            if (relu) {
+                                uint4* mp = reinterpret_cast<uint4*>(mask_tile + ((size_t)layer * 128 + row) * 8);
+                                mp[0] = make_uint4(mask[0], mask[1], mask[2], mask[3]);
+                                mp[1] = make_uint4(mask[4], mask[5], mask[6], mask[7]);
+                            }
+                            if (!kDirectSave) {
+                                named_bar_sync(1 + s, TILE_M);
+                                if (elected) {
+                                    int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
+                                    bulk_s2g(save_tile + off, act_base, 32768);
+                                    bulk_s2g(save_tile + off + 32768, act_base + 32768, 32768);
+                                    bulk_commit();
+                                }
+                            }
+                        }
+                        if (elected) trace_ev(P.trace, 2 + s, it, ph, 2);
+                        arrive(bar_lo);
+                        arrive(bar_hi);
+                        continue;
+                    }
                     if (ph == 8) trunk_part1<true, true, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held, gimg);
                     else if (relu) trunk_part1<true, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held, gimg);
                     else trunk_part1<false, false, SAVE>(t_lane, bias, wsig, sig2, mask, rs, held, gimg);

@@ -58,7 +58,8 @@ constexpr int SM_ACTR = SM_ACCF + 32;                      // 2 sub-tiles x 2 K-
 constexpr int SM_PFULL = SM_ACTR + 32;                     // STAGES mbarriers: peer CTA's ring slot is full (pair mode)
 constexpr int SM_TMEM = SM_PFULL + 8 * STAGES;             // u32
 constexpr int DIRB_ROWS = 5;                               // staged per-ray ddir biases per sub-tile (N >= 32 always fits)
-constexpr int SM_DIRB = (SM_TMEM + 16 + 15) & ~15;          // 2 x DIRB_ROWS x 128 floats (float4 aligned)
+constexpr int SM_TOK = SM_TMEM + 16;                       // 2 mbarriers: issue token of the alternating pair-mode issuers
+constexpr int SM_DIRB = (SM_TOK + 16 + 15) & ~15;           // 2 x DIRB_ROWS x 128 floats (float4 aligned)
 constexpr int SM_TOTAL = SM_DIRB + 2 * DIRB_ROWS * 512;
 constexpr int SMEM_BYTES = SM_TOTAL + 1024;                // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory limit");
@@ -130,10 +131,11 @@ __device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B, bool p
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(B.full + 8 * i, 1);
-            (void)shared_chunks;
-            mbar_init(B.empty + 8 * i, pair ? 1 : 2);   // releases per slot: single CTA: both sub-tiles' issuers; pair: one commit
+            mbar_init(B.empty + 8 * i, (pair && !shared_chunks) ? 1 : 2);   // commits per slot: one per consuming sub-tile
             mbar_init(B.pfull + 8 * i, 1);
         }
+        mbar_init(base + SM_TOK, 1);
+        mbar_init(base + SM_TOK + 8, 1);
         for (int i = 0; i < 4; ++i) {                 // index = sub-tile * 2 + half
             mbar_init(B.accf + 8 * i, 1);
             mbar_init(B.actr + 8 * i, pair ? 2 * TILE_M : TILE_M);
@@ -364,60 +366,61 @@ __device__ __forceinline__ void issuer_loop_pair(uint32_t base, const Barriers& 
     }
 }
 
-// Pair mode with SHARED weight chunks: ONE issuer thread (leader CTA) feeds the tensor pipe for both sub-tiles in strict
-// alternation -- sub-tile 0 phase p, sub-tile 1 phase p, sub-tile 0 phase p+1, ... -- so that the MMA windows of the two
+// Pair mode with SHARED weight chunks: two issuer threads (leader CTA, one per sub-tile) that ALTERNATE on the tensor pipe
+// through a token -- sub-tile 0 phase p, sub-tile 1 phase p, sub-tile 0 phase p+1, ... -- so that the MMA windows of the two
 // sub-tiles never interleave and each sub-tile's epilogue runs under the other's window.  Every chunk of a phase is loaded
-// once per CTA, consumed twice, and released by the commit that follows sub-tile 1's MMAs.  All barriers a window needs
-// (the phase's chunk barriers of both CTAs, then the A tile) are waited for BEFORE its first MMA, while the previous window
-// still executes: the 16 MMAs of a window are issued back to back.
+// once per CTA, consumed by both sub-tiles and released by both commits.  A thread waits for everything its window needs
+// (the phase's chunk barriers of both CTAs, its A tile) while the OTHER thread issues; holding the token it only issues:
+// a cta_group::2 MMA costs ~105 cycles to issue, 16 of them fit under the 2 048 cycles they take to execute.
 __device__ __forceinline__ void issuer_loop_pair_shared(uint32_t base, const Barriers& B, uint32_t tmem_base,
-                                                        const Program& prog, int n_tiles, long long* trace = nullptr) {
+                                                        const Program& prog, int s, int n_tiles, long long* trace = nullptr) {
     const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
     const uint32_t lbo_bits = (16u >> 4) << 16;
     const uint32_t ring0 = ((base + SM_RING) & 0x3FFFF) >> 4;
     const uint32_t idesc256 = make_idesc_bf16(256, 256, 0, 0), idesc128 = make_idesc_bf16(256, 128, 0, 0);
-    uint32_t g_base = 0;
-    uint32_t actr_par = 0;
+    const uint32_t a_tile = ((base + SM_ACT + s * 65536) & 0x3FFFF) >> 4;
+    const uint32_t d_tmem = tmem_base + s * 256;
+    const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;
+    const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;
+    const uint32_t tok_mine = base + SM_TOK + 8 * s, tok_other = base + SM_TOK + 8 * (1 - s);
+    uint32_t g_base = 0, actr_par = 0, n = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
-        for (int ph = 0; ph < prog.n_phases; ++ph) {
+        for (int ph = 0; ph < prog.n_phases; ++ph, ++n) {
             const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
             const uint32_t idesc = (n_ch == kbs) ? idesc128 : idesc256;
-            // the phase's weight chunks in both CTAs (usually long complete: they were prefetched behind sub-tile 1)
             for (int kb = 0; kb < kbs; ++kb) {
                 const uint32_t g = g_base + kb, lap = g / STAGES, slot = g - lap * STAGES;
                 mbar_wait(B.full + 8 * slot, lap & 1, 4);
                 mbar_wait_cluster(B.pfull + 8 * slot, lap & 1, 8);
             }
-            for (int s = 0; s < 2; ++s) {
-                const uint32_t a_tile = ((base + SM_ACT + s * 65536) & 0x3FFFF) >> 4;
-                const uint32_t d_tmem = tmem_base + s * 256;
-                const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;
-                const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;
-                trace_ev(trace, s, tile, ph, 0);
-                mbar_wait_cluster(bar_lo, actr_par, 3);
-                mbar_wait_cluster(bar_hi, actr_par, 5);
-                trace_ev(trace, s, tile, ph, 1);
-                tc_fence_after();
-                for (int kb = 0; kb < kbs; ++kb) {
-                    const uint32_t g = g_base + kb, lap = g / STAGES, slot = g - lap * STAGES;
-                    const uint32_t a_lo = (a_tile + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
-                    const uint32_t b_lo = (ring0 + slot * (CHUNK_BYTES >> 4)) | lbo_bits;
-                    const bool acc0 = (kb > 0) || (flags & PH_ACC);
-                    const int n_mma = ((flags & PH_ENC) && kb == 1) ? 1 : 4;
+            trace_ev(trace, s, tile, ph, 0);
+            mbar_wait_cluster(bar_lo, actr_par, 3);
+            mbar_wait_cluster(bar_hi, actr_par, 5);
+            // the token: sub-tile 0 owns it at the start; afterwards each window is handed over by the other thread
+            if (s == 1) mbar_wait(tok_mine, n & 1, 10);
+            else if (n > 0) mbar_wait(tok_mine, (n - 1) & 1, 10);
+            trace_ev(trace, s, tile, ph, 1);
+            tc_fence_after();
+            for (int kb = 0; kb < kbs; ++kb) {
+                const uint32_t g = g_base + kb, lap = g / STAGES, slot = g - lap * STAGES;
+                const uint32_t a_lo = (a_tile + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
+                const uint32_t b_lo = (ring0 + slot * (CHUNK_BYTES >> 4)) | lbo_bits;
+                const bool acc0 = (kb > 0) || (flags & PH_ACC);
+                const int n_mma = ((flags & PH_ENC) && kb == 1) ? 1 : 4;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (k < n_mma) {
-                            const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
-                            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
-                            mma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (acc0 || k > 0) ? 1u : 0u);
-                        }
+                for (int k = 0; k < 4; ++k) {
+                    if (k < n_mma) {
+                        const uint64_t ad = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                        mma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (acc0 || k > 0) ? 1u : 0u);
                     }
-                    if (s == 1) mma_commit_2cta(B.empty + 8 * slot, 0x3);      // both sub-tiles are done with the chunk
                 }
-                mma_commit_2cta(bar_h0, 0x3);
-                mma_commit_2cta(bar_h1, 0x3);
-                trace_ev(trace, s, tile, ph, 2);
+                mma_commit_2cta(B.empty + 8 * slot, 0x3);      // the slot is recycled when both sub-tiles' commits arrived
             }
+            mma_commit_2cta(bar_h0, 0x3);
+            mma_commit_2cta(bar_h1, 0x3);
+            mbar_arrive(tok_other);
+            trace_ev(trace, s, tile, ph, 2);
             actr_par ^= 1;
             g_base += kbs;
         }
