@@ -76,7 +76,7 @@ def main():
     ap.add_argument("--npz", required=True)
     args = ap.parse_args()
     conf = json.load(open(args.config))
-    use_bn = bool(conf.get("BATCH_NORM", False))     # the B200 path renders BN checkpoints (folded), it does not train them
+    use_bn = bool(conf.get("BATCH_NORM", False))     # the B200 path renders BN checkpoints on the fused kernels (folded) and trains them on its layer-by-layer path
     roles, shapes = expected_shapes(conf)
     trainer = build_trainer(conf)
     nets = (("coarse", trainer.coarse_model), ("fine", trainer.fine_model))
