@@ -44,6 +44,9 @@ def main():
     trainer.forward_pass_with_minibatch(o_w.reshape(-1, 3), d_w.reshape(-1, 3),
                                         nk.generate_t_vals(near, far, H * W, Nc, rand_sampling=False),
                                         batch_size=args.tile, maps_only=True)
+    if world > 1:
+        # the gather's point-to-point channels are set up on first use: do that outside the timed sweep, like the kernels' warm-up
+        gather_rows(torch.zeros((1, 8, 8, 3), dtype=torch.uint8, device="cuda"))
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
