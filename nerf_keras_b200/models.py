@@ -443,9 +443,6 @@ class NeRFTrainer:
                               "un-stopped term (models.py:166-175) is not carried through this path (DESIGN.md)")
             # BATCH_NORM=true: batch statistics couple all samples of a batch between consecutive layers, so training
             # runs on the layer-by-layer fp32 path (csrc/bn_train.cu); rendering keeps the fused kernels (folded BN).
-            if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                                  and torch.distributed.get_world_size() > 1):
-                raise NotImplementedError("data-parallel training with BATCH_NORM=true is not supported")
             self.optimizer = optimizer
             self._rebuild_ctx_inference_only()
             self._bn_init_state()
@@ -539,7 +536,20 @@ class NeRFTrainer:
                                               _ptr(st["ws"]), st["ws"].numel(), _stream()), "bn train_step")
         st["step"] += 1
         lr, n, nbn = float(self.optimizer.learning_rate), st["n"], st["nbn"]
-        adam = lambda p, g, m, v, k: _lib.check(L.nerf_adam_flat(p, g, m, v, k, st["step"], lr, 1.0, _stream()), "adam")
+        # data parallel (train_tpu_*.py): gradients of the Dense and BatchNormalization parameters are averaged over the
+        # replicas; batch statistics stay per replica (Keras' BatchNormalization is not synchronised across replicas) and the
+        # moving statistics are averaged, which is what a MEAN-aggregated replica variable ends up holding
+        world, scale = self._world(), 1.0
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(st["grads"], group=self.process_group)
+            dist.all_reduce(st["bn_grads"], group=self.process_group)
+            for i in range(2):
+                mv = st["bn"][4 * i * nbn + 2 * nbn:4 * (i + 1) * nbn]
+                dist.all_reduce(mv, group=self.process_group)
+                mv.mul_(1.0 / world)
+            scale = 1.0 / world
+        adam = lambda p, g, m, v, k: _lib.check(L.nerf_adam_flat(p, g, m, v, k, st["step"], lr, scale, _stream()), "adam")
         adam(_ptr(st["params"]), _ptr(st["grads"]), _ptr(st["m"]), _ptr(st["v"]), 2 * n)
         for i in range(2):      # gamma | beta of each net are the first 2 nbn floats of its [gamma | beta | mean | var] block
             e = 4 * i * nbn * 4

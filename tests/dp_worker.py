@@ -75,6 +75,26 @@ def main():
                     "median_abs_diff_vs_1gpu": float((wa - wb).abs().median()),
                     "graphs": len(a._graphs), "steps": a._ctx.optimizer_state()[2]}
         keep += [a, b]
+    # (3) BATCH_NORM=true under data parallelism: per-replica batch statistics (as Keras), averaged gradients and moving
+    # statistics -> every rank holds the same weights and BN parameters after every step, and the loss goes down
+    import warnings
+    warnings.simplefilter("ignore")
+    mcb = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+    mfb = nk.create_nerf_complete_model(8, 256, 4, 10, 4, bn=True)
+    mcb.set_flat_weights(O.flatten_weights(wc)); mfb.set_flat_weights(O.flatten_weights(wf))
+    nb = 64
+    trb = nk.NeRFTrainer(mcb, mfb, nb, Nc, Nf, 10, 4, stop_grad_samples=True)
+    trb.compile(nk.Adam(5e-4), nk.MeanSquaredError())
+    sb = [x[rank * nb:(rank + 1) * nb].contiguous() for x in (img, o, d, t, u)]
+    losses = []
+    for _ in range(6):
+        trb.reset_metrics()
+        losses.append(float(trb.train_step((sb[0], (sb[1], sb[2], sb[3])), u_pdf=sb[4])["loss"]))
+    wbn = torch.from_numpy(np.concatenate([mcb.get_flat_weights(), mfb.get_flat_weights()] +
+                                          [mcb.get_bn_params()[r][k] for r in mcb.bn for k in ("gamma", "beta", "mean", "var")])).to(dev)
+    ref = wbn.clone()
+    torch.distributed.broadcast(ref, 0)
+    res["batch_norm_dp"] = {"ranks_identical": bool(torch.equal(ref, wbn)), "first_loss": losses[0], "last_loss": losses[-1]}
     if rank == 0:
         print("DP_RESULT " + json.dumps(res), flush=True)
     from nerf_keras_b200.dist import shutdown

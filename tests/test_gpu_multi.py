@@ -6,6 +6,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -33,3 +34,5 @@ def test_two_gpu_gradients_equal_single_gpu_on_concatenated_batch():
         assert r["ranks_identical"] and r["steps"] == 4, (tag, r)
         assert r["update_cosine_vs_1gpu"] >= 0.98 and r["median_abs_diff_vs_1gpu"] <= 2e-5, (tag, r)
     assert res["overlap_graph"]["graphs"] == 1
+    bn = res["batch_norm_dp"]
+    assert bn["ranks_identical"] and np.isfinite(bn["last_loss"]) and bn["last_loss"] < bn["first_loss"], bn

@@ -278,3 +278,37 @@ def test_train_step_vs_reference_source(nk, R, tag):
     big = np.abs(mv_ref) > 4.5e-4                                       # |g| well above eps: a full-size +-lr step
     agree = np.mean(np.sign(mv[big]) == np.sign(mv_ref[big]))
     assert big.mean() > 0.3 and agree > 0.97, (big.mean(), agree)
+
+
+def test_graph_cache_follows_buffers_and_batch_sizes(nk):
+    """One graph per distinct set of input buffers (and batch size); eager steps for buffers seen once; release_graphs()."""
+    from nerf_keras_b200.synthetic import HostPrefetcher
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    tr = _trainer(nk, wc, wf, 96, 16, 32, stop_grad_samples=True)
+    full = _dev_batch(g)[:4]
+    half = tuple(x[:48].contiguous() for x in full)
+    for _ in range(3):
+        tr.train_step((full[0], full[1:4]))
+        tr.train_step((half[0], half[1:4]))
+    assert len(tr._graphs) == 2 and tr._ctx.optimizer_state()[2] == 6
+    # temporaries (new device tensors every call) never match a captured graph: plain eager steps, same result path
+    for _ in range(3):
+        tr.train_step((g["img"], (g["o"], g["d"], g["t"])))
+    assert tr._ctx.optimizer_state()[2] == 9
+    # a host prefetcher hands out two alternating staging slots, also after being re-iterated: two more graphs, not more
+    host = [tuple(torch.from_numpy(np.ascontiguousarray(g[k])).pin_memory() for k in ("img", "o", "d", "t")) for _ in range(2)]
+    pf = HostPrefetcher((host[i % 2] for i in range(1 << 20)), torch.device("cuda"))
+    n0 = len(tr._graphs)
+    for rep in range(2):
+        it = iter(pf)
+        for _ in range(5):
+            img, o, d, t = next(it)
+            tr.train_step((img, (o, d, t)))
+    assert len(tr._graphs) - n0 <= 2 and tr._ctx.optimizer_state()[2] == 19
+    losses = float(tr.loss_tracker.result())
+    assert np.isfinite(losses)
+    tr.release_graphs()
+    assert len(tr._graphs) == 0
+    tr.train_step((full[0], full[1:4]))
+    assert tr._ctx.optimizer_state()[2] == 20
