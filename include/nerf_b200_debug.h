@@ -41,12 +41,20 @@ int nerf_selftest_gemm_ts(const float* a, const float* b, float* c, int n, int k
                           long long* cycles_dev, void* stream);
 /* Selects an experimental variant of the fused forward kernel (same results within bf16 rounding; slower than the default,
    kept for the measurements in DESIGN.md): 0 = default single-CTA kernel, 1 = CTA pair (cta_group::2, M = 256 MMAs over an
-   SM pair), 4 = CTA pair with the activations resident in tensor memory (TMEM-A "TS" MMAs). */
+   SM pair), 17 = CTA pair with every weight chunk staged once for both sub-tiles, 49 = 17 with a CTA-scope proxy fence,
+   4 = CTA pair with the activations resident in tensor memory (TMEM-A "TS" MMAs), 64 = single CTA with weight-stationary
+   MMA pairs (tcgen05.mma.ws, B kept in the collector) from one issuer warp, 192 = the same issue order with plain MMAs,
+   320 = weight-stationary pairs from two issuer warps (one per N-half, collector buffers b0 / b1). */
 int nerf_debug_pair_mode(int on);
 /* MMA issue-rate probe (cycles for `reps` x 4 back-to-back 128 x n x 16 MMAs). */
 int nerf_selftest_mma_rate(int n, int reps, int mode, long long* cycles_dev, void* stream);
 /* Self-test of the tcgen05 building block: C (M,N) fp32 = A (M,K) bf16-rounded x B^T, B (N,K). */
 int nerf_selftest_gemm(const float* a, const float* b, float* c, int m, int n, int k, int mode, void* stream);
+
+/* Probe of the tcgen05 collector variants: two A tiles against one B tile.  variant 0 plain, 1 tcgen05.mma.ws with B kept
+   in the collector for the second MMA, 2 A kept across the two N-halves (n = 256).  C1 = A1 B^T, C2 = A2 B^T, (128, n). */
+int nerf_selftest_collector(const float* a1, const float* a2, const float* b, float* c1, float* c2, int n, int k, int variant,
+                            int reps, long long* cycles_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,7 @@ SIGNATURES = {
     "nerf_selftest_gemm_2cta": (_I, [_P, _P, _P, _I, _I, _P]),
     "nerf_selftest_gemm_ts": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nerf_selftest_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "nerf_selftest_collector": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "nerf_bn_param_count": (_L, [_P]),
     "nerf_bn_workspace_bytes": (_L, [_P, _L]),
     "nerf_bn_forward_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _L, _P]),

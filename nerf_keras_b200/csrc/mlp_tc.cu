@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
     const int64_t n_units = PAIR ? (P.n_pairs + 1) / 2 : P.n_pairs;
     Barriers B;
     const bool shared_chunks = PAIR && (P.dbg & 2);     // pair mode: one ring fill per chunk, consumed by both sub-tiles
-    init_barriers(base, B, PAIR, shared_chunks);
+    const bool ws_issue = !PAIR && (P.dbg & 8);         // weight-stationary MMAs: one issuer, B read once for both sub-tiles
+    init_barriers(base, B, PAIR, shared_chunks, ws_issue);
     float* side = reinterpret_cast<float*>(smem + SM_SIDE);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_TMEM);
     if (warp == 9) {
@@ -393,6 +394,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
             if (PAIR) producer_loop_pair(base, B, P.w_chunks, c_fwd_prog, rank, my_pairs, shared_chunks);
             else producer_loop(base, B, P.w_chunks, N_CHUNKS, total_chunks);
         }
+    } else if (warp >= 9 && !PAIR && ws_issue) {
+        // weight-stationary issue: the whole warp runs the loop (uniform datapath), one lane's MMAs are predicated on
+        if (P.dbg & 32) {          // two issuer warps, one per N-half
+            if (warp == 9) issuer_loop_ws2<0>(base, B, tmem_base, c_fwd_prog, my_pairs, P.trace);
+            else issuer_loop_ws2<1>(base, B, tmem_base, c_fwd_prog, my_pairs, P.trace);
+        } else if (warp == 9) issuer_loop_ws(base, B, tmem_base, c_fwd_prog, my_pairs, P.trace, (P.dbg & 16) != 0);
     } else if (warp >= 9) {
         if (lane == 0) {
             if (!PAIR) issuer_loop(base, B, tmem_base, c_fwd_prog, warp - 9, my_pairs, P.trace);

@@ -125,13 +125,14 @@ struct Barriers {
 };
 
 // pair = true: the CTA is one half of a cta_group::2 pair; the leader's A-tile barriers also collect the peer's workers
-__device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B, bool pair = false, bool shared_chunks = false) {
+__device__ __forceinline__ void init_barriers(uint32_t base, Barriers& B, bool pair = false, bool shared_chunks = false,
+                                              bool one_issuer = false) {
     B.full = base + SM_FULL; B.empty = base + SM_EMPTY; B.accf = base + SM_ACCF; B.actr = base + SM_ACTR;
     B.pfull = base + SM_PFULL;
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(B.full + 8 * i, 1);
-            mbar_init(B.empty + 8 * i, (pair && !shared_chunks) ? 1 : 2);   // commits per slot: one per consuming sub-tile
+            mbar_init(B.empty + 8 * i, ((pair && !shared_chunks) || one_issuer) ? 1 : 2);   // commits per slot
             mbar_init(B.pfull + 8 * i, 1);
         }
         mbar_init(base + SM_TOK, 1);
@@ -223,6 +224,143 @@ __device__ __forceinline__ void issuer_loop(uint32_t base, const Barriers& B, ui
             mma_commit(bar_h1);
             actr_par ^= 1;
             trace_ev(trace, s, tile, ph, 2);              // issuer: all MMAs of the phase issued
+        }
+    }
+}
+
+// ---- weight-stationary issue: ONE issuer thread for both sub-tiles -----------------------------------------------------
+// Both sub-tiles multiply their own A tile with the SAME weight chunk.  tcgen05.mma.ws keeps the B operand of an MMA in the
+// collector: the pair (sub-tile 0: B_KEEP, sub-tile 1: B_REUSE) reads the 4 KB B slice from shared memory once instead of
+// twice -- a quarter of the MMA operand traffic of the kernel, which is bound by exactly that (512 -> 384 KB per phase pair).
+// The sub-tiles then advance in lockstep chunk by chunk; the N-half structure still overlaps the epilogue of columns 0..127
+// with the MMAs of columns 128..255, and the K-half release overlaps the second epilogue half with the next phase's start.
+__device__ __forceinline__ void issuer_loop_ws(uint32_t base, const Barriers& B, uint32_t tmem_base, const Program& prog,
+                                               int n_tiles, long long* trace = nullptr, bool plain = false) {
+    // executed by ALL lanes of the issuer warp (warp-uniform control flow); MMAs and commits are predicated on lane 0
+    const uint32_t elect = (threadIdx.x & 31) == 0 ? 1u : 0u;
+    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
+    const uint32_t lbo_bits = (16u >> 4) << 16;
+    const uint32_t a_tile0 = ((base + SM_ACT) & 0x3FFFF) >> 4, a_tile1 = ((base + SM_ACT + 65536) & 0x3FFFF) >> 4;
+    const uint32_t ring0 = ((base + SM_RING) & 0x3FFFF) >> 4;
+    const int n_phases = prog.n_phases;
+    int slot = 0;
+    uint32_t ring_par = 0, actr_par = 0;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        for (int ph = 0; ph < n_phases; ++ph) {
+            const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
+            const int hi_kb = (kbs >= 4) ? (kbs >> 1) : 0;
+            if (elect) trace_ev(trace, 0, tile, ph, 0);
+            mbar_wait(B.actr, actr_par, 3);                 // K-blocks 0,1 of both A tiles
+            mbar_wait(B.actr + 16, actr_par, 3);
+            if (hi_kb == 0) { mbar_wait(B.actr + 8, actr_par, 5); mbar_wait(B.actr + 24, actr_par, 5); }
+            if (elect) trace_ev(trace, 0, tile, ph, 1);
+            int h = 0, kb = 0;
+            for (int j = 0; j < n_ch; ++j) {
+                if (h == 0 && kb == hi_kb && hi_kb != 0) { mbar_wait(B.actr + 8, actr_par, 5); mbar_wait(B.actr + 24, actr_par, 5); }
+                mbar_wait(B.full + 8 * slot, ring_par, 4);
+                tc_fence_after();
+                const uint32_t a0_lo = (a_tile0 + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
+                const uint32_t a1_lo = (a_tile1 + kb * ((TILE_M * 128) >> 4)) | lbo_bits;
+                const uint32_t b_lo = (ring0 + slot * (CHUNK_BYTES >> 4)) | lbo_bits;
+                const uint32_t d0 = tmem_base + h * 128, d1 = tmem_base + 256 + h * 128;
+                const bool acc0 = (kb > 0) || (flags & PH_ACC);
+                const int n_mma = ((flags & PH_ENC) && kb == 1) ? 1 : 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < n_mma) {
+                        const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                        const uint64_t ad0 = ((uint64_t)desc_hi << 32) | (uint64_t)(a0_lo + 2 * k);
+                        const uint64_t ad1 = ((uint64_t)desc_hi << 32) | (uint64_t)(a1_lo + 2 * k);
+                        const uint32_t acc = (acc0 || k > 0) ? 1u : 0u;
+                        if (plain) {     // experiment: the same single-warp issue order with ordinary MMAs
+                            mma_bf16_uniform<0>(d0, ad0, bd, idesc, acc, elect);
+                            mma_bf16_uniform<0>(d1, ad1, bd, idesc, acc, elect);
+                        } else {
+                            mma_bf16_uniform<1>(d0, ad0, bd, idesc, acc, elect);
+                            mma_bf16_uniform<2>(d1, ad1, bd, idesc, acc, elect);
+                        }
+                    }
+                }
+                mma_commit_uniform(B.empty + 8 * slot, elect);
+                if (++slot == STAGES) { slot = 0; ring_par ^= 1; }
+                if (++kb == kbs) {
+                    kb = 0;
+                    if (h == 0 && j + 1 < n_ch) { mma_commit_uniform(B.accf, elect); mma_commit_uniform(B.accf + 16, elect); }
+                    ++h;
+                }
+            }
+            if (n_ch == kbs) { mma_commit_uniform(B.accf, elect); mma_commit_uniform(B.accf + 16, elect); }
+            mma_commit_uniform(B.accf + 8, elect);
+            mma_commit_uniform(B.accf + 24, elect);
+            actr_par ^= 1;
+            if (elect) trace_ev(trace, 0, tile, ph, 2);
+        }
+    }
+}
+
+// Two-warp version of the weight-stationary issue: warp `half` = 0 issues the MMAs of columns 0..127 (N-half 0) of BOTH
+// sub-tiles, warp 1 those of columns 128..255, each keeping the shared B slice in its own collector buffer (b0 / b1).  The two
+// warps own disjoint accumulator columns and disjoint chunks of the ring (every chunk is consumed by exactly one of them), so a
+// single busy warp no longer has to issue all 64 MMAs of a phase (~165 cycles per MMA next to eight epilogue warps).
+template <int HALF>
+__device__ __forceinline__ void issuer_loop_ws2(uint32_t base, const Barriers& B, uint32_t tmem_base, const Program& prog,
+                                                int n_tiles, long long* trace = nullptr) {
+    const uint32_t elect = (threadIdx.x & 31) == 0 ? 1u : 0u;
+    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t desc_hi = (uint32_t)((1024u >> 4) | (1u << 14) | (2u << 29));
+    const uint32_t lbo_bits = (16u >> 4) << 16;
+    const uint32_t a_tile0 = ((base + SM_ACT) & 0x3FFFF) >> 4, a_tile1 = ((base + SM_ACT + 65536) & 0x3FFFF) >> 4;
+    const uint32_t ring0 = ((base + SM_RING) & 0x3FFFF) >> 4;
+    // __shfl_sync results are known to be warp-uniform: the descriptor arithmetic below then stays on the uniform datapath
+    // instead of going through an ELECT / R2UR.BROADCAST loop per MMA
+    const uint32_t d0 = __shfl_sync(0xffffffffu, tmem_base + HALF * 128, 0), d1 = d0 + 256;
+    const int n_phases = prog.n_phases;
+    uint32_t g = 0;             // ring position of the current phase's first chunk
+    uint32_t actr_par = 0;
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        for (int ph = 0; ph < n_phases; ++ph) {
+            const int n_ch = prog.chunks[ph], kbs = prog.kb[ph], flags = prog.flags[ph];
+            const bool single = (n_ch == kbs);                // the phase has N-half 0 only (128-wide layer)
+            const int hi_kb = (kbs >= 4) ? (kbs >> 1) : 0;
+            // every phase of the hand-off barriers has to be observed (also by the warp that has no work in a 128-wide phase):
+            // a parity wait on a phase that has not even started yet succeeds at once
+            if (elect) trace_ev(trace, HALF, tile, ph, 0);
+            mbar_wait(B.actr, actr_par, 3);
+            mbar_wait(B.actr + 16, actr_par, 3);
+            if (HALF == 1 || hi_kb == 0) { mbar_wait(B.actr + 8, actr_par, 5); mbar_wait(B.actr + 24, actr_par, 5); }
+            if (elect) trace_ev(trace, HALF, tile, ph, 1);
+            if (HALF == 0 || !single) {
+                for (int kb = 0; kb < kbs; ++kb) {
+                    if (HALF == 0 && kb == hi_kb && hi_kb != 0) { mbar_wait(B.actr + 8, actr_par, 5); mbar_wait(B.actr + 24, actr_par, 5); }
+                    const uint32_t pos = g + HALF * kbs + kb, lap = pos / STAGES, slot = pos - lap * STAGES;
+                    mbar_wait(B.full + 8 * slot, lap & 1, 4);
+                    tc_fence_after();
+                    const uint32_t a0_lo = __shfl_sync(0xffffffffu, (a_tile0 + kb * ((TILE_M * 128) >> 4)) | lbo_bits, 0);
+                    const uint32_t a1_lo = a0_lo + (65536 >> 4);
+                    const uint32_t b_lo = __shfl_sync(0xffffffffu, (ring0 + slot * (CHUNK_BYTES >> 4)) | lbo_bits, 0);
+                    const bool acc0 = (kb > 0) || (flags & PH_ACC);
+                    const int n_mma = ((flags & PH_ENC) && kb == 1) ? 1 : 4;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < n_mma) {
+                            const uint64_t bd = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                            const uint64_t ad0 = ((uint64_t)desc_hi << 32) | (uint64_t)(a0_lo + 2 * k);
+                            const uint64_t ad1 = ((uint64_t)desc_hi << 32) | (uint64_t)(a1_lo + 2 * k);
+                            const uint32_t acc = (acc0 || k > 0) ? 1u : 0u;
+                            mma_bf16_uniform<HALF == 0 ? 1 : 3>(d0, ad0, bd, idesc, acc, elect);
+                            mma_bf16_uniform<HALF == 0 ? 2 : 4>(d1, ad1, bd, idesc, acc, elect);
+                        }
+                    }
+                    mma_commit_uniform(B.empty + 8 * slot, elect);
+                }
+                mma_commit_uniform(B.accf + 8 * HALF, elect);           // this N-half of sub-tile 0 ...
+                mma_commit_uniform(B.accf + 16 + 8 * HALF, elect);      // ... and of sub-tile 1
+                if (HALF == 0 && single) { mma_commit_uniform(B.accf + 8, elect); mma_commit_uniform(B.accf + 24, elect); }
+                if (elect) trace_ev(trace, HALF, tile, ph, 2);
+            }
+            actr_par ^= 1;
+            g += n_ch;
         }
     }
 }

@@ -746,6 +746,146 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int reps, int m
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Collector probe: two 128-row A tiles against ONE B tile (the situation of the forward kernel's two sub-tiles and a
+// shared weight chunk).  variant 0: plain SS MMAs; 1: tcgen05.mma.ws with B kept in the collector for the second MMA;
+// 2: plain MMAs with A kept in the collector across two N-halves.  C1 = A1 x B^T, C2 = A2 x B^T (128 x N each).
+// reps > 1 (with K = 64): rate probe -- descriptors precomputed, nothing but accumulating MMAs in the loop.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) collector_probe_kernel(const float* __restrict__ A1, const float* __restrict__ A2,
+                                                                 const float* __restrict__ Bm, float* __restrict__ C1,
+                                                                 float* __restrict__ C2, int N, int K, int variant, int reps,
+                                                                 long long* __restrict__ cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t a_bytes = 128 * K * 2, b_bytes = N * K * 2;
+    uint8_t* a1_img = smem;
+    uint8_t* a2_img = smem + a_bytes;
+    uint8_t* b_img = smem + 2 * a_bytes;
+    const uint32_t bar = base + 2 * a_bytes + b_bytes;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + 2 * a_bytes + b_bytes + 16);
+    for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+        const int r = i / K, k = i - r * K;
+        const uint32_t off = (k >> 6) * (128 * 128) + sw128_offset(r, k & 63);
+        *reinterpret_cast<__nv_bfloat16*>(a1_img + off) = __float2bfloat16(A1[i]);
+        *reinterpret_cast<__nv_bfloat16*>(a2_img + off) = __float2bfloat16(A2[i]);
+    }
+    for (int i = threadIdx.x; i < N * K; i += blockDim.x) {          // B as N/128 blocks of [128 n x K], K-blocks of 64 inside
+        const int r = i / K, k = i - r * K;
+        const uint32_t off = (r >> 7) * (128 * K * 2) + (k >> 6) * (128 * 128) + sw128_offset(r & 127, k & 63);
+        *reinterpret_cast<__nv_bfloat16*>(b_img + off) = __float2bfloat16(Bm[i]);
+    }
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(base + 2 * a_bytes + b_bytes + 16, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+        long long t0 = clock64();
+        if (reps > 1 && K == 64) {
+            uint64_t a1d[4], a2d[4], b0d[4], b1d[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                a1d[kk] = make_sdesc_sw128(base + kk * 32, 16, 1024);
+                a2d[kk] = make_sdesc_sw128(base + a_bytes + kk * 32, 16, 1024);
+                b0d[kk] = make_sdesc_sw128(base + 2 * a_bytes + kk * 32, 16, 1024);
+                b1d[kk] = make_sdesc_sw128(base + 2 * a_bytes + (N == 256 ? 128 * K * 2 : 0) + kk * 32, 16, 1024);
+            }
+            t0 = clock64();
+            for (int rep = 0; rep < reps; ++rep) {      // four MMAs per k-step in every variant: (A1, A2) x (B half 0, B half 1)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    if (variant == 1) {
+                        mma_bf16_ss_ws(tmem_base, a1d[kk], b0d[kk], idesc, 1u, 0);
+                        mma_bf16_ss_ws(tmem_base + 256, a2d[kk], b0d[kk], idesc, 1u, 1);
+                        mma_bf16_ss_ws(tmem_base + 128, a1d[kk], b1d[kk], idesc, 1u, 0);
+                        mma_bf16_ss_ws(tmem_base + 384, a2d[kk], b1d[kk], idesc, 1u, 1);
+                    } else if (variant == 2) {
+                        mma_bf16_ss_akeep(tmem_base, a1d[kk], b0d[kk], idesc, 1u, 0);
+                        mma_bf16_ss_akeep(tmem_base + 128, a1d[kk], b1d[kk], idesc, 1u, 1);
+                        mma_bf16_ss_akeep(tmem_base + 256, a2d[kk], b0d[kk], idesc, 1u, 0);
+                        mma_bf16_ss_akeep(tmem_base + 384, a2d[kk], b1d[kk], idesc, 1u, 1);
+                    } else if (variant == 3) {      // plain, ONE accumulator
+                        mma_bf16_ss(tmem_base, a1d[kk], b0d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base, a2d[kk], b0d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base, a1d[kk], b1d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base, a2d[kk], b1d[kk], idesc, 1u);
+                    } else if (variant == 4) {      // plain, two accumulators alternating per MMA
+                        mma_bf16_ss(tmem_base, a1d[kk], b0d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base + 256, a2d[kk], b0d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base, a1d[kk], b1d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base + 256, a2d[kk], b1d[kk], idesc, 1u);
+                    } else if (variant == 5) {      // plain, accumulator changes once per k-step group (4 MMAs per accumulator)
+                        const uint32_t d = tmem_base + (rep & 3) * 128;
+                        mma_bf16_ss(d, a1d[kk], b0d[kk], idesc, 1u);
+                        mma_bf16_ss(d, a2d[kk], b0d[kk], idesc, 1u);
+                        mma_bf16_ss(d, a1d[kk], b1d[kk], idesc, 1u);
+                        mma_bf16_ss(d, a2d[kk], b1d[kk], idesc, 1u);
+                    } else if (variant == 6) {      // .ws, ONE accumulator pair (keep / reuse alternate, accumulators alternate)
+                        mma_bf16_ss_ws(tmem_base, a1d[kk], b0d[kk], idesc, 1u, 0);
+                        mma_bf16_ss_ws(tmem_base + 256, a2d[kk], b0d[kk], idesc, 1u, 1);
+                        mma_bf16_ss_ws(tmem_base, a1d[kk], b1d[kk], idesc, 1u, 0);
+                        mma_bf16_ss_ws(tmem_base + 256, a2d[kk], b1d[kk], idesc, 1u, 1);
+                    } else {
+                        mma_bf16_ss(tmem_base, a1d[kk], b0d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base + 256, a2d[kk], b0d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base + 128, a1d[kk], b1d[kk], idesc, 1u);
+                        mma_bf16_ss(tmem_base + 384, a2d[kk], b1d[kk], idesc, 1u);
+                    }
+                }
+            }
+        } else {
+            for (int nh = 0; nh < N / 128; ++nh) {
+                for (int k16 = 0; k16 < K / 16; ++k16) {
+                    const int kb = k16 >> 2, kk = k16 & 3;
+                    const uint64_t a1 = make_sdesc_sw128(base + kb * (128 * 128) + kk * 32, 16, 1024);
+                    const uint64_t a2 = make_sdesc_sw128(base + a_bytes + kb * (128 * 128) + kk * 32, 16, 1024);
+                    const uint64_t bd = make_sdesc_sw128(base + 2 * a_bytes + nh * (128 * K * 2) + kb * (128 * 128) + kk * 32, 16, 1024);
+                    const uint32_t acc = (k16 > 0) ? 1u : 0u;
+                    const uint32_t d1 = tmem_base + nh * 128, d2 = tmem_base + 256 + nh * 128;
+                    if (variant == 1) {
+                        mma_bf16_ss_ws(d1, a1, bd, idesc, acc, 0);
+                        mma_bf16_ss_ws(d2, a2, bd, idesc, acc, 1);
+                    } else if (variant == 2) {      // A kept: the same (a, b) product twice would double the result, so keep + plain second tile
+                        mma_bf16_ss_akeep(d1, a1, bd, idesc, acc, 0);
+                        mma_bf16_ss_akeep(d2, a2, bd, idesc, acc, 0);
+                    } else {
+                        mma_bf16_ss(d1, a1, bd, idesc, acc);
+                        mma_bf16_ss(d2, a2, bd, idesc, acc);
+                    }
+                }
+            }
+        }
+        mma_commit(bar);
+        mbar_wait(bar, 0, 9);
+        if (cycles) cycles[0] = clock64() - t0;
+    }
+    __syncthreads();
+    mbar_wait(bar, 0, 9);
+    tc_fence_after();
+    const int row = threadIdx.x;
+    for (int cg = 0; cg < N / 32; ++cg) {
+        uint32_t v[32], w[32];
+        tmem_ld32(tmem_base + (uint32_t(32 * warp) << 16) + cg * 32, v);
+        tmem_ld32(tmem_base + (uint32_t(32 * warp) << 16) + 256 + cg * 32, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            C1[(int64_t)row * N + cg * 32 + q] = __uint_as_float(v[q]);
+            C2[(int64_t)row * N + cg * 32 + q] = __uint_as_float(w[q]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 namespace nerf {
@@ -831,3 +971,16 @@ extern "C" int nerf_selftest_gemm_ts(const float* a, const float* b, float* c, i
     return NERF_OK;
 }
 
+
+// Probe of the MMA collector variants (see collector_probe_kernel): C1 = A1 x B^T, C2 = A2 x B^T, both (128, n).
+extern "C" int nerf_selftest_collector(const float* a1, const float* a2, const float* b, float* c1, float* c2, int n, int k,
+                                       int variant, int reps, long long* cycles_dev, void* stream) {
+    NERF_CHECK_ARG(a1 && a2 && b && c1 && c2 && (n == 128 || n == 256) && k >= 64 && k <= 256 && (k % 64) == 0, "bad arguments");
+    NERF_CHECK_ARG(variant >= 0 && variant <= 6 && reps >= 1 && (variant <= 2 || reps > 1), "variant 0..2 (3..6: rate probes, reps > 1)");
+    size_t smem = (size_t)(256 + n) * k * 2 + 64 + 1024;
+    NERF_CHECK_ARG(smem <= 227 * 1024, "operands do not fit in shared memory");
+    NERF_CUDA(cudaFuncSetAttribute(collector_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    collector_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a1, a2, b, c1, c2, n, k, variant, reps, cycles_dev);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}

@@ -129,6 +129,97 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Collector variants.  tcgen05.mma keeps the A operand of the previous MMA in the collector (A_KEEP / A_REUSE in SASS);
+// tcgen05.mma.ws ("weight stationary") keeps B: two MMAs that multiply DIFFERENT A tiles with the SAME B tile read B from
+// shared memory once (B_KEEP / B_REUSE).  usage: 0 = fill (read + keep), 1 = lastuse (reuse, then release).
+__device__ __forceinline__ void mma_bf16_ss_ws(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate, int usage) {
+    if (usage == 0)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// Warp-uniform issue: ALL lanes of the issuer warp execute the surrounding code, the instruction itself is predicated on
+// `elect` (one lane).  The descriptors are then computed in the uniform datapath (UTCHMMA takes them from uniform registers;
+// under a divergent `if (lane == 0)` every operand costs an R2UR move, ~100 cycles per MMA for a single issuing thread).
+template <int USAGE /* 0 plain, 1 .ws B fill, 2 .ws B lastuse, 3 / 4: the same on collector buffer b1 */>
+__device__ __forceinline__ void mma_bf16_uniform(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate, uint32_t elect) {
+    if (USAGE == 3)
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.ws.cta_group::1.kind::f16.collector::b1::fill [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elect)
+            : "memory");
+    else if (USAGE == 4)
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.ws.cta_group::1.kind::f16.collector::b1::lastuse [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elect)
+            : "memory");
+    else if (USAGE == 1)
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::fill [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elect)
+            : "memory");
+    else if (USAGE == 2)
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.ws.cta_group::1.kind::f16.collector::b0::lastuse [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elect)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elect)
+            : "memory");
+}
+__device__ __forceinline__ void mma_commit_uniform(uint32_t bar, uint32_t elect) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(elect)
+        : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss_akeep(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate, int usage) {
+    if (usage == 0)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
 // mbarrier arrives (count 1) when all previously issued MMAs of this thread have completed.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {

@@ -16,7 +16,7 @@ u = torch.rand(B, Nf, device="cuda")
 L.nerf_debug_pair_mode(0)
 ref = tr.mlp_forward_rays("coarse", o, d, t).clone()
 torch.cuda.synchronize()
-for pm in (17, 49):
+for pm in (1, 17, 49, 64, 320):
     L.nerf_debug_pair_mode(pm)
     for rep in range(2):
         got = tr.mlp_forward_rays("coarse", o, d, t).clone()
@@ -24,7 +24,7 @@ for pm in (17, 49):
         bad = ((got - ref).abs() > 1e-3).any(-1).any(-1)
         print(f"pair mode {pm} rep {rep}: max abs diff {(got - ref).abs().max().item():.3e}; rays with diff {int(bad.sum())} of {B}; "
               f"first bad {bad.nonzero()[:8].flatten().tolist()}", flush=True)
-for mode in (0, 17, 49):
+for mode in (0, 1, 17, 49, 64, 320):
     L.nerf_debug_pair_mode(mode)
     for _ in range(3): tr.forward_pass(o, d, t, u_pdf=u, maps_only=True)
     torch.cuda.synchronize()
