@@ -139,6 +139,12 @@ int nerf_train_phases(nerf_ctx* ctx, const float* images, const float* o, const 
  * forward re-evaluates the last sample of every ray with the fp32 CUDA-core MLP and uses its sigma, so the sign decision
  * is the fp32 one (one extra fp32 MLP evaluation per ray and net).  Inference passes only. */
 int nerf_set_exact_far_sigma(nerf_ctx* ctx, int on);
+/* Training option (default 0 = off).  wgrad_sms > 0: during the backward of a net the weight-gradient kernel runs on
+ * `wgrad_sms` SMs NEXT TO the dX-chain kernel (which keeps the others) and consumes every tile's dZ images as the chain
+ * publishes them, instead of after it on all SMs.  Same results (different summation order of the split-K reduction);
+ * measured slower on B200 at every split, kept as the built form of "dW accumulated where dZ is produced".
+ * Accepts 13 .. SMs/2; applies to nets with at least one tile pair per SM. */
+int nerf_set_backward_overlap(nerf_ctx* ctx, int wgrad_sms);
 /* Seed of the in-kernel uniform draws (keras.utils.set_random_seed, train_lego.py:22). */
 int nerf_set_seed(nerf_ctx* ctx, uint64_t seed);
 /* LEARNING_RATE lives in device memory (the step may be replayed from a CUDA graph): change it between steps. */

@@ -26,9 +26,15 @@ int nerf_sample_pdf_bwd(const float* t, const float* weights, const float* u, co
 /* Test hook: out (batch, nf) = the uniforms the in-kernel generator gives sample_pdf for (seed, counter); a training step
  * uses counter = number of optimiser updates applied so far, an inference pass 2^62 + its call index since nerf_set_seed. */
 int nerf_debug_pdf_draws(uint64_t seed, uint64_t counter, int64_t batch, int nf, float* out, void* stream);
-/* Timing experiments only: bit0 skip the CUDA-core side jobs, bit1 skip the MMAs, bit2 skip the final
- * reduction of the weight-gradient kernel (results are then wrong by construction). */
+/* Experiments on the backward.  Timing only (results wrong by construction): bit0 / bit3 skip the CUDA-core side
+ * jobs, bit1 skip the MMAs, bit2 skip the final reduction of the weight-gradient kernel.  Scheduling (results
+ * unchanged): bit6 no overlap (weight gradient after the dX chain, each on all SMs), bit7 weight gradient after the
+ * chain but on the overlap budget of SMs, bits 8.. = that budget (0: the context's default). */
 int nerf_debug_flags(int flags);
+/* Diagnostics: per weight-gradient CTA eight int64 {job, tiles, end of CTA (globaltimer ns), ns its loader waited for
+ * the dX chain's progress counters, ns it waited for free ring slots, end of its loader (ns), start of the CTA (ns), 0}; device buffer of
+ * 2 nets x 148 x 8 int64, NULL disables. */
+int nerf_debug_wgrad_stats(long long* dev_buf);
 /* Diagnostics: timeline trace of CTA 0 of the fused forward kernel (device buffer of 768 int64 clock stamps,
  * NULL disables). */
 int nerf_debug_trace(long long* dev_buf);

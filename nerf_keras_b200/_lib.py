@@ -54,6 +54,7 @@ SIGNATURES = {
     "nerf_adam_step": (_I, [_P, _F, _P]),
     "nerf_set_seed": (_I, [_P, C.c_uint64]),
     "nerf_set_exact_far_sigma": (_I, [_P, _I]),
+    "nerf_set_backward_overlap": (_I, [_P, _I]),
     "nerf_set_learning_rate": (_I, [_P, _F, _P]),
     "nerf_get_optimizer_state": (_I, [_P, _P, _P, C.POINTER(_L), _P]),
     "nerf_set_optimizer_state": (_I, [_P, _P, _P, _L, _P]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "nerf_debug_flags": (_I, [_I]),
     "nerf_debug_pair_mode": (_I, [_I]),
     "nerf_debug_trace": (_I, [_P]),
+    "nerf_debug_wgrad_stats": (_I, [_P]),
     "nerf_selftest_gemm_2cta": (_I, [_P, _P, _P, _I, _I, _P]),
     "nerf_selftest_gemm_ts": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nerf_selftest_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

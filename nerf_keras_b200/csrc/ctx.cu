@@ -149,7 +149,12 @@ extern "C" int nerf_destroy(nerf_ctx* ctx) {
     cudaFree(ctx->tr_dpred_c); cudaFree(ctx->tr_dpred_f); cudaFree(ctx->tr_drgb_c); cudaFree(ctx->tr_drgb_f);
     cudaFree(ctx->tr_ddirbias); cudaFree(ctx->tr_ddelta_f); cudaFree(ctx->tr_dtp_f); cudaFree(ctx->tr_dw_extra);
     cudaFree(ctx->w_ig); cudaFree(ctx->far_t); cudaFree(ctx->far_pred);
-    for (int n = 0; n < 2; ++n) { cudaFree(ctx->act_save[n]); cudaFree(ctx->dz_save[n]); cudaFree(ctx->mask_save[n]); }
+    for (int n = 0; n < 2; ++n) {
+        cudaFree(ctx->act_save[n]); cudaFree(ctx->dz_save[n]); cudaFree(ctx->mask_save[n]); cudaFree(ctx->chain_progress[n]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     tc_free(ctx);
     delete ctx;
     return NERF_OK;
@@ -234,6 +239,14 @@ static int patch_far_sigma(nerf_ctx* ctx, int net, const float* o, const float* 
 extern "C" int nerf_set_exact_far_sigma(nerf_ctx* ctx, int on) {
     NERF_CHECK_ARG(ctx != nullptr, "null ctx");
     ctx->exact_far_sigma = on != 0;
+    return NERF_OK;
+}
+
+extern "C" int nerf_set_backward_overlap(nerf_ctx* ctx, int wgrad_sms) {
+    NERF_CHECK_ARG(ctx != nullptr, "null ctx");
+    NERF_CHECK_ARG(wgrad_sms == 0 || (wgrad_sms >= 13 && wgrad_sms <= num_sms() / 2), "wgrad_sms: 0 or 13 .. SMs / 2");
+    if (wgrad_sms && !ctx->side_stream) return fail(NERF_ERR_STATE, "nerf_set_backward_overlap: ctx was not created with training=1");
+    ctx->wgrad_ctas = wgrad_sms;
     return NERF_OK;
 }
 

@@ -72,6 +72,14 @@ struct nerf_ctx {
     // un-stopped gradient through the fine sample positions (stop_grad_samples = 0)
     __nv_bfloat16* w_ig = nullptr;                 // W0^T / W5b^T operand image of the input-gradient kernel
     float *tr_ddelta_f = nullptr, *tr_dtp_f = nullptr, *tr_dw_extra = nullptr;
+    // backward overlap: the weight-gradient kernel runs on `wgrad_ctas` SMs NEXT TO the dX chain (side stream, forked and
+    // joined by events so that it is captured into the step graph), consuming each tile's dZ images as the chain
+    // publishes them (chain_progress, one counter per tile).  0 = one kernel after the other.
+    int wgrad_ctas = 0;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint32_t* chain_progress[2] = {nullptr, nullptr};
+    int64_t progress_tiles[2] = {0, 0};
 };
 
 namespace nerf {

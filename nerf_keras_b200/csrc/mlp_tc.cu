@@ -142,7 +142,13 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ 
 // from registers with 256-bit global stores (two swizzled 16-byte chunks = one 32-byte sector).  Measured on B200,
 // forward of both nets per 4096-ray step: bulk stores 1.85 ms, 256-bit register stores 2.06 ms, 128-bit register
 // stores 2.44 ms -- the LSU path loses to the TMA engine even though it spares the shared-memory reads.
+#ifdef NERF_EXP_COALESCED_SAVE
+constexpr bool kDirectSave = true;
+constexpr bool kCoalescedSave = true;     // TIMING EXPERIMENT: [16-byte column group][row][16 B] image, 512 contiguous bytes per warp store
+#else
 constexpr bool kDirectSave = false;
+constexpr bool kCoalescedSave = false;
+#endif
 constexpr bool kSplitImageStore = true;
 constexpr bool kHybridSave = false;       // K-blocks 0,1 by 256-bit register stores during the first epilogue half, K-blocks 2,3 by
                                           // one bulk store: measured 1.90 ms per step vs 1.65 with two bulk stores -- off   // bulk-store K-blocks 0,1 as soon as they are written (two 32 KB stores per phase)
@@ -201,7 +207,13 @@ __device__ __forceinline__ void trunk_group(const uint32_t (&v)[32], const float
 #pragma unroll
         for (int q = 0; q < 16; ++q) held[CG * 16 + q] = pk[q];
     }
-    if (SAVE && (kDirectSave || (kHybridSave && !STORE))) {
+    if (SAVE && kCoalescedSave) {
+        const uint32_t row = threadIdx.x & 127;
+        const uint64_t b = gimg + (rs.off[0] & ~127u) - ((row >> 3) * 1024 + (row & 7) * 128) + (CG / 2) * (TILE_M * 128) + row * 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            st_global_v4(b + ((CG & 1) * 4 + c) * 2048, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    } else if (SAVE && (kDirectSave || (kHybridSave && !STORE))) {
         const bool odd = (rs.off[0] >> 7) & 1;                 // row parity (bit 7 of the row's shared-memory address)
 #pragma unroll
         for (int j = 0; j < 2; ++j)

@@ -92,7 +92,19 @@ struct BwdParams {
     const float* side;
     const uint32_t* mask_save;
     uint8_t* dz_save;
+    uint32_t* progress;     // per tile: number of dZ images whose bulk stores are complete (null: nobody is listening)
 };
+
+// The weight-gradient kernel may run NEXT TO this kernel on other SMs and consume a tile's dZ images while they are
+// still in L2.  The thread that issues a sub-tile's bulk stores publishes how many images of the tile are complete:
+// 1 = [ddir + head], 2 = feature, 3 .. 10 = Z7 .. Z0.  cp.async.bulk.wait_group N (not .read) returns once all but the N
+// most recent groups have been written; the counter is then released at gpu scope.
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void publish_progress(uint32_t* p, uint32_t v) {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // one 32-column group of a chain epilogue: optional sigma-head term, ReLU mask, bf16; stored to the A tile or held
 template <bool SIGMA, bool MASK, int CG, bool STORE>
@@ -197,6 +209,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
         const uint32_t bar_lo = B.actr + 16 * s, bar_hi = bar_lo + 8;    // A tile hand-off, K-halves
         const uint32_t bar_h0 = B.accf + 16 * s, bar_h1 = bar_h0 + 8;    // accumulator hand-off, N-halves
         uint32_t accf_par = 0;
+        int64_t prev_tile = -1;                                          // elected thread: tile whose last stores are in flight
 
         for (int it = 0; it < my_pairs; ++it) {
             const int64_t pair = blockIdx.x + (int64_t)it * gridDim.x;
@@ -208,7 +221,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
             const float4 dp = valid ? P.dpreds[g_row] : make_float4(0.f, 0.f, 0.f, 0.f);
 
             // ---- prologue: rgb head backward + ddir ReLU mask -> dZ_ddir (128 wide) ----
-            if (elected) bulk_wait_read0();
+            if (elected) {
+                bulk_wait_read0();
+                if (P.progress && prev_tile >= 0) {      // all but the previous tile's very last store (Z0, second half)
+                    bulk_wait_group<1>();
+                    publish_progress(P.progress + prev_tile, 9);
+                }
+            }
             named_bar_sync(1 + s, TILE_M);
             {
                 const uint4 mk4 = *reinterpret_cast<const uint4*>(mask_tile + ((size_t)8 * 128 + row) * 8);
@@ -272,7 +291,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
                 mbar_wait(bar_h1, accf_par, 6);                      // every MMA of the phase is complete
                 accf_par ^= 1;
                 tc_fence_after();
-                if (elected) bulk_wait_read0();                      // previous image store has finished reading the tile
+                if (elected) {
+                    bulk_wait_read0();                               // previous image store has finished reading the tile
+                    if (P.progress && ph >= 1) {
+                        // groups so far: [ddir + head], then two per phase; all but the last two (= phase ph-1) are written
+                        bulk_wait_group<2>();
+                        if (ph == 1 && prev_tile >= 0) publish_progress(P.progress + prev_tile, 10);
+                        publish_progress(P.progress + tile, (uint32_t)ph);
+                    }
+                }
                 named_bar_sync(1 + s, TILE_M);
                 store_held(rs, held);
                 tc_fence_before();
@@ -291,8 +318,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
                 if (elected) { bulk_s2g(dz_tile + dst + 32768, act_base + 32768, 32768); bulk_commit(); }
                 if (ph < B_PHASES - 1) mbar_arrive(bar_hi);
             }
+            prev_tile = tile;
         }
-        if (elected) bulk_wait_all0();
+        if (elected) {
+            bulk_wait_all0();
+            if (P.progress && prev_tile >= 0) publish_progress(P.progress + prev_tile, 10);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -304,38 +335,74 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
 // ------------------------------------------------------------------------------------------------
 constexpr int WG_THREADS = 320;            // warps 0-3: side jobs + final reduction, 4: loader, 5: MMA issuer, 6-9: side jobs
 constexpr int WG_SIDE_WARPS = 8;
-constexpr int WG_STAGES = 3;
-constexpr int WG_SLOT = 65536;             // A half-blocks (4 x 8 KB) + B half-blocks (4 x 8 KB)
-constexpr int WG_SM_BAR = WG_STAGES * WG_SLOT;
-constexpr int WG_SMEM = WG_SM_BAR + 128 + 1024;
+// Two rings of WHOLE 128-sample tiles.  X ring: 3 stages x 32 KB (two 64-feature K-blocks = one M=128 block of the
+// operand, contiguous in the saved image); dZ ring: 128 KB, stages of n_b x 16 KB (the whole dZ image, contiguous).
+// Every stage is filled by ONE bulk copy of 16 .. 64 KB: the copy engine of an SM retires one cp.async.bulk per ~130 ns
+// whatever its size (tools/micro/bulk_bw.cu: 63 GB/s per SM with 8 KB copies, 125 / 159 / 198 GB/s with 16 / 32 / 64 KB),
+// so a CTA fed by 8 KB copies cannot outrun ~50 GB/s -- invisible while 148 CTAs share HBM, decisive when the kernel runs
+// on a fraction of the SMs next to the dX chain (tc_backward).
+constexpr int WG_A_STAGES = 3;
+constexpr int WG_A_SLOT = 32768;
+constexpr int WG_B_MAX_STAGES = 4;
+constexpr int WG_B_RING = 131072;
+constexpr int WG_SM_A = 0;
+constexpr int WG_SM_B = WG_A_STAGES * WG_A_SLOT;
+constexpr int WG_SM_BAR = WG_SM_B + WG_B_RING;
+constexpr int WG_SMEM = WG_SM_BAR + 256 + 1024;
 constexpr int WG_NJOBS = 13;
 
 struct WgJob {
     int64_t a_off;       // byte offset of the X image inside a saved-activation tile
     int64_t b_off;       // byte offset of the dZ image inside a dZ tile
     int n_a;             // 64-feature blocks of X: 1, 2 or 4
-    int n_b;             // 64-feature blocks of dZ: 2 or 4
+    int n_b;             // 64-feature blocks of dZ: 1, 2 or 4
     int64_t w_dst;       // float offset (in the grads blob of this net) of dW row 0
     int ld;              // fan_out
     int rows;            // valid rows of dW produced by this job
     int col_lo, col_hi;  // valid columns [col_lo, col_hi) of the accumulator that are written to dW
     int64_t bias_dst;    // float offset of the bias gradient (column sums of dZ), or -1
     int64_t sig_dst;     // float offset of dW_sigma (256,1): column sums of the X image weighted by d sigma per sample, or -1
+    int need;            // progress count of the dX chain (images stored so far for a tile) at which this job's dZ image exists
 };
 struct WgParams {
-    int debug;              // bit0: skip side jobs, bit1: skip MMAs, bit2: skip final reduction (timing experiments)
+    int debug;              // bit0 / bit3: skip side jobs, bit1: skip MMAs, bit2: skip final reduction (timing experiments)
     WgJob jobs[WG_NJOBS];
-    int cta_first[WG_NJOBS + 1];   // 1-D grid: job j owns CTAs [cta_first[j], cta_first[j+1]) and splits its samples among them
+    int cta_first[WG_NJOBS + 1];   // 1-D grid: job j owns CTAs [cta_first[j], cta_first[j+1]); its tiles are dealt round-robin
     const uint8_t* act_save;
     const uint8_t* dz_save;
     const float4* dpreds;
     int64_t M;
-    int64_t n_half_tiles;   // 2 * tiles
+    int64_t n_tiles;
+    const uint32_t* progress;   // per tile: images the concurrently running dX chain has completed (null: chain already done)
+    long long* stats;           // diagnostics (nerf_debug_wgrad_stats): per CTA {job, tiles, end ns, ns waiting for the chain, ns waiting for slots}
     float* grads;           // this net's gradient blob
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Bounded wait for the chain's progress counter of one tile (same policy as mbar_wait: trap instead of hanging)
+__device__ __forceinline__ void wait_progress(const uint32_t* p, uint32_t need, int code) {
+    if (ld_acquire_gpu(p) >= need) return;
+    long long t0 = 0;
+    uint32_t n = 0;
+    while (ld_acquire_gpu(p) < need) {
+        __nanosleep(200);
+        if ((++n & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > TC5_TIMEOUT_CYCLES) {
+                printf("wgrad: chain progress wait timeout code=%d block=%d need=%u have=%u\n", code, blockIdx.x, need,
+                       ld_acquire_gpu(p));
+                __trap();
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgParams P) {
@@ -348,132 +415,200 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     while (job_id + 1 < WG_NJOBS && (int)blockIdx.x >= P.cta_first[job_id + 1]) ++job_id;
     const WgJob& J = P.jobs[job_id];
     const int job_ctas = P.cta_first[job_id + 1] - P.cta_first[job_id], job_cta = (int)blockIdx.x - P.cta_first[job_id];
-    const uint32_t bar_full = base + WG_SM_BAR, bar_empty = bar_full + 8 * WG_STAGES, bar_done = bar_empty + 8 * WG_STAGES;
-    const int STG = (P.debug & 16) ? 2 : WG_STAGES;     // experiment: ring depth 2 (16 instead of 24 bulk copies in flight)
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_SM_BAR + 8 * (2 * WG_STAGES + 1));
+    const uint32_t bar_afull = base + WG_SM_BAR, bar_aempty = bar_afull + 8 * WG_A_STAGES,
+                   bar_bfull = bar_aempty + 8 * WG_A_STAGES, bar_bempty = bar_bfull + 8 * WG_B_MAX_STAGES,
+                   bar_done = bar_bempty + 8 * WG_B_MAX_STAGES;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_SM_BAR + 200);
+    const int n_mh = (J.n_a == 4) ? 2 : 1;                     // M = 128 blocks of the operand (X stages per tile)
+    const uint32_t b_bytes = (uint32_t)J.n_b * 16384u;
+    int b_stages = WG_B_RING / (int)b_bytes;
+    if (b_stages > WG_B_MAX_STAGES) b_stages = WG_B_MAX_STAGES;
+    const bool side_off = (P.debug & (1 | 8)) != 0;
+    const bool do_sig = J.sig_dst >= 0 && !side_off && !(P.debug & 32), do_bias = J.bias_dst >= 0 && !side_off;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < WG_STAGES; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1 + 32 * WG_SIDE_WARPS);   // tcgen05.commit + the side-job threads
+        for (int i = 0; i < WG_A_STAGES; ++i) {
+            mbar_init(bar_afull + 8 * i, 1);
+            mbar_init(bar_aempty + 8 * i, 1 + (do_sig ? 32 * WG_SIDE_WARPS : 0));   // tcgen05.commit (+ the side-job threads)
+        }
+        for (int i = 0; i < WG_B_MAX_STAGES; ++i) {
+            mbar_init(bar_bfull + 8 * i, 1);
+            mbar_init(bar_bempty + 8 * i, 1 + (do_bias ? 32 * WG_SIDE_WARPS : 0));
         }
         mbar_init(bar_done, 1);
         fence_barrier_init();
     }
-    if (warp == 5) tmem_alloc(base + WG_SM_BAR + 8 * (2 * WG_STAGES + 1), 512);
+    if (P.stats && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.stats[(size_t)blockIdx.x * 8 + 6] = t;
+    }
+    if (warp == 5) tmem_alloc(base + WG_SM_BAR + 200, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // this CTA's slab of half-tiles (64 samples each)
-    const int64_t per = (P.n_half_tiles + job_ctas - 1) / job_ctas;
-    const int64_t ht0 = (int64_t)job_cta * per;
-    const int64_t ht1 = (ht0 + per < P.n_half_tiles) ? ht0 + per : P.n_half_tiles;
-    const int n_ht = (ht1 > ht0) ? (int)(ht1 - ht0) : 0;
-    const int n_a_load = (J.n_a == 1) ? 2 : J.n_a;   // a single 64-feature block is loaded twice (M = 128 MMA)
-    const int n_mh = (J.n_a == 4) ? 2 : 1;
+    // this CTA's tiles: job_cta, job_cta + job_ctas, ... (the order in which the dX chain produces them)
+    const int n_my = (P.n_tiles > job_cta) ? (int)((P.n_tiles - job_cta + job_ctas - 1) / job_ctas) : 0;
 
     if (warp == 4) {
         // ===================== loader =====================
         if (lane == 0) {
-            int slot = 0;
-            uint32_t par = 1;
-            for (int i = 0; i < n_ht; ++i) {
-                const int64_t ht = ht0 + i;
-                const int64_t tile = ht >> 1;
-                const int half = (int)(ht & 1);
-                mbar_wait(bar_empty + 8 * slot, par, 11);
-                const uint32_t dst = base + slot * WG_SLOT;
-                mbar_arrive_expect_tx(bar_full + 8 * slot, (uint32_t)(n_a_load + J.n_b) * 8192u);
-                const uint8_t* a_src = P.act_save + tile * SAVE_TILE_BYTES + J.a_off + half * 8192;
-                const uint8_t* b_src = P.dz_save + tile * DZ_TILE_BYTES + J.b_off + half * 8192;
-                if (P.debug & 32) {
-                    // TIMING EXPERIMENT ONLY (wrong operands): the same bytes as two large copies per stage
-                    bulk_g2s(dst, a_src - half * 8192 + half * (n_a_load * 8192), n_a_load * 8192, bar_full + 8 * slot);
-                    bulk_g2s(dst + 32768, b_src - half * 8192 + half * (J.n_b * 8192), J.n_b * 8192, bar_full + 8 * slot);
-                } else {
-                for (int b = 0; b < n_a_load; ++b)
-                    bulk_g2s(dst + b * 8192, a_src + (J.n_a == 1 ? 0 : b) * 16384, 8192, bar_full + 8 * slot);
-                for (int b = 0; b < J.n_b; ++b)
-                    bulk_g2s(dst + 32768 + b * 8192, b_src + b * 16384, 8192, bar_full + 8 * slot);
+            int as = 0, bs = 0;
+            uint32_t apar = 1, bpar = 1;
+            long long t_flag = 0, t_slot = 0;
+            auto now_ns = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+            for (int i = 0; i < n_my; ++i) {
+                const int64_t tile = job_cta + (int64_t)i * job_ctas;
+                long long t0 = P.stats ? now_ns() : 0;
+                mbar_wait(bar_bempty + 8 * bs, bpar, 11);
+                if (P.stats) { const long long t1 = now_ns(); t_slot += t1 - t0; t0 = t1; }
+                if (P.progress) {
+                    // the chain kernel runs next to this one: its bulk stores of this image have completed (and were
+                    // released at gpu scope) once the tile's counter has reached `need`; order the acquire before the
+                    // async-proxy read below
+                    wait_progress(P.progress + tile, (uint32_t)J.need, 15);
+                    fence_proxy_async_all();
+                    if (P.stats) t_flag += now_ns() - t0;
                 }
-                if (++slot == STG) { slot = 0; par ^= 1; }
+                mbar_arrive_expect_tx(bar_bfull + 8 * bs, b_bytes);
+                bulk_g2s(base + WG_SM_B + bs * b_bytes, P.dz_save + tile * DZ_TILE_BYTES + J.b_off, b_bytes, bar_bfull + 8 * bs);
+                if (++bs == b_stages) { bs = 0; bpar ^= 1; }
+                const uint8_t* a_src = P.act_save + tile * SAVE_TILE_BYTES + J.a_off;
+                for (int mh = 0; mh < n_mh; ++mh) {
+                    t0 = P.stats ? now_ns() : 0;
+                    mbar_wait(bar_aempty + 8 * as, apar, 12);
+                    if (P.stats) t_slot += now_ns() - t0;
+                    const uint32_t dst = base + WG_SM_A + as * WG_A_SLOT;
+                    mbar_arrive_expect_tx(bar_afull + 8 * as, WG_A_SLOT);
+                    if (J.n_a == 1) {        // a single 64-feature block is loaded twice (M = 128 MMA)
+                        bulk_g2s(dst, a_src, 16384, bar_afull + 8 * as);
+                        bulk_g2s(dst + 16384, a_src, 16384, bar_afull + 8 * as);
+                    } else {
+                        bulk_g2s(dst, a_src + mh * 32768, 32768, bar_afull + 8 * as);
+                    }
+                    if (++as == WG_A_STAGES) { as = 0; apar ^= 1; }
+                }
+            }
+            if (P.stats) {
+                long long* o = P.stats + (size_t)blockIdx.x * 8;
+                o[0] = job_id; o[1] = n_my; o[3] = t_flag; o[4] = t_slot; o[5] = now_ns();
             }
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64 * J.n_b, 1, 1);
-            int slot = 0;
-            uint32_t par = 0;
-            for (int i = 0; i < n_ht; ++i) {
-                mbar_wait(bar_full + 8 * slot, par, 12);
-                tc_fence_after();
-                const uint32_t a0 = base + slot * WG_SLOT, b0 = a0 + 32768;
-                for (int mh = 0; mh < ((P.debug & 2) ? 0 : n_mh); ++mh) {
+            int as = 0, bs = 0;
+            uint32_t apar = 0, bpar = 0;
+            for (int i = 0; i < n_my; ++i) {
+                mbar_wait(bar_bfull + 8 * bs, bpar, 13);
+                const uint32_t b0 = base + WG_SM_B + bs * b_bytes;
+                for (int mh = 0; mh < n_mh; ++mh) {
+                    mbar_wait(bar_afull + 8 * as, apar, 14);
+                    tc_fence_after();
+                    const uint32_t a0 = base + WG_SM_A + as * WG_A_SLOT;
+                    if (!(P.debug & 2)) {
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        const uint64_t ad = make_sdesc_sw128(a0 + mh * 16384 + k4 * 2048, 8192, 1024);
-                        const uint64_t bd = make_sdesc_sw128(b0 + k4 * 2048, 8192, 1024);
-                        mma_bf16_ss(tmem_base + mh * 256, ad, bd, idesc, (i > 0 || k4 > 0) ? 1u : 0u);
+                        for (int k = 0; k < 8; ++k) {      // 128 samples = 8 x K16; 16 sample rows = 2048 bytes
+                            const uint64_t ad = make_sdesc_sw128(a0 + k * 2048, 16384, 1024);
+                            const uint64_t bd = make_sdesc_sw128(b0 + k * 2048, 16384, 1024);
+                            mma_bf16_ss(tmem_base + mh * 256, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
+                    mma_commit(bar_aempty + 8 * as);
+                    if (++as == WG_A_STAGES) { as = 0; apar ^= 1; }
                 }
-                mma_commit(bar_empty + 8 * slot);
-                if (++slot == STG) { slot = 0; par ^= 1; }
+                mma_commit(bar_bempty + 8 * bs);
+                if (++bs == b_stages) { bs = 0; bpar ^= 1; }
             }
             mma_commit(bar_done);
         }
     } else {
         // ===================== side jobs + final reduction =====================
-        // Eight side warps (one single warp per scheduler is latency-bound: a dependent-issue chain of ~1.1 K instructions
-        // per half-tile made the job's CTAs the stragglers); side warp sw takes rows [8 sw, 8 sw + 8) of each 64-sample
-        // half-tile, lane <-> (64-column block, 16-byte chunk) = 8 columns.
+        // Eight side warps; side warp sw takes rows [16 sw, 16 sw + 16) of each 128-sample tile.
+        //   bias gradient (column sums of the dZ image): lane <-> (64-column block cb = lane / 8, 16-byte chunk ch) = 8 columns
+        //   sigma head (X = h8, two stages of 128 features): lane <-> (block cb = (lane / 8) & 1, row half (lane / 16), chunk ch)
         const int sw = (warp < 4) ? warp : warp - 2;
-        const int cb = lane >> 3, ch = lane & 7;
+        const int sub = lane >> 3, ch = lane & 7;
         float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias: partial column sums (8 columns per lane)
-        float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // sigma head: column sums of X weighted by d sigma
-        auto accum = [&](uint32_t img, float wgt, float (&acc)[8], int rr) {
-            const uint32_t addr = img + cb * 8192 + sw * 1024 + rr * 128 + ((ch ^ rr) << 4);
-            uint32_t w0, w1, w2, w3;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(addr));
-            acc[0] = fmaf(wgt, __uint_as_float(w0 << 16), acc[0]); acc[1] = fmaf(wgt, __uint_as_float(w0 & 0xFFFF0000u), acc[1]);
-            acc[2] = fmaf(wgt, __uint_as_float(w1 << 16), acc[2]); acc[3] = fmaf(wgt, __uint_as_float(w1 & 0xFFFF0000u), acc[3]);
-            acc[4] = fmaf(wgt, __uint_as_float(w2 << 16), acc[4]); acc[5] = fmaf(wgt, __uint_as_float(w2 & 0xFFFF0000u), acc[5]);
-            acc[6] = fmaf(wgt, __uint_as_float(w3 << 16), acc[6]); acc[7] = fmaf(wgt, __uint_as_float(w3 & 0xFFFF0000u), acc[7]);
+        float sg[2][8] = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
+        // eight rows at a time: all loads first, then the FMAs (two warps per scheduler: the side jobs live on instruction-
+        // level parallelism; one load -> eight dependent FMAs per row ran at ~80 cycles per row)
+        auto load8 = [&](uint32_t blk, int row0, uint4 (&v)[8]) {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const int row = row0 + rr;
+                const uint32_t addr = blk + row * 128 + ((ch ^ (row & 7)) << 4);
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[rr].x), "=r"(v[rr].y), "=r"(v[rr].z), "=r"(v[rr].w) : "r"(addr));
+            }
         };
-        int slot = 0;
-        uint32_t par = 0;
-        for (int i = 0; i < n_ht; ++i) {
-            // d sigma of this warp's 8 samples: one load per lane, issued before the wait so that its latency is hidden
-            float my_ds = 0.f;
-            if (J.sig_dst >= 0 && lane < 8) my_ds = __ldg(&P.dpreds[(ht0 + i) * 64 + sw * 8 + lane].w);
-            mbar_wait(bar_full + 8 * slot, par, 13);
-            const uint32_t a0 = base + slot * WG_SLOT, b0 = a0 + 32768;
-            if (J.sig_dst >= 0 && !(P.debug & (1 | 8))) {
-                // dW_sigma[f] += sum over the half-tile's samples of h8[sample][f] * d sigma[sample]  (models.py:42): the
-                // X image of this job IS h8, so the sigma head costs no extra HBM traffic (it used to be a job of its own)
+        auto fma8 = [&](const uint4& w, float wgt, float (&acc)[8]) {
+            acc[0] = fmaf(wgt, __uint_as_float(w.x << 16), acc[0]); acc[1] = fmaf(wgt, __uint_as_float(w.x & 0xFFFF0000u), acc[1]);
+            acc[2] = fmaf(wgt, __uint_as_float(w.y << 16), acc[2]); acc[3] = fmaf(wgt, __uint_as_float(w.y & 0xFFFF0000u), acc[3]);
+            acc[4] = fmaf(wgt, __uint_as_float(w.z << 16), acc[4]); acc[5] = fmaf(wgt, __uint_as_float(w.z & 0xFFFF0000u), acc[5]);
+            acc[6] = fmaf(wgt, __uint_as_float(w.w << 16), acc[6]); acc[7] = fmaf(wgt, __uint_as_float(w.w & 0xFFFF0000u), acc[7]);
+        };
+        if (do_sig || do_bias) {
+            int as = 0, bs = 0;
+            uint32_t apar = 0, bpar = 0;
+            // d sigma of this warp's 16 samples of a tile: one load per lane, fetched ONE TILE AHEAD
+            float next_ds = 0.f;
+            if (do_sig && lane < 16 && n_my > 0) next_ds = __ldg(&P.dpreds[(int64_t)job_cta * TILE_M + sw * 16 + lane].w);
+            for (int i = 0; i < n_my; ++i) {
+                const int64_t tile = job_cta + (int64_t)i * job_ctas;
+                const float my_ds = next_ds;
+                if (do_sig && lane < 16 && i + 1 < n_my) next_ds = __ldg(&P.dpreds[(tile + job_ctas) * TILE_M + sw * 16 + lane].w);
+                if (do_bias) {
+                    mbar_wait(bar_bfull + 8 * bs, bpar, 16);
+                    if (sub < J.n_b && !(P.debug & 16)) {
+                        const uint32_t blk = base + WG_SM_B + bs * b_bytes + sub * 16384;
+                        uint4 v[8];
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr) accum(a0, __shfl_sync(0xffffffffu, my_ds, rr), sg, rr);
-            }
-            if (J.bias_dst >= 0 && !(P.debug & (1 | 8)) && cb < J.n_b) {
-                // bias gradient: column sums of the dZ half-tile
+                        for (int h = 0; h < 2; ++h) {
+                            load8(blk, sw * 16 + 8 * h, v);
 #pragma unroll
-                for (int rr = 0; rr < 8; ++rr) accum(b0, 1.0f, cs, rr);
+                            for (int rr = 0; rr < 8; ++rr) fma8(v[rr], 1.0f, cs);
+                        }
+                    }
+                    mbar_arrive(bar_bempty + 8 * bs);
+                    if (++bs == b_stages) { bs = 0; bpar ^= 1; }
+                }
+                if (do_sig) {
+                    // dW_sigma[f] += sum over the tile's samples of h8[sample][f] * d sigma[sample]  (models.py:42): the X
+                    // image of this job IS h8, so the sigma head costs no extra HBM traffic
+                    float wrow[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) wrow[rr] = __shfl_sync(0xffffffffu, my_ds, (sub >> 1) * 8 + rr);
+                    for (int mh = 0; mh < n_mh; ++mh) {
+                        mbar_wait(bar_afull + 8 * as, apar, 17);
+                        const uint32_t blk = base + WG_SM_A + as * WG_A_SLOT + (sub & 1) * 16384;
+                        uint4 v[8];
+                        load8(blk, sw * 16 + (sub >> 1) * 8, v);
+                        float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) fma8(v[rr], wrow[rr], part);
+                        mbar_arrive(bar_aempty + 8 * as);
+                        if (++as == WG_A_STAGES) { as = 0; apar ^= 1; }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { if (mh == 0) sg[0][q] += part[q]; else sg[1][q] += part[q]; }
+                    }
+                }
             }
-            mbar_arrive(bar_empty + 8 * slot);
-            if (++slot == STG) { slot = 0; par ^= 1; }
         }
-        if (n_ht > 0) {
-            if (J.bias_dst >= 0 && (lane >> 3) < J.n_b) {
+        if (n_my > 0) {
+            if (do_bias && sub < J.n_b) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) atomicAdd(P.grads + J.bias_dst + (lane >> 3) * 64 + (lane & 7) * 8 + q, cs[q]);
+                for (int q = 0; q < 8; ++q) atomicAdd(P.grads + J.bias_dst + sub * 64 + ch * 8 + q, cs[q]);
             }
-            if (J.sig_dst >= 0) {
+            if (do_sig) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) atomicAdd(P.grads + J.sig_dst + (lane >> 3) * 64 + (lane & 7) * 8 + q, sg[q]);
+                for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) atomicAdd(P.grads + J.sig_dst + mh * 128 + (sub & 1) * 64 + ch * 8 + q, sg[mh][q]);
             }
-            if (n_mh > 0 && !(P.debug & 4) && warp < 4) {     // TMEM lane quarters belong to warps 0-3
+            if (!(P.debug & 4) && warp < 4) {     // TMEM lane quarters belong to warps 0-3
                 mbar_wait(bar_done, 0, 14);
                 tc_fence_after();
                 const int N = 64 * J.n_b;
@@ -504,6 +639,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     }
     tc_fence_before();
     __syncthreads();
+    if (P.stats && threadIdx.x == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.stats[(size_t)blockIdx.x * 8 + 2] = t;
+    }
     if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
@@ -825,6 +965,8 @@ __global__ void __launch_bounds__(128) sample_pdf_bwd_kernel(const float* __rest
 namespace nerf {
 int64_t tc_save_bytes_per_tile();
 int g_wg_debug = 0;
+long long* g_wg_stats = nullptr;
+constexpr int WG_OVERLAP_CTAS = 0;       // default: no overlap (measured slower); nerf_set_backward_overlap opts in
 
 int tc_train_alloc(nerf_ctx* ctx) {
     const nerf_config& c = ctx->cfg;
@@ -838,7 +980,13 @@ int tc_train_alloc(nerf_ctx* ctx) {
         NERF_CUDA(cudaMalloc((void**)&ctx->dz_save[net], (size_t)(tiles[net] * DZ_TILE_BYTES)));
         NERF_CUDA(cudaMalloc((void**)&ctx->mask_save[net], (size_t)(tiles[net] * MASK_TILE_BYTES)));
         NERF_CUDA(cudaMalloc((void**)&ctx->w_bwd[net], (size_t)B_CHUNKS * CHUNK_BYTES));
+        NERF_CUDA(cudaMalloc((void**)&ctx->chain_progress[net], (size_t)tiles[net] * 4));
+        ctx->progress_tiles[net] = tiles[net];
     }
+    NERF_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    NERF_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    NERF_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    ctx->wgrad_ctas = WG_OVERLAP_CTAS;
     NERF_CUDA(cudaMalloc((void**)&ctx->w_ig, IG_W_BYTES));
     NERF_CUDA(cudaFuncSetAttribute(nerf_input_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IG_SMEM));
     NERF_CUDA(cudaFuncSetAttribute(nerf_mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -903,7 +1051,25 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     P.side = ctx->side[net];
     P.mask_save = ctx->mask_save[net];
     P.dz_save = reinterpret_cast<uint8_t*>(ctx->dz_save[net]);
-    int grid = (int)(n_pairs < num_sms() ? n_pairs : num_sms());
+    // Overlap: with at least one full wave of tile pairs the chain gives up `wg_ctas` SMs to the weight-gradient kernel,
+    // which follows it tile by tile (see publish_progress / wait_progress).  Both kernels need a whole SM per CTA
+    // (shared memory), so chain CTAs + weight-gradient CTAs <= SMs keeps every CTA resident: the chain never waits for
+    // the consumer, the consumer only for counters the chain is certain to publish -- no deadlock.
+    int wg_ctas = (g_wg_debug >> 8) ? (g_wg_debug >> 8) : ctx->wgrad_ctas;
+    if (g_wg_debug & 64) wg_ctas = 0;
+    const bool budgeted = wg_ctas >= WG_NJOBS && wg_ctas <= num_sms() / 2 && n_pairs >= num_sms();
+    const bool overlap = budgeted && !(g_wg_debug & 128) && ctx->side_stream && n_pairs * 2 <= ctx->progress_tiles[net];
+    const int chain_sms = overlap ? num_sms() - wg_ctas : num_sms();
+    P.progress = overlap ? ctx->chain_progress[net] : nullptr;
+    int grid = (int)(n_pairs < chain_sms ? n_pairs : chain_sms);
+    cudaStream_t wst = st;
+    timing_begin(3, st);
+    if (overlap) {
+        NERF_CUDA(cudaMemsetAsync(ctx->chain_progress[net], 0, (size_t)n_pairs * 2 * 4, st));
+        NERF_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        NERF_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        wst = ctx->side_stream;
+    }
     timing_begin(1, st);
     nerf_mlp_bwd_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
     timing_end(1, st);
@@ -915,11 +1081,15 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     W.dz_save = reinterpret_cast<const uint8_t*>(ctx->dz_save[net]);
     W.dpreds = reinterpret_cast<const float4*>(d_preds);
     W.M = M;
-    W.n_half_tiles = n_pairs * 4;
+    W.n_tiles = n_pairs * 2;
+    W.progress = P.progress;
+    W.stats = g_wg_stats ? g_wg_stats + (size_t)net * 148 * 8 : nullptr;
     W.grads = grads;
     auto job = [&](int i, int64_t a_off, int n_a, int64_t b_off, int n_b, int64_t w_dst, int ld, int rows, int col_lo,
                    int col_hi, int64_t bias, int64_t sig = -1) {
-        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, col_lo, col_hi, bias, sig};
+        // images of a tile leave the chain kernel in the order [ddir + head], feature, Z7, Z6, .. Z0 (progress 1 .. 10)
+        const int need = (b_off >= DZ_DDIR) ? 1 : (b_off == DZ_FEAT) ? 2 : 10 - (int)((b_off - DZ_Z) / 65536);
+        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, col_lo, col_hi, bias, sig, need};
     };
     job(0, SAVE_ENC, 1, DZ_Z, 4, off.w[0], H, ENC_X, 0, H, off.b[0]);
     for (int l = 1; l <= 4; ++l)
@@ -946,23 +1116,44 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
         dir_image_kernel<<<dim3(stream_grid(B * 32, 128), 1), 128, 0, st>>>(d, B, A);
         NERF_LAUNCHED();
     }
-    int slabs = num_sms() / WG_NJOBS;
-    if (slabs < 1) slabs = 1;
-    if (slabs > W.n_half_tiles) slabs = (int)W.n_half_tiles;
-    // CTAs per job: equal shares, the spare SMs go to the feature job (its side warps also compute the sigma head)
-    int spare = num_sms() - slabs * WG_NJOBS;
-    if (slabs >= W.n_half_tiles) spare = 0;
     W.cta_first[0] = 0;
-    for (int j = 0; j < WG_NJOBS; ++j) W.cta_first[j + 1] = W.cta_first[j] + slabs + ((j == 9 && spare > 0) ? spare : 0);
-    timing_begin(2, st);
-    nerf_wgrad_tc_kernel<<<W.cta_first[WG_NJOBS], WG_THREADS, WG_SMEM, st>>>(W);
-    timing_end(2, st);
+    if (!budgeted) {
+        // the kernel owns the GPU: equal shares, the spare SMs go to the feature job (its side warps also compute the sigma head)
+        int slabs = num_sms() / WG_NJOBS;
+        if (slabs < 1) slabs = 1;
+        if (slabs > W.n_tiles) slabs = (int)W.n_tiles;
+        int spare = num_sms() - slabs * WG_NJOBS;
+        if (slabs >= W.n_tiles) spare = 0;
+        for (int j = 0; j < WG_NJOBS; ++j) W.cta_first[j + 1] = W.cta_first[j] + slabs + ((j == 9 && spare > 0) ? spare : 0);
+    } else {
+        // a budget of SMs next to the chain: shares in proportion to a job's time per tile = bytes streamed (units of
+        // 16 KB at the ~60 GB/s one CTA sustains) + ~0.5 us of fixed cost per tile (2 units; measured on the rgb-head job,
+        // tools/r2_wg_stats.py: with a share by bytes alone its two CTAs finished 1 ms after everybody else)
+        static const int units[WG_NJOBS] = {8, 10, 10, 10, 10, 10, 8, 10, 10, 10, 8, 5, 6};
+        int cnt[WG_NJOBS];
+        for (int j = 0; j < WG_NJOBS; ++j) cnt[j] = 1;
+        for (int sum = WG_NJOBS; sum < wg_ctas; ++sum) {       // next CTA to the job with the most bytes per CTA
+            int best = 0;
+            for (int j = 1; j < WG_NJOBS; ++j) if (units[j] * cnt[best] > units[best] * cnt[j]) best = j;
+            ++cnt[best];
+        }
+        for (int j = 0; j < WG_NJOBS; ++j) W.cta_first[j + 1] = W.cta_first[j] + cnt[j];
+    }
+    timing_begin(2, wst);
+    nerf_wgrad_tc_kernel<<<W.cta_first[WG_NJOBS], WG_THREADS, WG_SMEM, wst>>>(W);
+    timing_end(2, wst);
     NERF_LAUNCHED();
+    if (overlap) {
+        NERF_CUDA(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        NERF_CUDA(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    }
+    timing_end(3, st);
     return NERF_OK;
 }
 }  // namespace nerf
 
 extern "C" int nerf_debug_flags(int flags) { nerf::g_wg_debug = flags; return NERF_OK; }
+extern "C" int nerf_debug_wgrad_stats(long long* dev_buf) { nerf::g_wg_stats = dev_buf; return NERF_OK; }
 
 namespace nerf {
 // dtp[m] = < d_ray, dL/dpts[m] > of one net from its saved dZ0 / dZ5 images (tc_backward must have run)

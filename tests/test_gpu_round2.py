@@ -312,3 +312,41 @@ def test_graph_cache_follows_buffers_and_batch_sizes(nk):
     assert len(tr._graphs) == 0
     tr.train_step((full[0], full[1:4]))
     assert tr._ctx.optimizer_state()[2] == 20
+
+
+@pytest.mark.gpu
+def test_backward_overlap_matches_sequential():
+    """nerf_set_backward_overlap: the weight-gradient kernel consuming dZ images NEXT TO the dX chain (progress counters,
+    side stream) gives the gradients of the default schedule (only the split-K summation order differs)."""
+    import ctypes as C
+    import nerf_keras_b200 as nk
+    from nerf_keras_b200 import _lib
+    from nerf_keras_b200.models import _ptr, _stream
+    L = _lib.lib()
+    B, Nc, Nf = 2048, 64, 128      # 512 / 1536 tile pairs: both nets are above the one-pair-per-SM threshold
+    nk.set_random_seed(7)
+    c = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    f = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    tr = nk.NeRFTrainer(c, f, B, Nc, Nf, 10, 4)
+    tr.compile(nk.Adam(learning_rate=5e-4), nk.MeanSquaredError())
+    o, d = nk.get_rays(64, 32, 60.0, nk.pose_spherical(20.0, -30.0, 4.0))
+    o, d = o.reshape(-1, 3).contiguous(), d.reshape(-1, 3).contiguous()
+    t = nk.generate_t_vals(2.0, 6.0, B, Nc, True, u=np.random.default_rng(5).random(Nc, dtype=np.float32))
+    u = torch.rand(B, Nf, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    img = torch.rand(B, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(4))
+    metrics = torch.empty(3, device="cuda")
+    grads = {}
+    for sms in (0, 52, 0, 74):
+        _lib.check(L.nerf_set_backward_overlap(tr._ctx.handle, sms), "overlap")
+        _lib.check(L.nerf_train_forward_backward(tr._ctx.handle, _ptr(img), _ptr(o), _ptr(d), _ptr(t), _ptr(u), B,
+                                                 _ptr(metrics), _stream()), "fb")
+        torch.cuda.synchronize()
+        grads.setdefault(sms, []).append(tr._ctx.grad_tensor().cpu().numpy().copy())
+    ref = grads[0][0]
+    assert np.isfinite(ref).all() and np.abs(ref).max() > 0
+    rerun = np.abs(grads[0][1] - ref).max()                    # atomics: run-to-run noise of the default schedule
+    for sms in (52, 74):
+        err = np.abs(grads[sms][0] - ref).max()
+        assert err <= max(4 * rerun, 1e-5 * np.abs(ref).max()), (sms, err, rerun)
+    assert L.nerf_set_backward_overlap(tr._ctx.handle, 5) != 0     # below the 13 jobs: refused
+    _lib.check(L.nerf_set_backward_overlap(tr._ctx.handle, 0), "overlap off")

@@ -7,8 +7,10 @@
 using namespace tc5;
 
 // each CTA streams its own contiguous region (region_bytes) or a strided pattern (stride between copies)
+// tiled != 0: the weight-gradient kernel's pattern instead -- CTA b reads image (b / 4) of tiles (b % 4), (b % 4) + 4, ..
+// of `tiled`-byte tile records (one copy per tile; the records of consecutive copies are 4 x tiled bytes apart)
 __global__ void __launch_bounds__(64, 1) bw_kernel(const uint8_t* src, size_t region_bytes, int copy_bytes, int depth,
-                                                   size_t stride, int iters) {
+                                                   size_t stride, int iters, size_t tiled = 0, size_t total = 0) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -22,6 +24,12 @@ __global__ void __launch_bounds__(64, 1) bw_kernel(const uint8_t* src, size_t re
     if (threadIdx.x == 0) {
         const uint8_t* p = src + (size_t)blockIdx.x * region_bytes;
         size_t off = 0;
+        if (tiled) {
+            p = src;
+            off = (size_t)(blockIdx.x % 4) * tiled + (size_t)(blockIdx.x / 4) * 65536;
+            stride = 4 * tiled;
+            region_bytes = total - tiled;
+        }
         int slot = 0; uint32_t par = 0;
         // prime
         for (int i = 0; i < depth && i < iters; ++i) {
@@ -41,8 +49,9 @@ __global__ void __launch_bounds__(64, 1) bw_kernel(const uint8_t* src, size_t re
     }
 }
 
-int main() {
+int main(int argc, char** argv) {
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (argc > 1) sms = atoi(argv[1]);      // CTA count (default: one per SM): per-SM streaming limit at a reduced grid
     const size_t region = 64ull << 20;                 // 64 MiB per CTA -> 9.25 GiB total, far beyond L2
     uint8_t* src; cudaMalloc(&src, region * sms); cudaMemset(src, 1, region * sms);
     cudaFuncSetAttribute(bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -60,8 +69,19 @@ int main() {
         cudaEventRecord(b); cudaEventSynchronize(b);
         float ms; cudaEventElapsedTime(&ms, a, b);
         cudaError_t e = cudaGetLastError();
-        printf("pattern=%s copy=%6d B depth=%3d (%3d KB in flight/SM): %8.1f GB/s %s\n", pattern ? "strided" : "seq", s, depth, kb,
+        printf("ctas=%d pattern=%s copy=%6d B depth=%3d (%3d KB in flight/SM): %8.1f GB/s %s\n", sms, pattern ? "strided" : "seq", s, depth, kb,
                (double)iters * s * sms / ms / 1e6, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    }
+    // weight-gradient-like pattern: 64 KB images out of 640 KB tile records vs the same copies from image-major storage
+    for (size_t rec : {(size_t)655360, (size_t)65536}) for (int depth : {1, 2, 3}) {
+        const int s = 65536;
+        int iters = (int)((48ull << 20) / s);
+        cudaEventRecord(a);
+        bw_kernel<<<sms, 64, 1024 + 1024 + depth * s, 0>>>(src, region, s, depth, 0, iters, rec, region * sms);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        printf("ctas=%d pattern=tiles of %zu B copy=%6d B depth=%3d: %8.1f GB/s %s\n", sms, rec, s, depth,
+               (double)iters * s * sms / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }

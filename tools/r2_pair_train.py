@@ -1,5 +1,6 @@
-"""Experiment: training step with the forward kernel in CTA-pair mode (nerf_debug_pair_mode 49: shared chunks, alternating
-issuers, CTA-scope fence) vs the default single-CTA kernel: per-kernel CUDA-event times (eager steps)."""
+"""Experiment: training step with an opt-in variant of the forward kernel (nerf_debug_pair_mode: 49 / 17 CTA pair with
+shared chunks, 64 / 320 weight-stationary MMAs) vs the default single-CTA kernel: per-kernel CUDA-event times (eager
+steps).  usage: r2_pair_train.py [mode ...]"""
 import ctypes as C, json, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,6 +27,6 @@ def run(mode, steps=10):
         out[nm] = a.value / steps
     return out
 for rep in range(2):
-    for mode in (0, 49, 17):
+    for mode in ([int(x) for x in sys.argv[1:]] or (0, 49, 17)):
         print(mode, json.dumps(run(mode)))
 L.nerf_debug_pair_mode(0)
