@@ -1,8 +1,9 @@
 // BATCH_NORM=true training (models.py:30-33, 49-52 with training=True): BatchNormalization after every trunk Dense and
 // after the direction Dense uses the statistics of the CURRENT batch over all (ray, sample) rows, which couples every
 // sample of a batch between consecutive layers.  That does not fit the fused per-tile tcgen05 kernels, so this path is
-// layer by layer in fp32: plain library GEMMs (cuBLAS sgemm, no TF32) between hand-written statistics / normalise /
-// backward kernels, with the sampling, compositing, resampling and metric kernels of the main path around it.
+// layer by layer on fp32 activations: tcgen05 GEMMs on split bf16 operands (gemm_tc.cu: fp32-grade results, no library
+// GEMM) between hand-written statistics / normalise / backward kernels, with the sampling, compositing, resampling and
+// metric kernels of the main path around it.
 // It serves the reference's BN configs, which are small-batch (256-512 rays, 48-192 samples per ray); it is not the
 // benchmark path.  Inference with BN uses the fused kernels (the moving statistics fold into W, b on the host).
 //
@@ -13,13 +14,15 @@
 //                          dz = gamma rstd (dy - dbeta / M - zhat dgamma / M);  dW = x^T dz;  dx = dz W^T;  db = 0
 // Gradient semantics: stop-gradient on the fine sample positions (the original NeRF's); the reference's un-stopped term
 //  is not carried through this path.
-#include <cublas_v2.h>
-#include <dlfcn.h>
-
 #include <vector>
 
 #include "common.cuh"
 
+namespace nerf {
+// gemm_tc.cu: tcgen05 MMAs on split bf16 operands, fp32 accumulation in tensor memory; skinny head shapes on CUDA cores
+int tc_gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+                int64_t ldb, float beta, float* C, int64_t ldc);
+}  // namespace nerf
 extern "C" int nerf_metrics_grad(const float*, const float*, const float*, int64_t, float*, float*, float*, void*);
 extern "C" int nerf_volume_render_bwd(const float* preds, const float* t, const float* d_rgb, const float* d_w_extra, int64_t batch,
                                       int num_samples, float* d_preds, float* d_delta, void* stream);
@@ -55,47 +58,10 @@ Arch make_arch(const nerf_config& c) {
     return a;
 }
 
-// cuBLAS is bound at first use (dlopen), so that the library itself has no load-time dependency on it: only BN training
-// needs it, and a missing libcublas must not take the tcgen05 path down with it.
-struct Blas {
-    void* lib = nullptr;
-    cublasHandle_t h = nullptr;
-    cublasStatus_t (*create)(cublasHandle_t*) = nullptr;
-    cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
-    cublasStatus_t (*set_math)(cublasHandle_t, cublasMath_t) = nullptr;
-    cublasStatus_t (*sgemm)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const float*, const float*, int,
-                            const float*, int, const float*, float*, int) = nullptr;
-} g_blas;
-
-int blas_init() {
-    if (g_blas.h) return NERF_OK;
-    for (const char* name : {"libcublas.so.12", "libcublas.so"}) {
-        g_blas.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-        if (g_blas.lib) break;
-    }
-    if (!g_blas.lib) return fail(NERF_ERR_STATE, "BATCH_NORM training needs libcublas.so.12 (dlopen failed)");
-    g_blas.create = reinterpret_cast<decltype(g_blas.create)>(dlsym(g_blas.lib, "cublasCreate_v2"));
-    g_blas.set_stream = reinterpret_cast<decltype(g_blas.set_stream)>(dlsym(g_blas.lib, "cublasSetStream_v2"));
-    g_blas.set_math = reinterpret_cast<decltype(g_blas.set_math)>(dlsym(g_blas.lib, "cublasSetMathMode"));
-    g_blas.sgemm = reinterpret_cast<decltype(g_blas.sgemm)>(dlsym(g_blas.lib, "cublasSgemm_v2"));
-    if (!g_blas.create || !g_blas.set_stream || !g_blas.set_math || !g_blas.sgemm)
-        return fail(NERF_ERR_STATE, "BATCH_NORM training: cuBLAS symbols not found");
-    if (g_blas.create(&g_blas.h) != CUBLAS_STATUS_SUCCESS) return fail(NERF_ERR_CUDA, "cublasCreate failed");
-    g_blas.set_math(g_blas.h, CUBLAS_PEDANTIC_MATH);      // plain fp32 FMAs: no TF32, no reduced-precision accumulation
-    return NERF_OK;
-}
-
-// row-major C (M x N) = op(A) op(B) + beta C   (column-major cuBLAS sees C^T = op(B)^T op(A)^T)
+// row-major C (M x N) = op(A) op(B) + beta C on the tensor cores (gemm_tc.cu); no library GEMM is involved
 int gemm(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb,
          float beta, float* C, int ldc) {
-    int rc = blas_init();
-    if (rc) return rc;
-    g_blas.set_stream(g_blas.h, st);
-    const float alpha = 1.0f;
-    cublasStatus_t s = g_blas.sgemm(g_blas.h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, (int)M, K, &alpha,
-                                    B, ldb, A, lda, &beta, C, ldc);
-    if (s != CUBLAS_STATUS_SUCCESS) return fail(NERF_ERR_CUDA, "cublasSgemm failed");
-    return NERF_OK;
+    return nerf::tc_gemm_f32(st, ta, tb, M, N, K, A, lda, B, ldb, beta, C, ldc);
 }
 #define GEMM(...) do { int _rc = gemm(__VA_ARGS__); if (_rc) return _rc; } while (0)
 

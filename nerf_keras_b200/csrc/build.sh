@@ -7,7 +7,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr ${EXTRA_NVCC_FLAGS:-})
 OBJS=()
 PIDS=()
-for f in ops mlp_fp32 ctx mlp_tc mlp_tc_experimental mlp_tc_bwd bn_train; do
+for f in ops mlp_fp32 ctx mlp_tc mlp_tc_experimental mlp_tc_bwd bn_train gemm_tc; do
   src="$HERE/$f.cu"; obj="$HERE/$f.o"
   stale=0
   [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/../../include/nerf_b200.h" -nt "$obj" || "$HERE/../../include/nerf_b200_debug.h" -nt "$obj" ]] && stale=1

@@ -1,0 +1,492 @@
+// fp32-in / fp32-out GEMMs on the Blackwell tensor cores for the BATCH_NORM training path (bn_train.cu), sm_100a only.
+//
+// BATCH_NORM=true (models.py:30-33,49-52) needs the statistics of the WHOLE batch between two Dense layers, so that path
+// runs layer by layer and its contractions are plain GEMMs over row-major fp32 activations.  They used to go to cuBLAS
+// sgemm; they now run here as tcgen05 MMAs with split operands ("bf16x3"): every fp32 value x is written to shared
+// memory as hi = bf16(x) and lo = bf16(x - hi), and  A B ~= Ahi Bhi + Alo Bhi + Ahi Blo  accumulates in fp32 in tensor
+// memory (the dropped Alo Blo term is 2^-16 relative) -- fp32-grade results at a third of the bf16 MMA rate, which is
+// still ~20x the fp32 FMA rate.  Two kernels:
+//   gemm_rows_kernel   C (M x N) = A (M x K) op(B) [+ C]      M = samples (large), K, N <= 256
+//       one 128-row tile of A at a time: 8 warps convert it (hi / lo, K-major, 128B-swizzled), a producer thread
+//       streams the pre-split B chunks ([128 n x 64 k], hi then lo) through a 4-slot ring, one thread issues the MMAs,
+//       warps 0-3 write the accumulator out.
+//   gemm_tn_kernel     C (Mo x N) += A^T B,  A (Ms x Mo), B (Ms x N): the contraction runs over the SAMPLES
+//       a [128 samples x 64 features] tile stored K-major IS an MN-major operand of the transposed product (the trick of
+//       nerf_wgrad_tc_kernel), so the same conversion feeds it; each CTA owns a slab of sample tiles and one 128-column
+//       half of N, keeps its (<= 256 x 128) accumulator in tensor memory and adds it to C with atomics at the end.
+// Skinny shapes (N <= 4 or K <= 4: the sigma / rgb heads) are CUDA-core kernels at the end of this file.
+#include "common.cuh"
+#include "tc5.cuh"
+
+using namespace nerf;
+using namespace tc5;
+
+namespace {
+
+constexpr int GT_THREADS = 320;      // warps 0-7: operand conversion (0-3 also epilogue), 8: B producer, 9: MMA issuer
+constexpr int GT_WORKERS = 256;
+constexpr int GT_KB = 4;             // K <= 256
+constexpr int GT_SM_AHI = 0;
+constexpr int GT_SM_ALO = GT_KB * 16384;
+constexpr int GT_SM_RING = 2 * GT_KB * 16384;          // 4 x 16 KB
+constexpr int GT_STAGES = 4;
+constexpr int GT_SM_BAR = GT_SM_RING + GT_STAGES * 16384;
+constexpr int GT_SMEM = GT_SM_BAR + 128 + 1024;
+
+__device__ __forceinline__ void split_store(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    *reinterpret_cast<__nv_bfloat16*>(hi_tile + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(lo_tile + off) = l;
+}
+
+__device__ __forceinline__ void split_store4(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, const float4& v) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                        h3 = __float2bfloat16_rn(v.w);
+    uint2 hi, lo;
+    hi.x = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+    hi.y = pack_bf16x2(__bfloat162float(h2), __bfloat162float(h3));
+    lo.x = pack_bf16x2(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+    lo.y = pack_bf16x2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+    *reinterpret_cast<uint2*>(hi_tile + off) = hi;
+    *reinterpret_cast<uint2*>(lo_tile + off) = lo;
+}
+
+// rows [row0, row0 + 128) x columns [col0, col0 + 64 * blocks) of a row-major fp32 matrix -> hi / lo bf16 tiles,
+// [block][128 rows][64] K-major 128B-swizzled; rows >= rows_end and columns >= cols_end read as zero.
+// `worker` = 0 .. 255 (8 warps): warp w takes rows w, w + 8, ..; lanes run along the columns (coalesced).  All loads of
+// a group of rows are issued before the first conversion (a load per iteration ran at one HBM round trip per element).
+__device__ __forceinline__ void convert_tile(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_end,
+                                             int col0, int cols_end, int blocks, uint8_t* hi_tile, uint8_t* lo_tile,
+                                             int worker) {
+    const int w = worker >> 5, lane = worker & 31;
+    const int ncols = blocks * 64;
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src + col0) & 15) == 0) && ((cols_end - col0) % 4 == 0 || cols_end - col0 >= ncols);
+    if (vec) {
+        // lane <-> four consecutive columns; up to two float4 per row and lane (256 columns), four rows in flight
+        for (int r0 = w; r0 < 128; r0 += 32) {
+            float4 v[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t g = row0 + r0 + 8 * i;
+                const float* __restrict__ p = src + g * ld + col0;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = 4 * lane + 128 * j;
+                    v[i][j] = (g < rows_end && c < ncols && col0 + c < cols_end) ? __ldg(reinterpret_cast<const float4*>(p + c))
+                                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = 4 * lane + 128 * j, r = r0 + 8 * i;
+                    if (c < ncols) split_store4(hi_tile, lo_tile, (uint32_t)(c >> 6) * 16384u + sw128_offset(r, c & 63), v[i][j]);
+                }
+        }
+    } else {
+        for (int r0 = w; r0 < 128; r0 += 16) {
+            float v[2][8];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int64_t g = row0 + r0 + 8 * i;
+                const float* __restrict__ p = src + g * ld + col0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = lane + 32 * j;
+                    v[i][j] = (g < rows_end && c < ncols && col0 + c < cols_end) ? __ldg(p + c) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = lane + 32 * j, r = r0 + 8 * i;
+                    if (c < ncols) split_store(hi_tile, lo_tile, (uint32_t)(c >> 6) * 16384u + sw128_offset(r, c & 63), v[i][j]);
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// B operand of gemm_rows_kernel, split and packed once per call: chunk ((h * KB + kb) * 2 + {hi, lo}) = [128 n x 64 k]
+//   tb = 0: B is (K x N) row-major -> B[n][k] = B[k * ldb + n];  tb = 1: B is (N x K) row-major
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_b_split_kernel(const float* __restrict__ B, int64_t ldb, int tb, int N, int K,
+                                                           int NH, int KB, uint8_t* __restrict__ out) {
+    const int total = NH * KB * 128 * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int k = i & 63, n = (i >> 6) & 127, kb = (i >> 13) % KB, h = (i >> 13) / KB;
+        if (!tb) {                       // run along n for coalesced reads of a (K x N) matrix
+            n = i & 127; k = (i >> 7) & 63;
+        }
+        const int gn = h * 128 + n, gk = kb * 64 + k;
+        float v = 0.f;
+        if (gn < N && gk < K) v = tb ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn];
+        uint8_t* chunk = out + (size_t)((h * KB + kb) * 2) * 16384;
+        split_store(chunk, chunk + 16384, sw128_offset(n, k), v);
+    }
+}
+
+struct RowsParams {
+    const float* A; int64_t lda;
+    const uint8_t* b_chunks;
+    float* C; int64_t ldc;
+    int64_t M; int N; int K;
+    int NH, KB;
+    float beta;
+};
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gemm_rows_kernel(const RowsParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = base + GT_SM_BAR, bar_empty = bar_full + 8 * GT_STAGES, bar_ready = bar_empty + 8 * GT_STAGES,
+                   bar_done = bar_ready + 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + GT_SM_BAR + 96);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < GT_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        mbar_init(bar_ready, GT_WORKERS);
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(base + GT_SM_BAR + 96, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t n_tiles = (P.M + 127) / 128;
+    const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int n_chunks = P.NH * P.KB * 2;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            int slot = 0; uint32_t par = 1;
+            for (int it = 0; it < my_tiles; ++it)
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(bar_empty + 8 * slot, par, 31);
+                    mbar_arrive_expect_tx(bar_full + 8 * slot, 16384);
+                    bulk_g2s(base + GT_SM_RING + slot * 16384, P.b_chunks + (size_t)c * 16384, 16384, bar_full + 8 * slot);
+                    if (++slot == GT_STAGES) { slot = 0; par ^= 1; }
+                }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+            int slot = 0; uint32_t par = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                mbar_wait(bar_ready, (uint32_t)(it & 1), 32);          // A tile converted; previous accumulator drained
+                tc_fence_after();
+                for (int h = 0; h < P.NH; ++h)
+                    for (int kb = 0; kb < P.KB; ++kb) {
+                        const uint32_t ahi = base + GT_SM_AHI + kb * 16384, alo = base + GT_SM_ALO + kb * 16384;
+                        const uint32_t d = tmem_base + h * 128;
+                        mbar_wait(bar_full + 8 * slot, par, 33);       // B hi
+                        tc_fence_after();
+                        uint32_t b = base + GT_SM_RING + slot * 16384;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_bf16_ss(d, make_sdesc_sw128(ahi + k * 32, 16, 1024), make_sdesc_sw128(b + k * 32, 16, 1024), idesc,
+                                        (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_bf16_ss(d, make_sdesc_sw128(alo + k * 32, 16, 1024), make_sdesc_sw128(b + k * 32, 16, 1024), idesc, 1u);
+                        mma_commit(bar_empty + 8 * slot);
+                        if (++slot == GT_STAGES) { slot = 0; par ^= 1; }
+                        mbar_wait(bar_full + 8 * slot, par, 34);       // B lo
+                        tc_fence_after();
+                        b = base + GT_SM_RING + slot * 16384;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_bf16_ss(d, make_sdesc_sw128(ahi + k * 32, 16, 1024), make_sdesc_sw128(b + k * 32, 16, 1024), idesc, 1u);
+                        mma_commit(bar_empty + 8 * slot);
+                        if (++slot == GT_STAGES) { slot = 0; par ^= 1; }
+                    }
+                mma_commit(bar_done);
+            }
+        }
+    } else {
+        const int worker = threadIdx.x;
+        const bool vec = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+        for (int it = 0; it < my_tiles; ++it) {
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            // the MMAs of the previous tile have finished reading the A tile (every worker waited for bar_done below)
+            convert_tile(P.A, P.lda, tile * 128, P.M, 0, P.K, P.KB, smem + GT_SM_AHI, smem + GT_SM_ALO, worker);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_ready);
+            mbar_wait(bar_done, (uint32_t)(it & 1), 35);
+            tc_fence_after();
+            if (warp < 4) {
+                const int64_t row = tile * 128 + 32 * warp + lane;
+                for (int cg = 0; cg < P.NH * 4; ++cg) {
+                    if (cg * 32 >= P.N) break;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + (uint32_t(32 * warp) << 16) + cg * 32, v);
+                    tmem_ld_wait();
+                    if (row < P.M) {
+                        float* dst = P.C + row * P.ldc + cg * 32;
+                        if (vec && cg * 32 + 32 <= P.N) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                                if (P.beta != 0.f) {
+                                    const float4 c = *reinterpret_cast<const float4*>(dst + 4 * q);
+                                    o.x = fmaf(P.beta, c.x, o.x); o.y = fmaf(P.beta, c.y, o.y);
+                                    o.z = fmaf(P.beta, c.z, o.z); o.w = fmaf(P.beta, c.w, o.w);
+                                }
+                                *reinterpret_cast<float4*>(dst + 4 * q) = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (cg * 32 + q < P.N) {
+                                    float o = __uint_as_float(v[q]);
+                                    if (P.beta != 0.f) o = fmaf(P.beta, dst[q], o);
+                                    dst[q] = o;
+                                }
+                        }
+                    }
+                }
+                tc_fence_before();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C (Mo x N) += A^T B over the samples:  A (Ms x Mo), B (Ms x N) row-major fp32.  grid = (slabs, N halves)
+// ------------------------------------------------------------------------------------------------
+constexpr int TN_SM_AHI = 0;                      // [4 blocks of 64 features][128 samples][64]
+constexpr int TN_SM_ALO = 65536;
+constexpr int TN_SM_BHI = 131072;                 // [2 blocks][128][64]
+constexpr int TN_SM_BLO = 131072 + 32768;
+constexpr int TN_SM_BAR = 196608;
+constexpr int TN_SMEM = TN_SM_BAR + 128 + 1024;
+
+struct TnParams {
+    const float* A; int64_t lda;
+    const float* B; int64_t ldb;
+    float* C; int64_t ldc;
+    int64_t Ms; int Mo; int N;
+};
+
+__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tn_kernel(const TnParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base = (raw_addr + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw_addr);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_ready = base + TN_SM_BAR, bar_done = bar_ready + 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TN_SM_BAR + 32);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_ready, GT_WORKERS);
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 9) tmem_alloc(base + TN_SM_BAR + 32, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nh = blockIdx.y;
+    const int MB = (P.Mo + 127) / 128;                 // M = 128 blocks of the transposed operand
+    const int64_t n_tiles = (P.Ms + 127) / 128;
+    const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);      // both operands MN-major
+            for (int it = 0; it < my_tiles; ++it) {
+                mbar_wait(bar_ready, (uint32_t)(it & 1), 36);
+                tc_fence_after();
+                for (int mb = 0; mb < MB; ++mb) {
+                    const uint32_t ahi = base + TN_SM_AHI + mb * 32768, alo = base + TN_SM_ALO + mb * 32768;
+                    const uint32_t bhi = base + TN_SM_BHI, blo = base + TN_SM_BLO;
+                    const uint32_t d = tmem_base + mb * 128;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {                       // 16 samples = 16 rows = 2048 bytes
+                        const uint64_t dah = make_sdesc_sw128(ahi + k * 2048, 16384, 1024), dal = make_sdesc_sw128(alo + k * 2048, 16384, 1024);
+                        const uint64_t dbh = make_sdesc_sw128(bhi + k * 2048, 16384, 1024), dbl = make_sdesc_sw128(blo + k * 2048, 16384, 1024);
+                        mma_bf16_ss(d, dah, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        mma_bf16_ss(d, dal, dbh, idesc, 1u);
+                        mma_bf16_ss(d, dah, dbl, idesc, 1u);
+                    }
+                }
+                mma_commit(bar_done);
+            }
+        }
+    } else if (warp < 8) {
+        const int worker = threadIdx.x;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            if (it > 0) mbar_wait(bar_done, (uint32_t)((it - 1) & 1), 37);      // the previous tile's MMAs have read the tiles
+            convert_tile(P.A, P.lda, tile * 128, P.Ms, 0, P.Mo, MB * 2, smem + TN_SM_AHI, smem + TN_SM_ALO, worker);
+            convert_tile(P.B, P.ldb, tile * 128, P.Ms, nh * 128, P.N, 2, smem + TN_SM_BHI, smem + TN_SM_BLO, worker);
+            fence_proxy_async_smem();
+            mbar_arrive(bar_ready);
+        }
+        if (my_tiles > 0 && warp < 4) {
+            mbar_wait(bar_done, (uint32_t)((my_tiles - 1) & 1), 38);
+            tc_fence_after();
+            for (int mb = 0; mb < MB; ++mb) {
+                const int r = mb * 128 + 32 * warp + lane;              // row of C = feature of A
+                for (int cg = 0; cg < 4; ++cg) {
+                    const int c0 = nh * 128 + cg * 32;
+                    if (c0 >= P.N) break;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + (uint32_t(32 * warp) << 16) + mb * 128 + cg * 32, v);
+                    tmem_ld_wait();
+                    if (r < P.Mo) {
+                        float* dst = P.C + (int64_t)r * P.ldc + c0;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if (c0 + q < P.N) atomicAdd(dst + q, __uint_as_float(v[q]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// skinny shapes on CUDA cores
+// ------------------------------------------------------------------------------------------------
+// C (M x N) = A (M x K) op(B) [+ C], N <= 4: one warp per row, lanes along K
+__global__ void __launch_bounds__(256) small_rows_dot_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                             int64_t ldb, int tb, float* __restrict__ C, int64_t ldc, int64_t M,
+                                                             int N, int K, float beta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = lane; k < K; k += 32) {
+            const float a = A[m * lda + k];
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                if (n < N) acc[n] = fmaf(a, tb ? B[(int64_t)n * ldb + k] : B[(int64_t)k * ldb + n], acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+        if (lane < N) {
+            float v = acc[0];
+            if (lane == 1) v = acc[1]; else if (lane == 2) v = acc[2]; else if (lane == 3) v = acc[3];
+            float* dst = C + m * ldc + lane;
+            *dst = (beta != 0.f) ? fmaf(beta, *dst, v) : v;
+        }
+    }
+}
+// C (M x N) = A (M x K) op(B) [+ C], K <= 4: one thread per output element
+__global__ void __launch_bounds__(256) small_rows_outer_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                               int64_t ldb, int tb, float* __restrict__ C, int64_t ldc, int64_t M,
+                                                               int N, int K, float beta) {
+    const int64_t total = M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / N;
+        const int n = (int)(i - m * N);
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(A[m * lda + k], tb ? B[(int64_t)n * ldb + k] : B[(int64_t)k * ldb + n], acc);
+        float* dst = C + m * ldc + n;
+        *dst = (beta != 0.f) ? fmaf(beta, *dst, acc) : acc;
+    }
+}
+// C (Mo x N) += A^T B, N <= 4, Mo <= 256: thread j owns column j of A over a slab of samples
+__global__ void __launch_bounds__(256) small_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                                                       int64_t ldb, float* __restrict__ C, int64_t ldc, int64_t Ms, int Mo, int N) {
+    const int j = threadIdx.x;
+    const int64_t per = (Ms + gridDim.x - 1) / gridDim.x;
+    const int64_t m0 = (int64_t)blockIdx.x * per, m1 = (m0 + per < Ms) ? m0 + per : Ms;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j < Mo) {
+        for (int64_t m = m0; m < m1; ++m) {
+            const float a = A[m * lda + j];
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                if (n < N) acc[n] = fmaf(a, __ldg(B + m * ldb + n), acc[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+            if (n < N) atomicAdd(C + (int64_t)j * ldc + n, acc[n]);
+    }
+}
+
+uint8_t* g_b_scratch = nullptr;      // split B chunks of the GEMM in flight (one stream at a time: the BN path is serial)
+constexpr size_t B_SCRATCH_BYTES = 2 * GT_KB * 2 * 16384;
+bool g_attr_set = false;
+
+}  // namespace
+
+namespace nerf {
+
+// row-major C (M x N) = op(A) op(B) + beta C, fp32 in and out.  ta: A is stored (K x M) and the contraction runs over
+// its rows (the sample dimension; beta must be 1: the result is ADDED to C); tb: B is stored (N x K).
+int tc_gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+                int64_t ldb, float beta, float* C, int64_t ldc) {
+    if (M <= 0 || N <= 0 || K <= 0) return NERF_OK;
+    if (!g_attr_set) {
+        NERF_CUDA(cudaFuncSetAttribute(gemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+        NERF_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
+        NERF_CUDA(cudaMalloc((void**)&g_b_scratch, B_SCRATCH_BYTES));
+        g_attr_set = true;
+    }
+    if (ta) {
+        // M = rows of C = features of A (<= 256), K = samples
+        if (tb) return fail(NERF_ERR_INVALID, "tc_gemm_f32: A^T B^T is not used by this library");
+        if (beta != 1.f) return fail(NERF_ERR_INVALID, "tc_gemm_f32: the transposed product accumulates into C (beta = 1)");
+        if (M > 256 || N > 256) return fail(NERF_ERR_INVALID, "tc_gemm_f32: transposed product limited to 256 x 256 outputs");
+        if (N <= 4) {
+            const int grid = (int)(ceil_div(K, 2048) < 4 * num_sms() ? ceil_div(K, 2048) : 4 * num_sms());
+            small_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, (int64_t)K, (int)M, N);
+            NERF_LAUNCHED();
+            return NERF_OK;
+        }
+        TnParams P = {A, lda, B, ldb, C, ldc, (int64_t)K, (int)M, N};
+        const int64_t tiles = ceil_div(K, 128);
+        const int NH = (N + 127) / 128;
+        int slabs = num_sms() / NH;
+        if (slabs > tiles) slabs = (int)tiles;
+        gemm_tn_kernel<<<dim3(slabs, NH), GT_THREADS, TN_SMEM, st>>>(P);
+        NERF_LAUNCHED();
+        return NERF_OK;
+    }
+    if (N <= 4) {
+        small_rows_dot_kernel<<<stream_grid(M * 32, 256), 256, 0, st>>>(A, lda, B, ldb, tb ? 1 : 0, C, ldc, M, N, K, beta);
+        NERF_LAUNCHED();
+        return NERF_OK;
+    }
+    if (K <= 4) {
+        small_rows_outer_kernel<<<stream_grid(M * N, 256), 256, 0, st>>>(A, lda, B, ldb, tb ? 1 : 0, C, ldc, M, N, K, beta);
+        NERF_LAUNCHED();
+        return NERF_OK;
+    }
+    if (N > 256 || K > 64 * GT_KB) return fail(NERF_ERR_INVALID, "tc_gemm_f32: N and K are limited to 256");
+    const int NH = (N + 127) / 128, KB = (K + 63) / 64;
+    pack_b_split_kernel<<<NH * KB * 4, 256, 0, st>>>(B, ldb, tb ? 1 : 0, N, K, NH, KB, g_b_scratch);
+    NERF_LAUNCHED();
+    RowsParams P = {A, lda, g_b_scratch, C, ldc, M, N, K, NH, KB, beta};
+    const int64_t tiles = ceil_div(M, 128);
+    gemm_rows_kernel<<<(int)(tiles < num_sms() ? tiles : num_sms()), GT_THREADS, GT_SMEM, st>>>(P);
+    NERF_LAUNCHED();
+    return NERF_OK;
+}
+
+}  // namespace nerf
+
+// test hook (nerf_b200_debug.h): the GEMM above on caller buffers
+extern "C" int nerf_selftest_gemm_f32(int ta, int tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
+                                      int64_t ldb, float beta, float* C, int64_t ldc, void* stream) {
+    NERF_CHECK_ARG(A && B && C, "null pointer");
+    return nerf::tc_gemm_f32((cudaStream_t)stream, ta != 0, tb != 0, M, N, K, A, lda, B, ldb, beta, C, ldc);
+}
