@@ -162,8 +162,9 @@ int nerf_metrics_accumulate(nerf_ctx* ctx, const float* images, const float* rgb
  * buffer scaled by grad_scale (1/world_size after a sum all-reduce); bumps the step count. */
 int nerf_adam_step(nerf_ctx* ctx, float grad_scale, void* stream);
 /* ---- BATCH_NORM=true training (models.py:30-33, 49-52 with training=True) --------------------------------------------
- * Batch statistics couple all samples of a batch between consecutive layers, so this is a separate, layer-by-layer fp32
- * path (cuBLAS sgemm between hand-written statistics / normalise / backward kernels; cuBLAS is bound at first use).  It
+ * Batch statistics couple all samples of a batch between consecutive layers, so this is a separate, layer-by-layer path on
+ * fp32 activations: tcgen05 GEMMs on split bf16 operands (hi + residual, fp32 accumulation: results to ~1e-5 of the
+ * products' scale; csrc/gemm_tc.cu, no library GEMM) between hand-written statistics / normalise / backward kernels.  It
  * serves the reference's small-batch BN configs and does not use a nerf_ctx: every buffer is the caller's.
  *   params   [coarse | fine], nerf_param_count() floats each: Dense kernels and biases, un-folded
  *   bn       [coarse | fine] x [gamma | beta | moving_mean | moving_variance], nerf_bn_param_count() floats each, layers in

@@ -143,8 +143,11 @@ __global__ void __launch_bounds__(128) dirbias_kernel(const float* __restrict__ 
 // forward of both nets per 4096-ray step: bulk stores 1.85 ms, 256-bit register stores 2.06 ms, 128-bit register
 // stores 2.44 ms -- the LSU path loses to the TMA engine even though it spares the shared-memory reads.
 #ifdef NERF_EXP_COALESCED_SAVE
+// TIMING EXPERIMENT (round 2; the weight-gradient kernel does not read this layout): images as [16-byte column group][row],
+// so that a warp's 128-bit register stores cover 512 contiguous bytes instead of 32 different 128-byte lines.  Measured
+// 1.91 ms per step (forward of both nets) against 1.57-1.75 ms with bulk stores: coalescing is not what the LSU path lacks.
 constexpr bool kDirectSave = true;
-constexpr bool kCoalescedSave = true;     // TIMING EXPERIMENT: [16-byte column group][row][16 B] image, 512 contiguous bytes per warp store
+constexpr bool kCoalescedSave = true;
 #else
 constexpr bool kDirectSave = false;
 constexpr bool kCoalescedSave = false;

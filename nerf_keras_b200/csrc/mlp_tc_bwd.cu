@@ -450,7 +450,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     const uint32_t tmem_base = *tmem_slot;
 
     // this CTA's tiles: job_cta, job_cta + job_ctas, ... (the order in which the dX chain produces them)
-    const int n_my = (P.n_tiles > job_cta) ? (int)((P.n_tiles - job_cta + job_ctas - 1) / job_ctas) : 0;
+    // next to the chain (P.progress): job_cta, job_cta + job_ctas, .. -- the order in which the chain produces tiles;
+    // alone: one contiguous slab of tiles per CTA (same speed as the interleaved order: 1.69 ms per step, HBM-bound)
+    const bool interleave = P.progress != nullptr;
+    const int64_t slab = (P.n_tiles + job_ctas - 1) / job_ctas;
+    const int64_t t_first = interleave ? job_cta : (int64_t)job_cta * slab, t_step = interleave ? job_ctas : 1;
+    int n_my;
+    if (interleave) n_my = (P.n_tiles > job_cta) ? (int)((P.n_tiles - job_cta + job_ctas - 1) / job_ctas) : 0;
+    else n_my = (int)((t_first + slab <= P.n_tiles) ? slab : (P.n_tiles > t_first ? P.n_tiles - t_first : 0));
 
     if (warp == 4) {
         // ===================== loader =====================
@@ -460,7 +467,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
             long long t_flag = 0, t_slot = 0;
             auto now_ns = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
             for (int i = 0; i < n_my; ++i) {
-                const int64_t tile = job_cta + (int64_t)i * job_ctas;
+                const int64_t tile = t_first + (int64_t)i * t_step;
                 long long t0 = P.stats ? now_ns() : 0;
                 mbar_wait(bar_bempty + 8 * bs, bpar, 11);
                 if (P.stats) { const long long t1 = now_ns(); t_slot += t1 - t0; t0 = t1; }
@@ -555,11 +562,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
             uint32_t apar = 0, bpar = 0;
             // d sigma of this warp's 16 samples of a tile: one load per lane, fetched ONE TILE AHEAD
             float next_ds = 0.f;
-            if (do_sig && lane < 16 && n_my > 0) next_ds = __ldg(&P.dpreds[(int64_t)job_cta * TILE_M + sw * 16 + lane].w);
+            if (do_sig && lane < 16 && n_my > 0) next_ds = __ldg(&P.dpreds[t_first * TILE_M + sw * 16 + lane].w);
             for (int i = 0; i < n_my; ++i) {
-                const int64_t tile = job_cta + (int64_t)i * job_ctas;
+                const int64_t tile = t_first + (int64_t)i * t_step;
                 const float my_ds = next_ds;
-                if (do_sig && lane < 16 && i + 1 < n_my) next_ds = __ldg(&P.dpreds[(tile + job_ctas) * TILE_M + sw * 16 + lane].w);
+                if (do_sig && lane < 16 && i + 1 < n_my) next_ds = __ldg(&P.dpreds[(tile + t_step) * TILE_M + sw * 16 + lane].w);
                 if (do_bias) {
                     mbar_wait(bar_bfull + 8 * bs, bpar, 16);
                     if (sub < J.n_b && !(P.debug & 16)) {
