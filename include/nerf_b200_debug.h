@@ -32,9 +32,10 @@ int nerf_debug_pdf_draws(uint64_t seed, uint64_t counter, int64_t batch, int nf,
  * chain but on the overlap budget of SMs, bits 8.. = that budget (0: the context's default). */
 int nerf_debug_flags(int flags);
 /* Test hook: the fp32 GEMM of the BATCH_NORM training path (csrc/gemm_tc.cu: tcgen05 MMAs on split bf16 operands).
- * Row-major C (M x N) = op(A) op(B) + beta C on device buffers; ta: A stored (K x M), result ADDED to C (beta = 1). */
+ * Row-major C (M x N) = op(A) op(B) + beta C on device buffers; ta: A stored (K x M), result ADDED to C (beta = 1);
+ * precise: three-way operand split (fp32-grade; what the forward GEMMs use) instead of two-way. */
 int nerf_selftest_gemm_f32(int ta, int tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
-                           int64_t ldb, float beta, float* C, int64_t ldc, void* stream);
+                           int64_t ldb, float beta, float* C, int64_t ldc, int precise, void* stream);
 /* Diagnostics: per weight-gradient CTA eight int64 {job, tiles, end of CTA (globaltimer ns), ns its loader waited for
  * the dX chain's progress counters, ns it waited for free ring slots, end of its loader (ns), start of the CTA (ns), 0}; device buffer of
  * 2 nets x 148 x 8 int64, NULL disables. */

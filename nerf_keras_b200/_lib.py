@@ -73,7 +73,7 @@ SIGNATURES = {
     "nerf_debug_pair_mode": (_I, [_I]),
     "nerf_debug_trace": (_I, [_P]),
     "nerf_debug_wgrad_stats": (_I, [_P]),
-    "nerf_selftest_gemm_f32": (_I, [_I, _I, _L, _I, _I, _P, _L, _P, _L, C.c_float, _P, _L, _P]),
+    "nerf_selftest_gemm_f32": (_I, [_I, _I, _L, _I, _I, _P, _L, _P, _L, C.c_float, _P, _L, _I, _P]),
     "nerf_selftest_gemm_2cta": (_I, [_P, _P, _P, _I, _I, _P]),
     "nerf_selftest_gemm_ts": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nerf_selftest_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

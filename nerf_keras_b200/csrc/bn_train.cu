@@ -21,7 +21,7 @@
 namespace nerf {
 // gemm_tc.cu: tcgen05 MMAs on split bf16 operands, fp32 accumulation in tensor memory; skinny head shapes on CUDA cores
 int tc_gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
-                int64_t ldb, float beta, float* C, int64_t ldc);
+                int64_t ldb, float beta, float* C, int64_t ldc, bool precise);
 }  // namespace nerf
 extern "C" int nerf_metrics_grad(const float*, const float*, const float*, int64_t, float*, float*, float*, void*);
 extern "C" int nerf_volume_render_bwd(const float* preds, const float* t, const float* d_rgb, const float* d_w_extra, int64_t batch,
@@ -59,9 +59,10 @@ Arch make_arch(const nerf_config& c) {
 }
 
 // row-major C (M x N) = op(A) op(B) + beta C on the tensor cores (gemm_tc.cu); no library GEMM is involved
+// forward products (precise = true) use the three-way operand split: their results decide ReLU signs
 int gemm(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, const float* A, int lda, const float* B, int ldb,
-         float beta, float* C, int ldc) {
-    return nerf::tc_gemm_f32(st, ta, tb, M, N, K, A, lda, B, ldb, beta, C, ldc);
+         float beta, float* C, int ldc, bool precise = false) {
+    return nerf::tc_gemm_f32(st, ta, tb, M, N, K, A, lda, B, ldb, beta, C, ldc, precise);
 }
 #define GEMM(...) do { int _rc = gemm(__VA_ARGS__); if (_rc) return _rc; } while (0)
 
@@ -239,9 +240,9 @@ int net_forward(cudaStream_t st, const nerf_config& cfg, const Arch& A, const fl
     for (int l = 0; l < L; ++l) {
         const Lay& ly = A.lay[l];
         float* z = nb.zh[l];
-        GEMM(st, false, false, M, H, xk, x, xk, P + ly.w, H, 0.f, z, H);
+        GEMM(st, false, false, M, H, xk, x, xk, P + ly.w, H, 0.f, z, H, true);
         if (ly.fi > xk)   // skip connection: [h, enc] @ W = h @ W[:H] + enc @ W[H:]
-            GEMM(st, false, false, M, H, A.ex, nb.enc, A.ex, P + ly.w + (int64_t)xk * H, H, 1.f, z, H);
+            GEMM(st, false, false, M, H, A.ex, nb.enc, A.ex, P + ly.w + (int64_t)xk * H, H, 1.f, z, H, true);
         if ((rc = batch_norm_fwd(st, z, nb.a[l], M, H, P + ly.b, gamma + l * H, beta + l * H, mmean + l * H, mvar + l * H,
                                  nb.mu[l], nb.rstd[l], sums)))
             return rc;
@@ -252,10 +253,10 @@ int net_forward(cudaStream_t st, const nerf_config& cfg, const Arch& A, const fl
     // (L-1) % skip != 0; the reference's 8 / 4 and every shipped config satisfy that
     if (ls.fi != H) return fail(NERF_ERR_INVALID, "BN training: a skip connection into the heads is not supported");
     GEMM(st, false, false, M, 1, H, x, H, P + ls.w, 1, 0.f, nb.preds + 3, 4);                 // sigma -> preds[:, 3]
-    GEMM(st, false, false, M, H, H, x, H, P + lf.w, H, 0.f, nb.feat, H);
+    GEMM(st, false, false, M, H, H, x, H, P + lf.w, H, 0.f, nb.feat, H, true);
     bias_rows_kernel<<<egrid(M * H), 256, 0, st>>>(nb.feat, M * H, H, P + lf.b);
-    GEMM(st, false, false, M, H / 2, H, nb.feat, H, P + ld.w, H / 2, 0.f, nb.zh_d, H / 2);
-    GEMM(st, false, false, M, H / 2, A.ed, nb.dirc, A.ed, P + ld.w + (int64_t)H * (H / 2), H / 2, 1.f, nb.zh_d, H / 2);
+    GEMM(st, false, false, M, H / 2, H, nb.feat, H, P + ld.w, H / 2, 0.f, nb.zh_d, H / 2, true);
+    GEMM(st, false, false, M, H / 2, A.ed, nb.dirc, A.ed, P + ld.w + (int64_t)H * (H / 2), H / 2, 1.f, nb.zh_d, H / 2, true);
     if ((rc = batch_norm_fwd(st, nb.zh_d, nb.a_d, M, H / 2, P + ld.b, gamma + L * H, beta + L * H, mmean + L * H, mvar + L * H,
                              nb.mu[L], nb.rstd[L], sums)))
         return rc;

@@ -5,11 +5,13 @@
 // sgemm; they now run here as tcgen05 MMAs with split operands ("bf16x3"): every fp32 value x is written to shared
 // memory as hi = bf16(x) and lo = bf16(x - hi), and  A B ~= Ahi Bhi + Alo Bhi + Ahi Blo  accumulates in fp32 in tensor
 // memory (the dropped Alo Blo term is 2^-16 relative) -- fp32-grade results at a third of the bf16 MMA rate, which is
-// still ~20x the fp32 FMA rate.  Two kernels:
+// still ~20x the fp32 FMA rate.  The forward GEMMs use a three-way split (hi + mid + lo = x exactly, six products):
+// a pre-activation that is off by 1e-5 flips ReLU decisions, and every flip is a visible difference in the gradients.
+// Two kernels:
 //   gemm_rows_kernel   C (M x N) = A (M x K) op(B) [+ C]      M = samples (large), K, N <= 256
-//       one 128-row tile of A at a time: 8 warps convert it (hi / lo, K-major, 128B-swizzled), a producer thread
-//       streams the pre-split B chunks ([128 n x 64 k], hi then lo) through a 4-slot ring, one thread issues the MMAs,
-//       warps 0-3 write the accumulator out.
+//       a pipeline over the 64-wide K-blocks of 128-row tiles: 8 warps convert A (K-major, 128B-swizzled part tiles) into
+//       a 3-stage ring, a producer thread streams the pre-split B chunks ([128 n x 64 k] per part) through a 4-slot ring,
+//       one thread issues the MMAs into one of two 256-column accumulators, 4 warps write the other one out.
 //   gemm_tn_kernel     C (Mo x N) += A^T B,  A (Ms x Mo), B (Ms x N): the contraction runs over the SAMPLES
 //       a [128 samples x 64 features] tile stored K-major IS an MN-major operand of the transposed product (the trick of
 //       nerf_wgrad_tc_kernel), so the same conversion feeds it; each CTA owns a slab of sample tiles and one 128-column
@@ -23,15 +25,8 @@ using namespace tc5;
 
 namespace {
 
-constexpr int GT_THREADS = 320;      // warps 0-7: operand conversion (0-3 also epilogue), 8: B producer, 9: MMA issuer
+constexpr int GT_THREADS = 320;      // transposed GEMM: warps 0-7 operand conversion (0-3 also the final write-out), 9: MMA issuer
 constexpr int GT_WORKERS = 256;
-constexpr int GT_KB = 4;             // K <= 256
-constexpr int GT_SM_AHI = 0;
-constexpr int GT_SM_ALO = GT_KB * 16384;
-constexpr int GT_SM_RING = 2 * GT_KB * 16384;          // 4 x 16 KB
-constexpr int GT_STAGES = 4;
-constexpr int GT_SM_BAR = GT_SM_RING + GT_STAGES * 16384;
-constexpr int GT_SMEM = GT_SM_BAR + 128 + 1024;
 
 __device__ __forceinline__ void split_store(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float v) {
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -110,22 +105,103 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ src, int6
 }
 
 // ------------------------------------------------------------------------------------------------
-// B operand of gemm_rows_kernel, split and packed once per call: chunk ((h * KB + kb) * 2 + {hi, lo}) = [128 n x 64 k]
-//   tb = 0: B is (K x N) row-major -> B[n][k] = B[k * ldb + n];  tb = 1: B is (N x K) row-major
+// Row GEMM:  C (M x N) = A (M x K) op(B) [+ C].  PARTS = 2: x ~ hi + lo (three products, ~1e-5 of the products' scale);
+// PARTS = 3: x = hi + mid + lo exactly (six products, fp32-grade) -- the FORWARD GEMMs of the BATCH_NORM path use it,
+// because a pre-activation that moves by 1e-5 flips ReLU decisions and every flip is a visible gradient difference.
 // ------------------------------------------------------------------------------------------------
+constexpr int GR_THREADS = 448;      // warps 0-7: A conversion, 8-11: epilogue, 12: B producer, 13: MMA issuer
+constexpr int GR_CONV = 256;
+constexpr int GR_A_STAGES = 3;       // stage = one 64-wide K-block of a 128-row tile, PARTS x 16 KB
+constexpr int GR_B_STAGES = 4;       // 16 KB chunks [128 n x 64 k] of one part of B
+constexpr int GR_SM_A = 0;
+constexpr int GR_SM_B = GR_A_STAGES * 3 * 16384;
+constexpr int GR_SM_BAR = GR_SM_B + GR_B_STAGES * 16384;
+constexpr int GR_SMEM = GR_SM_BAR + 256 + 1024;
+
+template <int PARTS>
+__device__ __forceinline__ void split_parts(float v, __nv_bfloat16 (&o)[3]) {
+    o[0] = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(o[0]);
+    o[1] = __float2bfloat16_rn(r1);
+    o[2] = (PARTS == 3) ? __float2bfloat16_rn(r1 - __bfloat162float(o[1])) : __float2bfloat16_rn(0.f);
+}
+
+// B split and packed once per call: chunk ((kb * NH + h) * PARTS + part) = [128 n x 64 k], K-major, 128B-swizzled
+//   tb = 0: B is (K x N) row-major -> B[n][k] = B[k * ldb + n];  tb = 1: B is (N x K) row-major
+template <int PARTS>
 __global__ void __launch_bounds__(256) pack_b_split_kernel(const float* __restrict__ B, int64_t ldb, int tb, int N, int K,
                                                            int NH, int KB, uint8_t* __restrict__ out) {
     const int total = NH * KB * 128 * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int k = i & 63, n = (i >> 6) & 127, kb = (i >> 13) % KB, h = (i >> 13) / KB;
+        int k = i & 63, n = (i >> 6) & 127;
+        const int h = (i >> 13) % NH, kb = (i >> 13) / NH;
         if (!tb) {                       // run along n for coalesced reads of a (K x N) matrix
             n = i & 127; k = (i >> 7) & 63;
         }
         const int gn = h * 128 + n, gk = kb * 64 + k;
         float v = 0.f;
         if (gn < N && gk < K) v = tb ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn];
-        uint8_t* chunk = out + (size_t)((h * KB + kb) * 2) * 16384;
-        split_store(chunk, chunk + 16384, sw128_offset(n, k), v);
+        __nv_bfloat16 parts[3];
+        split_parts<PARTS>(v, parts);
+        uint8_t* chunk = out + (size_t)((kb * NH + h) * PARTS) * 16384 + sw128_offset(n, k);
+#pragma unroll
+        for (int q = 0; q < PARTS; ++q) *reinterpret_cast<__nv_bfloat16*>(chunk + q * 16384) = parts[q];
+    }
+}
+
+// one K-block (columns [col0, col0 + 64)) of rows [row0, row0 + 128) -> PARTS tiles of [128][64] at stage + part * 16 KB.
+// All loads of the block are in flight before the first conversion.
+template <int PARTS>
+__device__ __forceinline__ void convert_block(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_end, int col0,
+                                              int cols_end, uint8_t* stage, int worker) {
+    const int w = worker >> 5, lane = worker & 31;
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((cols_end & 3) == 0);
+    if (vec) {
+        const int c = 4 * (lane & 15), rr = 2 * w + (lane >> 4);          // 16 lanes per row, two rows per warp instruction
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t g = row0 + rr + 16 * i;
+            v[i] = (g < rows_end && col0 + c < cols_end) ? __ldg(reinterpret_cast<const float4*>(src + g * ld + col0 + c))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t off = sw128_offset(rr + 16 * i, c);
+            __nv_bfloat16 a[3], b[3], cc[3], d[3];
+            split_parts<PARTS>(v[i].x, a); split_parts<PARTS>(v[i].y, b); split_parts<PARTS>(v[i].z, cc); split_parts<PARTS>(v[i].w, d);
+#pragma unroll
+            for (int q = 0; q < PARTS; ++q) {
+                uint2 o;
+                o.x = (uint32_t)__bfloat16_as_ushort(a[q]) | ((uint32_t)__bfloat16_as_ushort(b[q]) << 16);
+                o.y = (uint32_t)__bfloat16_as_ushort(cc[q]) | ((uint32_t)__bfloat16_as_ushort(d[q]) << 16);
+                *reinterpret_cast<uint2*>(stage + q * 16384 + off) = o;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[8][2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t g = row0 + w + 8 * (half * 8 + i);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = lane + 32 * j;
+                    v[i][j] = (g < rows_end && col0 + c < cols_end) ? __ldg(src + g * ld + col0 + c) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t off = sw128_offset(w + 8 * (half * 8 + i), lane + 32 * j);
+                    __nv_bfloat16 parts[3];
+                    split_parts<PARTS>(v[i][j], parts);
+#pragma unroll
+                    for (int q = 0; q < PARTS; ++q) *reinterpret_cast<__nv_bfloat16*>(stage + q * 16384 + off) = parts[q];
+                }
+        }
     }
 }
 
@@ -138,127 +214,140 @@ struct RowsParams {
     float beta;
 };
 
-__global__ void __launch_bounds__(GT_THREADS, 1) gemm_rows_kernel(const RowsParams P) {
+template <int PARTS>
+__global__ void __launch_bounds__(GR_THREADS, 1) gemm_rows_kernel(const RowsParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw_addr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = base + GT_SM_BAR, bar_empty = bar_full + 8 * GT_STAGES, bar_ready = bar_empty + 8 * GT_STAGES,
-                   bar_done = bar_ready + 8;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + GT_SM_BAR + 96);
+    constexpr uint32_t A_STAGE = PARTS * 16384;
+    const uint32_t bar_afull = base + GR_SM_BAR, bar_aempty = bar_afull + 8 * GR_A_STAGES, bar_bfull = bar_aempty + 8 * GR_A_STAGES,
+                   bar_bempty = bar_bfull + 8 * GR_B_STAGES, bar_accfull = bar_bempty + 8 * GR_B_STAGES, bar_accfree = bar_accfull + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + GR_SM_BAR + 192);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < GT_STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-        mbar_init(bar_ready, GT_WORKERS);
-        mbar_init(bar_done, 1);
+        for (int i = 0; i < GR_A_STAGES; ++i) { mbar_init(bar_afull + 8 * i, GR_CONV); mbar_init(bar_aempty + 8 * i, 1); }
+        for (int i = 0; i < GR_B_STAGES; ++i) { mbar_init(bar_bfull + 8 * i, 1); mbar_init(bar_bempty + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_accfull + 8 * i, 1); mbar_init(bar_accfree + 8 * i, 128); }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(base + GT_SM_BAR + 96, 256);
+    if (warp == 13) tmem_alloc(base + GR_SM_BAR + 192, 512);           // two 256-column accumulators
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int64_t n_tiles = (P.M + 127) / 128;
     const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-    const int n_chunks = P.NH * P.KB * 2;
 
-    if (warp == 8) {
-        if (lane == 0) {
-            int slot = 0; uint32_t par = 1;
-            for (int it = 0; it < my_tiles; ++it)
-                for (int c = 0; c < n_chunks; ++c) {
-                    mbar_wait(bar_empty + 8 * slot, par, 31);
-                    mbar_arrive_expect_tx(bar_full + 8 * slot, 16384);
-                    bulk_g2s(base + GT_SM_RING + slot * 16384, P.b_chunks + (size_t)c * 16384, 16384, bar_full + 8 * slot);
-                    if (++slot == GT_STAGES) { slot = 0; par ^= 1; }
-                }
-        }
-    } else if (warp == 9) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
-            int slot = 0; uint32_t par = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                mbar_wait(bar_ready, (uint32_t)(it & 1), 32);          // A tile converted; previous accumulator drained
-                tc_fence_after();
-                for (int h = 0; h < P.NH; ++h)
-                    for (int kb = 0; kb < P.KB; ++kb) {
-                        const uint32_t ahi = base + GT_SM_AHI + kb * 16384, alo = base + GT_SM_ALO + kb * 16384;
-                        const uint32_t d = tmem_base + h * 128;
-                        mbar_wait(bar_full + 8 * slot, par, 33);       // B hi
-                        tc_fence_after();
-                        uint32_t b = base + GT_SM_RING + slot * 16384;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_bf16_ss(d, make_sdesc_sw128(ahi + k * 32, 16, 1024), make_sdesc_sw128(b + k * 32, 16, 1024), idesc,
-                                        (kb > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_bf16_ss(d, make_sdesc_sw128(alo + k * 32, 16, 1024), make_sdesc_sw128(b + k * 32, 16, 1024), idesc, 1u);
-                        mma_commit(bar_empty + 8 * slot);
-                        if (++slot == GT_STAGES) { slot = 0; par ^= 1; }
-                        mbar_wait(bar_full + 8 * slot, par, 34);       // B lo
-                        tc_fence_after();
-                        b = base + GT_SM_RING + slot * 16384;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            mma_bf16_ss(d, make_sdesc_sw128(ahi + k * 32, 16, 1024), make_sdesc_sw128(b + k * 32, 16, 1024), idesc, 1u);
-                        mma_commit(bar_empty + 8 * slot);
-                        if (++slot == GT_STAGES) { slot = 0; par ^= 1; }
-                    }
-                mma_commit(bar_done);
+    if (warp < 8) {
+        // ===================== A conversion: one K-block per stage =====================
+        int s = 0; uint32_t par = 1;
+        for (int it = 0; it < my_tiles; ++it) {
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            for (int kb = 0; kb < P.KB; ++kb) {
+                mbar_wait(bar_aempty + 8 * s, par, 31);
+                convert_block<PARTS>(P.A, P.lda, tile * 128, P.M, kb * 64, P.K, smem + GR_SM_A + s * A_STAGE, threadIdx.x);
+                fence_proxy_async_smem();
+                mbar_arrive(bar_afull + 8 * s);
+                if (++s == GR_A_STAGES) { s = 0; par ^= 1; }
             }
         }
-    } else {
-        const int worker = threadIdx.x;
+    } else if (warp < 12) {
+        // ===================== epilogue: accumulator -> C =====================
+        const int q = warp - 8;                                        // TMEM lane quarter (warp % 4)
         const bool vec = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
         for (int it = 0; it < my_tiles; ++it) {
             const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
-            // the MMAs of the previous tile have finished reading the A tile (every worker waited for bar_done below)
-            convert_tile(P.A, P.lda, tile * 128, P.M, 0, P.K, P.KB, smem + GT_SM_AHI, smem + GT_SM_ALO, worker);
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_ready);
-            mbar_wait(bar_done, (uint32_t)(it & 1), 35);
+            const int buf = it & 1;
+            mbar_wait(bar_accfull + 8 * buf, (uint32_t)((it >> 1) & 1), 32);
             tc_fence_after();
-            if (warp < 4) {
-                const int64_t row = tile * 128 + 32 * warp + lane;
-                for (int cg = 0; cg < P.NH * 4; ++cg) {
-                    if (cg * 32 >= P.N) break;
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + (uint32_t(32 * warp) << 16) + cg * 32, v);
-                    tmem_ld_wait();
-                    if (row < P.M) {
-                        float* dst = P.C + row * P.ldc + cg * 32;
-                        if (vec && cg * 32 + 32 <= P.N) {
+            const int64_t row = tile * 128 + 32 * q + lane;
+            for (int cg = 0; cg < P.NH * 4; ++cg) {
+                if (cg * 32 >= P.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (uint32_t(32 * q) << 16) + buf * 256 + cg * 32, v);
+                tmem_ld_wait();
+                if (row < P.M) {
+                    float* dst = P.C + row * P.ldc + cg * 32;
+                    if (vec && cg * 32 + 32 <= P.N) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                                if (P.beta != 0.f) {
-                                    const float4 c = *reinterpret_cast<const float4*>(dst + 4 * q);
-                                    o.x = fmaf(P.beta, c.x, o.x); o.y = fmaf(P.beta, c.y, o.y);
-                                    o.z = fmaf(P.beta, c.z, o.z); o.w = fmaf(P.beta, c.w, o.w);
-                                }
-                                *reinterpret_cast<float4*>(dst + 4 * q) = o;
+                        for (int e = 0; e < 8; ++e) {
+                            float4 o = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
+                                                   __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+                            if (P.beta != 0.f) {
+                                const float4 c = *reinterpret_cast<const float4*>(dst + 4 * e);
+                                o.x = fmaf(P.beta, c.x, o.x); o.y = fmaf(P.beta, c.y, o.y);
+                                o.z = fmaf(P.beta, c.z, o.z); o.w = fmaf(P.beta, c.w, o.w);
                             }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (cg * 32 + q < P.N) {
-                                    float o = __uint_as_float(v[q]);
-                                    if (P.beta != 0.f) o = fmaf(P.beta, dst[q], o);
-                                    dst[q] = o;
-                                }
+                            *reinterpret_cast<float4*>(dst + 4 * e) = o;
                         }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (cg * 32 + e < P.N) {
+                                float o = __uint_as_float(v[e]);
+                                if (P.beta != 0.f) o = fmaf(P.beta, dst[e], o);
+                                dst[e] = o;
+                            }
                     }
                 }
-                tc_fence_before();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_accfree + 8 * buf);
+        }
+    } else if (warp == 12) {
+        // ===================== B producer =====================
+        if (lane == 0) {
+            const int n_chunks = P.KB * P.NH * PARTS;
+            int slot = 0; uint32_t par = 1;
+            for (int it = 0; it < my_tiles; ++it)
+                for (int c = 0; c < n_chunks; ++c) {
+                    mbar_wait(bar_bempty + 8 * slot, par, 33);
+                    mbar_arrive_expect_tx(bar_bfull + 8 * slot, 16384);
+                    bulk_g2s(base + GR_SM_B + slot * 16384, P.b_chunks + (size_t)c * 16384, 16384, bar_bfull + 8 * slot);
+                    if (++slot == GR_B_STAGES) { slot = 0; par ^= 1; }
+                }
+        }
+    } else {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+            int as = 0, bslot = 0; uint32_t apar = 0, bpar = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int buf = it & 1;
+                mbar_wait(bar_accfree + 8 * buf, (uint32_t)(((it >> 1) & 1) ^ 1), 34);    // epilogue of tile it - 2 has drained it
+                tc_fence_after();
+                for (int kb = 0; kb < P.KB; ++kb) {
+                    mbar_wait(bar_afull + 8 * as, apar, 35);
+                    tc_fence_after();
+                    const uint32_t a0 = base + GR_SM_A + as * A_STAGE;
+                    for (int h = 0; h < P.NH; ++h) {
+                        const uint32_t d = tmem_base + buf * 256 + h * 128;
+#pragma unroll
+                        for (int j = 0; j < PARTS; ++j) {                 // part j of B against parts 0 .. PARTS-1-j of A
+                            mbar_wait(bar_bfull + 8 * bslot, bpar, 36);
+                            tc_fence_after();
+                            const uint32_t b0 = base + GR_SM_B + bslot * 16384;
+#pragma unroll
+                            for (int i = 0; i < PARTS - j; ++i)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    mma_bf16_ss(d, make_sdesc_sw128(a0 + i * 16384 + k * 32, 16, 1024),
+                                                make_sdesc_sw128(b0 + k * 32, 16, 1024), idesc, (kb > 0 || j > 0 || i > 0 || k > 0) ? 1u : 0u);
+                            mma_commit(bar_bempty + 8 * bslot);
+                            if (++bslot == GR_B_STAGES) { bslot = 0; bpar ^= 1; }
+                        }
+                    }
+                    mma_commit(bar_aempty + 8 * as);
+                    if (++as == GR_A_STAGES) { as = 0; apar ^= 1; }
+                }
+                mma_commit(bar_accfull + 8 * buf);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 256);
+    if (warp == 13) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,7 +512,7 @@ __global__ void __launch_bounds__(256) small_tn_kernel(const float* __restrict__
 }
 
 uint8_t* g_b_scratch = nullptr;      // split B chunks of the GEMM in flight (one stream at a time: the BN path is serial)
-constexpr size_t B_SCRATCH_BYTES = 2 * GT_KB * 2 * 16384;
+constexpr size_t B_SCRATCH_BYTES = 2 * 4 * 3 * 16384;      // N halves x K-blocks x parts
 bool g_attr_set = false;
 
 }  // namespace
@@ -432,11 +521,13 @@ namespace nerf {
 
 // row-major C (M x N) = op(A) op(B) + beta C, fp32 in and out.  ta: A is stored (K x M) and the contraction runs over
 // its rows (the sample dimension; beta must be 1: the result is ADDED to C); tb: B is stored (N x K).
+// precise: three-way operand split (fp32-grade; row GEMMs only) instead of two-way (~1e-5 of the products' scale).
 int tc_gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
-                int64_t ldb, float beta, float* C, int64_t ldc) {
+                int64_t ldb, float beta, float* C, int64_t ldc, bool precise) {
     if (M <= 0 || N <= 0 || K <= 0) return NERF_OK;
     if (!g_attr_set) {
-        NERF_CUDA(cudaFuncSetAttribute(gemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+        NERF_CUDA(cudaFuncSetAttribute(gemm_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM));
+        NERF_CUDA(cudaFuncSetAttribute(gemm_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM));
         NERF_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM));
         NERF_CUDA(cudaMalloc((void**)&g_b_scratch, B_SCRATCH_BYTES));
         g_attr_set = true;
@@ -471,13 +562,20 @@ int tc_gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, cons
         NERF_LAUNCHED();
         return NERF_OK;
     }
-    if (N > 256 || K > 64 * GT_KB) return fail(NERF_ERR_INVALID, "tc_gemm_f32: N and K are limited to 256");
+    if (N > 256 || K > 256) return fail(NERF_ERR_INVALID, "tc_gemm_f32: N and K are limited to 256");
     const int NH = (N + 127) / 128, KB = (K + 63) / 64;
-    pack_b_split_kernel<<<NH * KB * 4, 256, 0, st>>>(B, ldb, tb ? 1 : 0, N, K, NH, KB, g_b_scratch);
-    NERF_LAUNCHED();
     RowsParams P = {A, lda, g_b_scratch, C, ldc, M, N, K, NH, KB, beta};
     const int64_t tiles = ceil_div(M, 128);
-    gemm_rows_kernel<<<(int)(tiles < num_sms() ? tiles : num_sms()), GT_THREADS, GT_SMEM, st>>>(P);
+    const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+    if (precise) {
+        pack_b_split_kernel<3><<<NH * KB * 4, 256, 0, st>>>(B, ldb, tb ? 1 : 0, N, K, NH, KB, g_b_scratch);
+        NERF_LAUNCHED();
+        gemm_rows_kernel<3><<<grid, GR_THREADS, GR_SMEM, st>>>(P);
+    } else {
+        pack_b_split_kernel<2><<<NH * KB * 4, 256, 0, st>>>(B, ldb, tb ? 1 : 0, N, K, NH, KB, g_b_scratch);
+        NERF_LAUNCHED();
+        gemm_rows_kernel<2><<<grid, GR_THREADS, GR_SMEM, st>>>(P);
+    }
     NERF_LAUNCHED();
     return NERF_OK;
 }
@@ -486,7 +584,7 @@ int tc_gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, cons
 
 // test hook (nerf_b200_debug.h): the GEMM above on caller buffers
 extern "C" int nerf_selftest_gemm_f32(int ta, int tb, int64_t M, int N, int K, const float* A, int64_t lda, const float* B,
-                                      int64_t ldb, float beta, float* C, int64_t ldc, void* stream) {
+                                      int64_t ldb, float beta, float* C, int64_t ldc, int precise, void* stream) {
     NERF_CHECK_ARG(A && B && C, "null pointer");
-    return nerf::tc_gemm_f32((cudaStream_t)stream, ta != 0, tb != 0, M, N, K, A, lda, B, ldb, beta, C, ldc);
+    return nerf::tc_gemm_f32((cudaStream_t)stream, ta != 0, tb != 0, M, N, K, A, lda, B, ldb, beta, C, ldc, precise != 0);
 }

@@ -86,10 +86,11 @@ def test_bn_forward_backward_matches_oracle_autograd(nk):
     got = grads.cpu().numpy()
     cos = float(np.dot(ref, got) / (np.linalg.norm(ref) * np.linalg.norm(got)))
     print('BN gradient vs oracle: cosine', cos, 'norm ratio', np.linalg.norm(got) / np.linalg.norm(ref))
-    assert cos >= 0.998 and abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1) <= 5e-3, cos
-    # Differences are single ReLU decisions: the split-bf16 tensor-core GEMMs (gemm_tc.cu) reproduce a pre-activation to
-    # ~1e-5 of its scale (the CPU BLAS of the oracle to ~1e-6 of another summation order), and among 3.3 M (sample, unit)
-    # entries per net a few dozen sit that close to the threshold (overall cosine 0.9991; it was 0.9999 with fp32 FMAs).  One flipped entry changes ONE column of that layer's dW by a few per cent (observed: unit 218 of d6 off by
+    assert cos >= 0.9995 and abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1) <= 3e-3, cos
+    # Differences are single ReLU decisions: the forward GEMMs (gemm_tc.cu, three-way split bf16 operands on the tensor
+    # cores) reproduce a pre-activation to ~1e-6 of its scale, the CPU BLAS of the oracle sums in another order, and among
+    # 3.3 M (sample, unit) entries per net a handful sit that close to the threshold (overall cosine 0.9998; 0.9992 with a
+    # two-way split, 0.9999 with fp32 FMAs).  One flipped entry changes ONE column of that layer's dW by a few per cent (observed: unit 218 of d6 off by
     # 2.2 %, every other column exact) and shows up as ~0.1-1 % noise in every layer below; the heads and the layers above the
     # first flip agree to 1e-5.  Hence: tight overall direction and norm, per-tensor relative L2 loose enough for a few flips.
     off, worst = 0, []
@@ -115,7 +116,7 @@ def test_bn_forward_backward_matches_oracle_autograd(nk):
         mine = bng.cpu().numpy()[net * 2 * nbn:(net + 1) * 2 * nbn]
         scale = max(np.abs(gam).max(), np.abs(bet).max())
         print('BN gamma / beta gradient rel. L2 error', np.linalg.norm(mine[:nbn] - gam) / np.linalg.norm(gam), np.linalg.norm(mine[nbn:] - bet) / np.linalg.norm(bet))
-        assert np.linalg.norm(mine[:nbn] - gam) <= 6e-2 * np.linalg.norm(gam) and np.linalg.norm(mine[nbn:] - bet) <= 6e-2 * np.linalg.norm(bet)
+        assert np.linalg.norm(mine[:nbn] - gam) <= 3e-2 * np.linalg.norm(gam) and np.linalg.norm(mine[nbn:] - bet) <= 3e-2 * np.linalg.norm(bet)
         assert np.abs(mine[:nbn] - gam).max() <= 0.2 * scale and np.abs(mine[nbn:] - bet).max() <= 0.2 * scale
     # moving statistics (momentum 0.99) updated in place like Keras does in training mode
     after = bn.cpu().numpy()

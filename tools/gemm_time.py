@@ -19,13 +19,16 @@ for name, ta, tb, N, K in (("rows  NN 256x256", 0, 0, 256, 256), ("rows  NT 256x
                            ("head  NN 1x256  ", 0, 0, 1, 256), ("head  TN 256x1  ", 1, 0, 1, 256)):
     if ta:
         A = torch.randn(M, K, device="cuda"); B = torch.randn(M, N, device="cuda"); Cc = torch.zeros(K, N, device="cuda")
-        ours = timeit(lambda: L.nerf_selftest_gemm_f32(1, 0, K, N, M, _ptr(A), K, _ptr(B), N, 1.0, _ptr(Cc), N, _stream()))
+        ours = timeit(lambda: L.nerf_selftest_gemm_f32(1, 0, K, N, M, _ptr(A), K, _ptr(B), N, 1.0, _ptr(Cc), N, 0, _stream()))
+        ours3 = None
         ref = timeit(lambda: torch.addmm(Cc, A.t(), B))
         flop = 2.0 * M * N * K
     else:
         A = torch.randn(M, K, device="cuda"); B = torch.randn((N, K) if tb else (K, N), device="cuda"); Cc = torch.empty(M, N, device="cuda")
-        ours = timeit(lambda: L.nerf_selftest_gemm_f32(0, tb, M, N, K, _ptr(A), K, _ptr(B), B.shape[1], 0.0, _ptr(Cc), N, _stream()))
+        ours = timeit(lambda: L.nerf_selftest_gemm_f32(0, tb, M, N, K, _ptr(A), K, _ptr(B), B.shape[1], 0.0, _ptr(Cc), N, 0, _stream()))
+        ours3 = timeit(lambda: L.nerf_selftest_gemm_f32(0, tb, M, N, K, _ptr(A), K, _ptr(B), B.shape[1], 0.0, _ptr(Cc), N, 1, _stream()))
         ref = timeit(lambda: torch.matmul(A, B.t() if tb else B, out=Cc))
         flop = 2.0 * M * N * K
     byts = 4.0 * (A.numel() + (B.numel() if ta else Cc.numel()))
-    print(f"{name} M={M}: tcgen05 split-bf16 {ours:.3f} ms ({flop / ours / 1e9:.1f} TFLOP/s fp32-equivalent, {byts / ours / 1e6:.0f} GB/s)   sgemm {ref:.3f} ms")
+    three = f", three-way split {ours3:.3f} ms" if ours3 is not None else ""
+    print(f"{name} M={M}: tcgen05 split-bf16 {ours:.3f} ms ({flop / ours / 1e9:.1f} TFLOP/s fp32-equivalent, {byts / ours / 1e6:.0f} GB/s){three}   sgemm {ref:.3f} ms")
