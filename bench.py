@@ -641,7 +641,7 @@ def main():
                                  "launches": kernel_n["mlp_fwd"], "share_of_step": kernel_ms["mlp_fwd"] / (eager_ms / steps)}
     if train and "wgrad" in kernel_ms:
         tiles = -(-B * Nc // 128) + (-(-B * (Nc + Nf) // 128) if Nf else 0)
-        wg_bytes = tiles * (655360 + 638976)
+        wg_bytes = tiles * (638976 + 638976)     # every saved activation image + every dZ image of a tile, once
         gbs = wg_bytes / (kernel_ms["wgrad"] * 1e-3) / 1e9
         wg_flop = samples_per_step * FLOP_PER_SAMPLE_FWD        # dW = X^T dZ: the forward's MACs once more
         cands["roofline_wgrad"] = {"bound": "hbm", "kernel": "nerf_wgrad_tc_kernel", "unit": "GB/s", "peak": peaks["hbm"],

@@ -147,7 +147,7 @@ extern "C" int nerf_destroy(nerf_ctx* ctx) {
     cudaFree(ctx->fw_t_all); cudaFree(ctx->fw_src_idx); cudaFree(ctx->fw_rgb_c); cudaFree(ctx->fw_rgb_f);
     cudaFree(ctx->fw_dirbias[0]); cudaFree(ctx->fw_dirbias[1]); cudaFree(ctx->dev_state); cudaFree(ctx->metric_sums);
     cudaFree(ctx->tr_dpred_c); cudaFree(ctx->tr_dpred_f); cudaFree(ctx->tr_drgb_c); cudaFree(ctx->tr_drgb_f);
-    cudaFree(ctx->tr_ddirbias); cudaFree(ctx->tr_ddelta_f); cudaFree(ctx->tr_dtp_f); cudaFree(ctx->tr_dw_extra);
+    cudaFree(ctx->tr_ddirsum[0]); cudaFree(ctx->tr_ddirsum[1]); cudaFree(ctx->tr_ddelta_f); cudaFree(ctx->tr_dtp_f); cudaFree(ctx->tr_dw_extra);
     cudaFree(ctx->w_ig); cudaFree(ctx->far_t); cudaFree(ctx->far_pred);
     for (int n = 0; n < 2; ++n) {
         cudaFree(ctx->act_save[n]); cudaFree(ctx->dz_save[n]); cudaFree(ctx->mask_save[n]); cudaFree(ctx->chain_progress[n]);
@@ -356,7 +356,6 @@ extern "C" int nerf_train_phases(nerf_ctx* ctx, const float* images, const float
                                          ctx->tr_drgb_c, single ? nullptr : ctx->tr_drgb_f, ctx->metric_sums, st)))
             return rc;
         if (!(phases & 4)) NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * np * 4, st));
-        if ((rc = tc_dir_images(ctx, d, batch, Nc, single ? 0 : Na, st))) return rc;
         if (!single) {
             // fine net first: its input gradient feeds the coarse net through sort + sample_pdf (models.py:165-175)
             float* gf = ctx->grads + np;

@@ -68,7 +68,7 @@ struct nerf_ctx {
     __nv_bfloat16* dz_save[2] = {nullptr, nullptr};
     uint32_t* mask_save[2] = {nullptr, nullptr};
     float *tr_dpred_c = nullptr, *tr_dpred_f = nullptr, *tr_drgb_c = nullptr, *tr_drgb_f = nullptr;
-    float* tr_ddirbias = nullptr;
+    float* tr_ddirsum[2] = {nullptr, nullptr};     // (max_rays, 128) per net: per-ray sums of dZ of the ddir layer (chain kernel)
     // un-stopped gradient through the fine sample positions (stop_grad_samples = 0)
     __nv_bfloat16* w_ig = nullptr;                 // W0^T / W5b^T operand image of the input-gradient kernel
     float *tr_ddelta_f = nullptr, *tr_dtp_f = nullptr, *tr_dw_extra = nullptr;
@@ -98,7 +98,6 @@ int tc_pack_weights(nerf_ctx* ctx, int net, cudaStream_t st);
 int tc_pack_all(nerf_ctx* ctx, bool tick_step, cudaStream_t st);     // forward images of both nets (+ step counter tick)
 int tc_pack_backward(nerf_ctx* ctx, cudaStream_t st);                // transposed images of both nets + input-gradient image
 int tc_dirbias(nerf_ctx* ctx, const float* d, int64_t B, int nets_mask, cudaStream_t st);
-int tc_dir_images(nerf_ctx* ctx, const float* d, int64_t B, int nc, int na, cudaStream_t st);
 bool stream_is_capturing(cudaStream_t st);
 int tc_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N, float* dtp,
                   cudaStream_t st);

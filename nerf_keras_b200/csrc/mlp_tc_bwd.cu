@@ -12,10 +12,11 @@
 //     tile is consumed as an MN-major operand (features along M/N, samples along K) without any
 //     transpose.  Accumulators stay in TMEM for a CTA's whole slab of samples; bias gradients (column
 //     sums of dZ) and the tiny sigma / rgb head gradients are CUDA-core side jobs on the same tiles.
-//     The sigma / rgb heads and the direction rows of Wddir are three more jobs of the same kernel: the
-//     chain kernel emits a [d rgb, d sigma] "head" dZ image, and
-//  3. dir_image_kernel writes the per-sample direction-encoding images (the forward kernel hoists that
-//     product into a per-ray bias, so the operand has to be materialised for the backward).
+//     The rgb head is one more job of the same kernel (the chain kernel emits a [d rgb, d sigma] "head" dZ image),
+//     the sigma head a side job of the feature layer's job.
+//  3. dirw_grad_kernel -- the direction rows of dW_ddir.  The forward kernel hoists that product into a per-ray bias;
+//     its backward is enc_d(ray)^T times the per-ray sums of dZ_ddir, which the chain kernel takes while the tile is
+//     in shared memory.
 #include "common.cuh"
 #include "ctx.cuh"
 #include "mlp_tc_common.cuh"
@@ -93,12 +94,17 @@ struct BwdParams {
     const uint32_t* mask_save;
     uint8_t* dz_save;
     uint32_t* progress;     // per tile: number of dZ images whose bulk stores are complete (null: nobody is listening)
+    int N;                  // samples per ray
+    float* ddir_sum;        // (rays, 128): per-ray column sums of dZ of the ddir layer, accumulated here (zeroed by the caller)
 };
 
 // The weight-gradient kernel may run NEXT TO this kernel on other SMs and consume a tile's dZ images while they are
 // still in L2.  The thread that issues a sub-tile's bulk stores publishes how many images of the tile are complete:
 // 1 = [ddir + head], 2 = feature, 3 .. 10 = Z7 .. Z0.  cp.async.bulk.wait_group N (not .read) returns once all but the N
 // most recent groups have been written; the counter is then released at gpu scope.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void publish_progress(uint32_t* p, uint32_t v) {
@@ -267,6 +273,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
             }
             mbar_arrive(bar_lo);
             mbar_arrive(bar_hi);
+            if (P.ddir_sum) {
+                // Direction rows of dW_ddir (models.py:48-54): the direction encoding is constant along a ray, so
+                //   sum_samples enc_d[k] dZ[sample][j] = sum_rays enc_d(ray)[k] (sum of the ray's dZ rows)[j].
+                // Thread <-> column j of the 128-wide dZ_ddir tile just written (bf16, as the GEMMs see it): per-ray sums go
+                // to ddir_sum, dirw_grad_kernel finishes the product.  Runs under the first MMA phase; K-blocks 0,1 are not
+                // overwritten before the barrier in front of store_held.  (This replaced a per-sample direction image,
+                // 16 KB per tile written by a kernel of its own and read back by a weight-gradient job.)
+                // Thread <-> (8-column group cg, 16-row block rb): sixteen 16-byte loads, eight independent sums, flushed
+                // with vector reductions at ray boundaries; four rows in flight at a time (register pressure).  A/B on one box:
+                // +0.013 ms on the chain kernels of a step, -0.05 ms on the weight gradient, -0.03 ms of image kernel.
+                const int cg = row & 15, rb = row >> 4;
+                const uint32_t blk = act_base + (cg >> 3) * (TILE_M * 128);
+                int64_t g = tile * TILE_M + rb * 16;
+                int64_t ray = g / P.N;
+                int rem = (int)(g - ray * P.N), cnt = 0;
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                auto flush = [&]() {
+                    float* dstp = P.ddir_sum + ray * 128 + cg * 8;
+                    red_add_v4(dstp, acc[0], acc[1], acc[2], acc[3]);
+                    red_add_v4(dstp + 4, acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                };
+#pragma unroll 1
+                for (int q4 = 0; q4 < 4; ++q4) {                      // four rows at a time: 16 registers of loads in flight
+                    uint4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rb * 16 + q4 * 4 + i;
+                        const uint32_t addr = blk + (r >> 3) * 1024 + (r & 7) * 128 + ((uint32_t)((cg & 7) ^ (r & 7)) << 4);
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w) : "r"(addr));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i, ++g) {
+                        if (g < P.M) {
+                            acc[0] += __uint_as_float(v[i].x << 16); acc[1] += __uint_as_float(v[i].x & 0xFFFF0000u);
+                            acc[2] += __uint_as_float(v[i].y << 16); acc[3] += __uint_as_float(v[i].y & 0xFFFF0000u);
+                            acc[4] += __uint_as_float(v[i].z << 16); acc[5] += __uint_as_float(v[i].z & 0xFFFF0000u);
+                            acc[6] += __uint_as_float(v[i].w << 16); acc[7] += __uint_as_float(v[i].w & 0xFFFF0000u);
+                            ++cnt;
+                            if (++rem == P.N) { flush(); rem = 0; cnt = 0; ++ray; }
+                        }
+                    }
+                }
+                if (cnt > 0) flush();
+            }
 
             for (int ph = 0; ph < B_PHASES; ++ph) {
                 int64_t dst;
@@ -349,7 +401,7 @@ constexpr int WG_SM_A = 0;
 constexpr int WG_SM_B = WG_A_STAGES * WG_A_SLOT;
 constexpr int WG_SM_BAR = WG_SM_B + WG_B_RING;
 constexpr int WG_SMEM = WG_SM_BAR + 256 + 1024;
-constexpr int WG_NJOBS = 13;
+constexpr int WG_NJOBS = 12;
 
 struct WgJob {
     int64_t a_off;       // byte offset of the X image inside a saved-activation tile
@@ -378,9 +430,6 @@ struct WgParams {
     float* grads;           // this net's gradient blob
 };
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -655,44 +704,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3. per-sample direction-encoding images for the direction rows of Wddir (models.py:48-54): the forward
-// kernel hoists that product into a per-ray bias, the backward wants it as a GEMM operand again.
-// One warp per ray writes the ray's N rows ([27 values | zeros], 128 bytes each) into the tiles' images.
+// 3. direction rows of dW_ddir (rows 256..282, models.py:48-54) from the per-ray sums of dZ_ddir the chain kernel took:
+//    dW[256 + k][j] += sum_rays enc_d(ray)[k] * S[ray][j].  The forward hoists this product into a per-ray bias
+//    (dirbias_kernel); this is its backward.  Thread <-> column j, 27 accumulators, one atomic per (k, j) and block.
 // ------------------------------------------------------------------------------------------------
-struct DirImageArgs {
-    int N[2];
-    uint8_t* act_save[2];
-};
-__global__ void __launch_bounds__(128) dir_image_kernel(const float* __restrict__ d, int64_t rays, const DirImageArgs A) {
-    const int N = A.N[blockIdx.y];
-    uint8_t* __restrict__ act_save = A.act_save[blockIdx.y];
-    const int lane = threadIdx.x & 31;
-    const int64_t warps_total = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ray < rays; ray += warps_total) {
-        // lane <-> channel pair (2 lane, 2 lane + 1) of the 64-wide row
-        float v[2];
+__global__ void __launch_bounds__(128) dirw_grad_kernel(const float* __restrict__ d, int64_t rays, const float* __restrict__ S,
+                                                        float* __restrict__ g_wdir /* (27, 128) */) {
+    __shared__ float enc[32];
+    const int j = threadIdx.x;
+    float acc[ENC_D];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int c = 2 * lane + q;
-            float x = 0.f;
-            if (c < 3) x = d[ray * 3 + c];
-            else if (c < ENC_D) {
-                int qq = c - 3, oct = qq / 6, r6 = qq - oct * 6, comp = r6 % 3;
-                float arg = __fmul_rn(exp2f((float)oct), d[ray * 3 + comp]);
-                x = (r6 >= 3) ? cosf(arg) : sinf(arg);
+    for (int k = 0; k < ENC_D; ++k) acc[k] = 0.f;
+    for (int64_t ray = blockIdx.x; ray < rays; ray += gridDim.x) {
+        if (j < ENC_D) {
+            float v;
+            if (j < 3) v = d[ray * 3 + j];
+            else {
+                const int q = j - 3, i = q / 6, r = q - i * 6, comp = r % 3;
+                const float arg = __fmul_rn(exp2f((float)i), d[ray * 3 + comp]);
+                v = (r >= 3) ? cosf(arg) : sinf(arg);
             }
-            v[q] = x;
+            enc[j] = v;
         }
-        const uint32_t w = pack_bf16x2(v[0], v[1]);
-        for (int n = 0; n < N; ++n) {
-            const int64_t m = ray * N + n;
-            const int64_t tile = m >> 7;
-            const int r = (int)(m & 127);
-            uint8_t* p = act_save + tile * SAVE_TILE_BYTES + SAVE_DIR + (r >> 3) * 1024 + (r & 7) * 128 +
-                         ((((lane >> 2) ^ (r & 7))) << 4) + (lane & 3) * 4;
-            *reinterpret_cast<uint32_t*>(p) = w;
-        }
+        __syncthreads();
+        const float sv = S[ray * 128 + j];
+#pragma unroll
+        for (int k = 0; k < ENC_D; ++k) acc[k] = fmaf(enc[k], sv, acc[k]);
+        __syncthreads();
     }
+#pragma unroll
+    for (int k = 0; k < ENC_D; ++k) atomicAdd(g_wdir + k * (H / 2) + j, acc[k]);
 }
 
 // bias gradients of the two heads: b_rgb = sum d rgb_raw, b_sigma = sum d sigma_raw  (float4 grid-stride reduce)
@@ -988,6 +1029,7 @@ int tc_train_alloc(nerf_ctx* ctx) {
         NERF_CUDA(cudaMalloc((void**)&ctx->mask_save[net], (size_t)(tiles[net] * MASK_TILE_BYTES)));
         NERF_CUDA(cudaMalloc((void**)&ctx->w_bwd[net], (size_t)B_CHUNKS * CHUNK_BYTES));
         NERF_CUDA(cudaMalloc((void**)&ctx->chain_progress[net], (size_t)tiles[net] * 4));
+        NERF_CUDA(cudaMalloc((void**)&ctx->tr_ddirsum[net], (size_t)c.max_rays * (H / 2) * 4));
         ctx->progress_tiles[net] = tiles[net];
     }
     NERF_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
@@ -1020,20 +1062,8 @@ int tc_pack_backward(nerf_ctx* ctx, cudaStream_t st) {
     return NERF_OK;
 }
 
-// direction-encoding operand images of both nets (rows of Wddir below the feature part), one launch
-int tc_dir_images(nerf_ctx* ctx, const float* d, int64_t B, int nc, int na, cudaStream_t st) {
-    DirImageArgs A = {};
-    A.N[0] = nc; A.act_save[0] = reinterpret_cast<uint8_t*>(ctx->act_save[0]);
-    A.N[1] = na; A.act_save[1] = reinterpret_cast<uint8_t*>(ctx->act_save[1]);
-    const int nets = (na > 0) ? 2 : 1;
-    dir_image_kernel<<<dim3(stream_grid(B * 32, 128, 4), nets), 128, 0, st>>>(d, B, A);
-    NERF_LAUNCHED();
-    return NERF_OK;
-}
-
 // gradients of one net given dL/dpreds; the forward must have run with save_acts on the same batch.
-// flags bit 0: the head bias gradients were already accumulated by volume_render_bwd; bit 1: the direction images of
-// this net are already in place (tc_dir_images)
+// flags bit 0: the head bias gradients were already accumulated by volume_render_bwd (bit 1: unused)
 int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
                 const float* d_preds, cudaStream_t st, int flags) {
     (void)o; (void)t;
@@ -1058,6 +1088,9 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     P.side = ctx->side[net];
     P.mask_save = ctx->mask_save[net];
     P.dz_save = reinterpret_cast<uint8_t*>(ctx->dz_save[net]);
+    P.N = N;
+    P.ddir_sum = ctx->tr_ddirsum[net];
+    NERF_CUDA(cudaMemsetAsync(ctx->tr_ddirsum[net], 0, (size_t)B * (H / 2) * 4, st));
     // Overlap: with at least one full wave of tile pairs the chain gives up `wg_ctas` SMs to the weight-gradient kernel,
     // which follows it tile by tile (see publish_progress / wait_progress).  Both kernels need a whole SM per CTA
     // (shared memory), so chain CTAs + weight-gradient CTAs <= SMs keeps every CTA resident: the chain never waits for
@@ -1080,6 +1113,9 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     timing_begin(1, st);
     nerf_mlp_bwd_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(P);
     timing_end(1, st);
+    NERF_LAUNCHED();
+    // direction rows of dW_ddir from the per-ray sums the chain just took
+    dirw_grad_kernel<<<num_sms(), 128, 0, st>>>(d, B, ctx->tr_ddirsum[net], grads + off.w[10] + (int64_t)H * (H / 2));
     NERF_LAUNCHED();
 
     WgParams W;
@@ -1110,17 +1146,9 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     job(10, SAVE_FEAT, 4, DZ_DDIR, 2, off.w[10], H / 2, H, 0, H / 2, off.b[10]);
     // rgb head: hd^T [d rgb, ..] -> columns 0..2 are dW_rgb (128,3)
     job(11, SAVE_HD, 2, DZ_HEAD, 1, off.w[11], 3, H / 2, 0, 3, -1);
-    // direction rows of Wddir: dirimg^T dZ_ddir -> rows 256..282 of dW_ddir
-    job(12, SAVE_DIR, 1, DZ_DDIR, 2, off.w[10] + (int64_t)H * (H / 2), H / 2, ENC_D, 0, H / 2, -1);
     if (!(flags & 1)) {
         head_bias_kernel<<<num_sms(), 256, 0, st>>>(reinterpret_cast<const float4*>(d_preds), M, grads + off.b[11],
                                                     grads + off.b[8]);
-        NERF_LAUNCHED();
-    }
-    if (!(flags & 2)) {
-        DirImageArgs A = {};
-        A.N[0] = N; A.act_save[0] = reinterpret_cast<uint8_t*>(ctx->act_save[net]);
-        dir_image_kernel<<<dim3(stream_grid(B * 32, 128), 1), 128, 0, st>>>(d, B, A);
         NERF_LAUNCHED();
     }
     W.cta_first[0] = 0;
@@ -1136,7 +1164,7 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
         // a budget of SMs next to the chain: shares in proportion to a job's time per tile = bytes streamed (units of
         // 16 KB at the ~60 GB/s one CTA sustains) + ~0.5 us of fixed cost per tile (2 units; measured on the rgb-head job,
         // tools/r2_wg_stats.py: with a share by bytes alone its two CTAs finished 1 ms after everybody else)
-        static const int units[WG_NJOBS] = {8, 10, 10, 10, 10, 10, 8, 10, 10, 10, 8, 5, 6};
+        static const int units[WG_NJOBS] = {8, 10, 10, 10, 10, 10, 8, 10, 10, 10, 8, 5};
         int cnt[WG_NJOBS];
         for (int j = 0; j < WG_NJOBS; ++j) cnt[j] = 1;
         for (int sum = WG_NJOBS; sum < wg_ctas; ++sum) {       // next CTA to the job with the most bytes per CTA

@@ -72,8 +72,7 @@ constexpr int64_t SAVE_ENC = 0;                         // [128 x 64] bf16(enc),
 constexpr int64_t SAVE_H = 16384;                       // + 65536 * i : output of trunk layer i (0..7)
 constexpr int64_t SAVE_FEAT = 16384 + 8 * 65536;        // feature (linear) output
 constexpr int64_t SAVE_HD = SAVE_FEAT + 65536;          // ddir output, 128 wide (32 KB)
-constexpr int64_t SAVE_DIR = SAVE_HD + 32768;           // [128 x 64] bf16 direction encoding (27 used), backward only
-constexpr int64_t SAVE_TILE_BYTES = SAVE_DIR + 16384;   // 655360
+constexpr int64_t SAVE_TILE_BYTES = SAVE_HD + 32768;    // 638976
 // ReLU sign masks per tile: [9 layers][128 rows][8 x u32]  (layer 8 = ddir, 4 words used)
 constexpr int64_t MASK_TILE_BYTES = 9 * 128 * 32;       // 36864
 // gradient (dZ) images per tile, written by the backward chain kernel
