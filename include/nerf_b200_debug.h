@@ -21,6 +21,9 @@ int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, const float* d,
  * d_w (B,nc) from dL/dt_all given as a direct part dtp (B,Na) and/or dL/d(delta) of the fine compositing. */
 int nerf_debug_input_grad(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t batch,
                           int num_samples, float* dtp, void* stream);
+/* The same quantity as left behind by the fused path of the weight-gradient kernel (what the training step uses)
+ * during the last nerf_debug_mlp_grads(NERF_NET_FINE, ...): device-to-device copy of batch * num_samples floats. */
+int nerf_debug_fused_input_grad(nerf_ctx* ctx, int64_t batch, int num_samples, float* dtp, void* stream);
 int nerf_sample_pdf_bwd(const float* t, const float* weights, const float* u, const int32_t* src_idx,
                         const float* dtp, const float* d_delta, int64_t batch, int nc, int nf, float* d_w, void* stream);
 /* Test hook: out (batch, nf) = the uniforms the in-kernel generator gives sample_pdf for (seed, counter); a training step

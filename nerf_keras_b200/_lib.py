@@ -67,6 +67,7 @@ SIGNATURES = {
     "nerf_debug_mlp_grads": (_I, [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P]),
     "nerf_selftest_mma_rate": (_I, [_I, _I, _I, _P, _P]),
     "nerf_debug_input_grad": (_I, [_P, _I, _P, _P, _P, _L, _I, _P, _P]),
+    "nerf_debug_fused_input_grad": (_I, [_P, _L, _I, _P, _P]),
     "nerf_sample_pdf_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _I, _P, _P]),
     "nerf_debug_pdf_draws": (_I, [C.c_uint64, C.c_uint64, _L, _I, _P, _P]),
     "nerf_debug_flags": (_I, [_I]),

@@ -363,13 +363,13 @@ extern "C" int nerf_train_phases(nerf_ctx* ctx, const float* images, const float
                                                    ctx->tr_dpred_f, q5 ? ctx->tr_ddelta_f : nullptr, gf + Lrgb.b_off,
                                                    gf + Lsig.b_off, st)))
                 return rc;
-            if ((rc = tc_backward(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dpred_f, st, 3))) return rc;
+            // q5: the fine net's input gradient (dtp) comes out of its weight-gradient kernel as a by-product
+            if ((rc = tc_backward(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dpred_f, st, q5 ? 7 : 3))) return rc;
         }
     }
     if (phases & NERF_PHASE_COARSE) {
         const float* d_w_extra = nullptr;
         if (q5) {
-            if ((rc = tc_input_grad(ctx, NERF_NET_FINE, o, d, ctx->fw_t_all, batch, Na, ctx->tr_dtp_f, st))) return rc;
             if ((rc = sample_pdf_backward(t, ctx->fw_w_c, dr, ctx->fw_src_idx, ctx->tr_dtp_f, ctx->tr_ddelta_f, batch, Nc,
                                           ctx->cfg.ns_fine, ctx->tr_dw_extra, st)))
                 return rc;
@@ -486,7 +486,18 @@ extern "C" int nerf_debug_mlp_grads(nerf_ctx* ctx, int net, const float* o, cons
     NERF_CUDA(cudaMemsetAsync(ctx->grads, 0, 2 * ctx->n_params * 4, st));
     float* dp = net == 0 ? ctx->tr_dpred_c : ctx->tr_dpred_f;   // tile-padded staging buffer
     NERF_CUDA(cudaMemcpyAsync(dp, d_preds, (size_t)batch * num_samples * 16, cudaMemcpyDeviceToDevice, st));
-    return tc_backward(ctx, net, o, d, t, batch, num_samples, dp, st, 0);
+    // the fine net also leaves its input gradient in the workspace (nerf_debug_fused_input_grad reads it)
+    return tc_backward(ctx, net, o, d, t, batch, num_samples, dp, st, net == 1 ? 4 : 0);
+}
+
+// Diagnostics: after nerf_debug_mlp_grads(NERF_NET_FINE, ...) -- the same quantity as nerf_debug_input_grad, as produced
+// by the weight-gradient kernel's fused path (what the training step uses); device-to-device copy of batch * num_samples floats.
+extern "C" int nerf_debug_fused_input_grad(nerf_ctx* ctx, int64_t batch, int num_samples, float* dtp, void* stream) {
+    NERF_CHECK_ARG(ctx && dtp && batch >= 1 && num_samples >= 1, "bad arguments");
+    if (!ctx->tr_dtp_f) return fail(NERF_ERR_STATE, "ctx was not created with training=1");
+    NERF_CHECK_ARG(batch * (int64_t)num_samples <= (int64_t)ctx->cfg.max_rays * (ctx->cfg.ns_coarse + ctx->cfg.ns_fine), "too large");
+    NERF_CUDA(cudaMemcpyAsync(dtp, ctx->tr_dtp_f, (size_t)batch * num_samples * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return NERF_OK;
 }
 
 // Diagnostics: after nerf_debug_mlp_grads(net, ...) -- dtp[m] = < d_ray, d(sum(preds * d_preds)) / d pts[m] >.

@@ -415,6 +415,7 @@ struct WgJob {
     int64_t bias_dst;    // float offset of the bias gradient (column sums of dZ), or -1
     int64_t sig_dst;     // float offset of dW_sigma (256,1): column sums of the X image weighted by d sigma per sample, or -1
     int need;            // progress count of the dX chain (images stored so far for a tile) at which this job's dZ image exists
+    int ig;              // -1, or which block of the input-gradient weight image (0: W0^T, 1: W5[256:]^T) this job's dZ image meets
 };
 struct WgParams {
     int debug;              // bit0 / bit3: skip side jobs, bit1: skip MMAs, bit2: skip final reduction (timing experiments)
@@ -428,6 +429,12 @@ struct WgParams {
     const uint32_t* progress;   // per tile: images the concurrently running dX chain has completed (null: chain already done)
     long long* stats;           // diagnostics (nerf_debug_wgrad_stats): per CTA {job, tiles, end ns, ns waiting for the chain, ns waiting for slots}
     float* grads;           // this net's gradient blob
+    // input gradient of the net (reference semantics, Q5), fused into the two jobs that stream dZ0 / dZ5 anyway:
+    //   dtp[m] += < d_ray, J_enc(p_m)^T (dZ_l[m] W_l^T) >;  null: not wanted
+    const __nv_bfloat16* w_ig;
+    const float *ig_o, *ig_d, *ig_t;
+    int ig_N;
+    float* dtp;
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
@@ -466,7 +473,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     const int job_ctas = P.cta_first[job_id + 1] - P.cta_first[job_id], job_cta = (int)blockIdx.x - P.cta_first[job_id];
     const uint32_t bar_afull = base + WG_SM_BAR, bar_aempty = bar_afull + 8 * WG_A_STAGES,
                    bar_bfull = bar_aempty + 8 * WG_A_STAGES, bar_bempty = bar_bfull + 8 * WG_B_MAX_STAGES,
-                   bar_done = bar_bempty + 8 * WG_B_MAX_STAGES;
+                   bar_done = bar_bempty + 8 * WG_B_MAX_STAGES, bar_d2full = bar_done + 8, bar_d2free = bar_d2full + 16,
+                   bar_w = bar_d2free + 16;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + WG_SM_BAR + 200);
     const int n_mh = (J.n_a == 4) ? 2 : 1;                     // M = 128 blocks of the operand (X stages per tile)
     const uint32_t b_bytes = (uint32_t)J.n_b * 16384u;
@@ -474,6 +482,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
     if (b_stages > WG_B_MAX_STAGES) b_stages = WG_B_MAX_STAGES;
     const bool side_off = (P.debug & (1 | 8)) != 0;
     const bool do_sig = J.sig_dst >= 0 && !side_off && !(P.debug & 32), do_bias = J.bias_dst >= 0 && !side_off;
+    // fused input gradient: these jobs have a 16 KB X image (two X stages are plenty); the third X slot holds the 32 KB
+    // weight image, tensor-memory columns 256..383 two 64-column accumulators
+    const bool do_ig = J.ig >= 0 && P.dtp != nullptr;
+    const int a_stages = do_ig ? 2 : WG_A_STAGES;
+    const uint32_t w_img = base + WG_SM_A + 2 * WG_A_SLOT;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < WG_A_STAGES; ++i) {
@@ -485,6 +498,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
             mbar_init(bar_bempty + 8 * i, 1 + (do_bias ? 32 * WG_SIDE_WARPS : 0));
         }
         mbar_init(bar_done, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_d2full + 8 * i, 1); mbar_init(bar_d2free + 8 * i, 128); }
+        mbar_init(bar_w, 1);
         fence_barrier_init();
     }
     if (P.stats && threadIdx.x == 0) {
@@ -515,6 +530,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
             uint32_t apar = 1, bpar = 1;
             long long t_flag = 0, t_slot = 0;
             auto now_ns = []() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+            if (do_ig) {
+                mbar_arrive_expect_tx(bar_w, 32768);
+                bulk_g2s(w_img, reinterpret_cast<const uint8_t*>(P.w_ig) + (size_t)J.ig * 32768, 32768, bar_w);
+            }
             for (int i = 0; i < n_my; ++i) {
                 const int64_t tile = t_first + (int64_t)i * t_step;
                 long long t0 = P.stats ? now_ns() : 0;
@@ -544,7 +563,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
                     } else {
                         bulk_g2s(dst, a_src + mh * 32768, 32768, bar_afull + 8 * as);
                     }
-                    if (++as == WG_A_STAGES) { as = 0; apar ^= 1; }
+                    if (++as == a_stages) { as = 0; apar ^= 1; }
                 }
             }
             if (P.stats) {
@@ -556,8 +575,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 64 * J.n_b, 1, 1);
+            const uint32_t idesc_ig = make_idesc_bf16(128, 64, 0, 0);      // [128 samples x 256] K-major times [64 x 256] K-major
             int as = 0, bs = 0;
             uint32_t apar = 0, bpar = 0;
+            if (do_ig) mbar_wait(bar_w, 0, 18);
             for (int i = 0; i < n_my; ++i) {
                 mbar_wait(bar_bfull + 8 * bs, bpar, 13);
                 const uint32_t b0 = base + WG_SM_B + bs * b_bytes;
@@ -574,7 +595,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
                         }
                     }
                     mma_commit(bar_aempty + 8 * as);
-                    if (++as == WG_A_STAGES) { as = 0; apar ^= 1; }
+                    if (++as == a_stages) { as = 0; apar ^= 1; }
+                }
+                if (do_ig) {
+                    // the dZ image of this stage once more, now as the K-major A operand: d_enc = dZ_l W_l^T  (M = 128, N = 64)
+                    const int buf = i & 1;
+                    mbar_wait(bar_d2free + 8 * buf, (uint32_t)(((i >> 1) & 1) ^ 1), 19);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            mma_bf16_ss(tmem_base + 256 + buf * 64, make_sdesc_sw128(b0 + kb * 16384 + k * 32, 16, 1024),
+                                        make_sdesc_sw128(w_img + kb * 8192 + k * 32, 16, 1024), idesc_ig, (kb > 0 || k > 0) ? 1u : 0u);
+                    mma_commit(bar_d2full + 8 * buf);
                 }
                 mma_commit(bar_bempty + 8 * bs);
                 if (++bs == b_stages) { bs = 0; bpar ^= 1; }
@@ -606,7 +640,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
             acc[4] = fmaf(wgt, __uint_as_float(w.z << 16), acc[4]); acc[5] = fmaf(wgt, __uint_as_float(w.z & 0xFFFF0000u), acc[5]);
             acc[6] = fmaf(wgt, __uint_as_float(w.w << 16), acc[6]); acc[7] = fmaf(wgt, __uint_as_float(w.w & 0xFFFF0000u), acc[7]);
         };
-        if (do_sig || do_bias) {
+        if (do_sig || do_bias || do_ig) {
             int as = 0, bs = 0;
             uint32_t apar = 0, bpar = 0;
             // d sigma of this warp's 16 samples of a tile: one load per lane, fetched ONE TILE AHEAD
@@ -646,10 +680,52 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
 #pragma unroll
                         for (int rr = 0; rr < 8; ++rr) fma8(v[rr], wrow[rr], part);
                         mbar_arrive(bar_aempty + 8 * as);
-                        if (++as == WG_A_STAGES) { as = 0; apar ^= 1; }
+                        if (++as == a_stages) { as = 0; apar ^= 1; }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) { if (mh == 0) sg[0][q] += part[q]; else sg[1][q] += part[q]; }
                     }
+                }
+                if (do_ig && warp < 4) {
+                    // positional-encoding backward of this tile's d_enc rows (thread <-> sample), data_utils.py:17-21,68-70
+                    const int buf = i & 1;
+                    const int64_t m = tile * TILE_M + 32 * warp + lane;
+                    const bool valid = m < P.M;
+                    const int64_t mm = valid ? m : (P.M - 1);
+                    const int64_t ray = mm / P.ig_N;
+                    const float tv = P.ig_t[mm];
+                    float dr[3], pt[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        dr[c] = P.ig_d[ray * 3 + c];
+                        pt[c] = __fadd_rn(P.ig_o[ray * 3 + c], __fmul_rn(dr[c], tv));
+                    }
+                    mbar_wait(bar_d2full + 8 * buf, (uint32_t)((i >> 1) & 1), 20);
+                    tc_fence_after();
+                    uint32_t v0[32], v1[32];
+                    const uint32_t ta = tmem_base + (uint32_t(32 * warp) << 16) + 256 + buf * 64;
+                    tmem_ld32(ta, v0);
+                    tmem_ld32(ta + 32, v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_d2free + 8 * buf);
+                    float de[64];
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) { de[q] = __uint_as_float(v0[q]); de[32 + q] = __uint_as_float(v1[q]); }
+                    // e = [p, sin(2^i p), cos(2^i p)]_i  ->  dp = de_p + sum_i 2^i (cos * de_sin - sin * de_cos)
+                    float accp = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float dp = de[c];
+                        float sv, cv;
+#pragma unroll
+                        for (int oct = 0; oct < 10; ++oct) {
+                            if (oct == 0 || oct == 5) sincosf((float)(1 << oct) * pt[c], &sv, &cv);
+                            else { const float s2 = 2.f * sv * cv, c2 = fmaf(-2.f * sv, sv, 1.f); sv = s2; cv = c2; }
+                            dp = fmaf((float)(1 << oct), cv * de[3 + 6 * oct + c] - sv * de[3 + 6 * oct + 3 + c], dp);
+                        }
+                        accp = fmaf(dr[c], dp, accp);
+                    }
+                    if (valid) atomicAdd(P.dtp + m, accp);
                 }
             }
         }
@@ -1063,10 +1139,10 @@ int tc_pack_backward(nerf_ctx* ctx, cudaStream_t st) {
 }
 
 // gradients of one net given dL/dpreds; the forward must have run with save_acts on the same batch.
-// flags bit 0: the head bias gradients were already accumulated by volume_render_bwd (bit 1: unused)
+// flags bit 0: the head bias gradients were already accumulated by volume_render_bwd (bit 1: unused); bit 2: also
+// leave the net's input gradient dtp[m] = < d_ray, dL/dpts[m] > in ctx->tr_dtp_f (fine net; see WgParams::dtp)
 int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const float* t, int64_t B, int N,
                 const float* d_preds, cudaStream_t st, int flags) {
-    (void)o; (void)t;
     const int64_t M = B * (int64_t)N;
     const int64_t n_pairs = ceil_div(M, 2 * TILE_M);
     // d_preds is the ctx-owned, tile-padded buffer: rows [M, padded) must carry zero gradient
@@ -1091,6 +1167,13 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     P.N = N;
     P.ddir_sum = ctx->tr_ddirsum[net];
     NERF_CUDA(cudaMemsetAsync(ctx->tr_ddirsum[net], 0, (size_t)B * (H / 2) * 4, st));
+    // flags bit 2: the input gradient of this net (dtp = ctx->tr_dtp_f) as a by-product of the jobs that stream dZ0 / dZ5.
+    // Zeroed HERE: in front of the fork, the weight-gradient kernel may run on the side stream next to the chain
+    const bool fuse_ig = (flags & 4) != 0 && ctx->tr_dtp_f != nullptr && ctx->w_ig != nullptr;
+    if (fuse_ig) {
+        if (net != 1) return fail(NERF_ERR_INVALID, "tc_backward: the input-gradient image is packed for the fine net only");
+        NERF_CUDA(cudaMemsetAsync(ctx->tr_dtp_f, 0, (size_t)M * 4, st));
+    }
     // Overlap: with at least one full wave of tile pairs the chain gives up `wg_ctas` SMs to the weight-gradient kernel,
     // which follows it tile by tile (see publish_progress / wait_progress).  Both kernels need a whole SM per CTA
     // (shared memory), so chain CTAs + weight-gradient CTAs <= SMs keeps every CTA resident: the chain never waits for
@@ -1127,18 +1210,22 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     W.n_tiles = n_pairs * 2;
     W.progress = P.progress;
     W.stats = g_wg_stats ? g_wg_stats + (size_t)net * 148 * 8 : nullptr;
+    W.w_ig = ctx->w_ig; W.ig_o = o; W.ig_d = d; W.ig_t = t; W.ig_N = N;
+    W.dtp = fuse_ig ? ctx->tr_dtp_f : nullptr;
     W.grads = grads;
     auto job = [&](int i, int64_t a_off, int n_a, int64_t b_off, int n_b, int64_t w_dst, int ld, int rows, int col_lo,
                    int col_hi, int64_t bias, int64_t sig = -1) {
         // images of a tile leave the chain kernel in the order [ddir + head], feature, Z7, Z6, .. Z0 (progress 1 .. 10)
         const int need = (b_off >= DZ_DDIR) ? 1 : (b_off == DZ_FEAT) ? 2 : 10 - (int)((b_off - DZ_Z) / 65536);
-        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, col_lo, col_hi, bias, sig, need};
+        W.jobs[i] = WgJob{a_off, b_off, n_a, n_b, w_dst, ld, rows, col_lo, col_hi, bias, sig, need, -1};
     };
     job(0, SAVE_ENC, 1, DZ_Z, 4, off.w[0], H, ENC_X, 0, H, off.b[0]);
     for (int l = 1; l <= 4; ++l)
         job(l, SAVE_H + 65536 * (l - 1), 4, DZ_Z + 65536 * l, 4, off.w[l], H, H, 0, H, off.b[l]);
     job(5, SAVE_H + 65536 * 4, 4, DZ_Z + 65536 * 5, 4, off.w[5], H, H, 0, H, off.b[5]);
     job(6, SAVE_ENC, 1, DZ_Z + 65536 * 5, 4, off.w[5] + (int64_t)H * H, H, ENC_X, 0, H, -1);
+    W.jobs[0].ig = 0;      // dZ0 W0^T
+    W.jobs[6].ig = 1;      // dZ5 W5[256:319]^T
     job(7, SAVE_H + 65536 * 5, 4, DZ_Z + 65536 * 6, 4, off.w[6], H, H, 0, H, off.b[6]);
     job(8, SAVE_H + 65536 * 6, 4, DZ_Z + 65536 * 7, 4, off.w[7], H, H, 0, H, off.b[7]);
     // feature layer; its X image is h8, so the same job also produces dW_sigma = h8^T d sigma as a side job

@@ -679,8 +679,11 @@ class NeRFTrainer:
         if not return_input_grad:
             return preds, grads
         dtp = torch.empty((B, N), device=o.device, dtype=torch.float32)
-        _lib.check(_lib.lib().nerf_debug_input_grad(self._ctx.handle, idx, _ptr(o), _ptr(d), _ptr(t), B, N, _ptr(dtp),
-                                                    _stream()), "debug_input_grad")
+        if return_input_grad == "fused":      # by-product of the weight-gradient kernel (what train_step uses)
+            _lib.check(_lib.lib().nerf_debug_fused_input_grad(self._ctx.handle, B, N, _ptr(dtp), _stream()), "fused_input_grad")
+        else:                                 # the stand-alone input-gradient kernel
+            _lib.check(_lib.lib().nerf_debug_input_grad(self._ctx.handle, idx, _ptr(o), _ptr(d), _ptr(t), B, N, _ptr(dtp),
+                                                        _stream()), "debug_input_grad")
         return preds, grads, dtp
 
     def forward_pass_with_minibatch(self, ray_origins, ray_directions, t_vals, l_xyz=None, l_dir=None, batch_size=512,

@@ -251,6 +251,11 @@ def test_input_gradient_matches_autograd(nk, name):
     assert np.isfinite(got).all()
     cos = float((ref * got).sum() / (np.linalg.norm(ref) * np.linalg.norm(got)))
     assert cos > 0.97 and abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1.0) < 0.1, (cos, np.linalg.norm(got), np.linalg.norm(ref))
+    # the training step takes the same quantity from the weight-gradient kernel (the jobs that stream dZ0 / dZ5 multiply
+    # them with W0^T / W5b^T on the way): same bf16 operands, fp32 accumulation split over two jobs
+    _, _, fused = tr.debug_mlp_grads("fine", g["o"], g["d"], g["t_all"], d_preds.numpy(), return_input_grad="fused")
+    fused = fused.cpu().numpy()
+    assert np.abs(fused - got).max() <= 2e-5 * np.abs(got).max() + 1e-9, (np.abs(fused - got).max(), np.abs(got).max())
 
 
 @pytest.mark.parametrize("name", ["lego_small", "fern_small"])
