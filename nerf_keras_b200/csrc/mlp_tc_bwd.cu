@@ -786,26 +786,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) nerf_wgrad_tc_kernel(const WgPa
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) dirw_grad_kernel(const float* __restrict__ d, int64_t rays, const float* __restrict__ S,
                                                         float* __restrict__ g_wdir /* (27, 128) */) {
-    __shared__ float enc[32];
+    __shared__ float enc[4][32];
     const int j = threadIdx.x;
     float acc[ENC_D];
 #pragma unroll
     for (int k = 0; k < ENC_D; ++k) acc[k] = 0.f;
-    for (int64_t ray = blockIdx.x; ray < rays; ray += gridDim.x) {
-        if (j < ENC_D) {
-            float v;
-            if (j < 3) v = d[ray * 3 + j];
-            else {
-                const int q = j - 3, i = q / 6, r = q - i * 6, comp = r % 3;
-                const float arg = __fmul_rn(exp2f((float)i), d[ray * 3 + comp]);
-                v = (r >= 3) ? cosf(arg) : sinf(arg);
+    // four rays per round: their four S loads are in flight together (one dependent L2 / HBM round trip per ray made this
+    // 30 us); threads 0..107 compute the 4 x 27 encoding values
+    for (int64_t ray0 = (int64_t)blockIdx.x * 4; ray0 < rays; ray0 += (int64_t)gridDim.x * 4) {
+        float sv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sv[q] = (ray0 + q < rays) ? __ldg(S + (ray0 + q) * 128 + j) : 0.f;
+        if (j < 4 * ENC_D) {
+            const int q = j / ENC_D, c = j - q * ENC_D;
+            const int64_t ray = ray0 + q;
+            float v = 0.f;
+            if (ray < rays) {
+                if (c < 3) v = d[ray * 3 + c];
+                else {
+                    const int qq = c - 3, i = qq / 6, r = qq - i * 6, comp = r % 3;
+                    const float arg = __fmul_rn(exp2f((float)i), d[ray * 3 + comp]);
+                    v = (r >= 3) ? cosf(arg) : sinf(arg);
+                }
             }
-            enc[j] = v;
+            enc[q][c] = v;
         }
         __syncthreads();
-        const float sv = S[ray * 128 + j];
 #pragma unroll
-        for (int k = 0; k < ENC_D; ++k) acc[k] = fmaf(enc[k], sv, acc[k]);
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < ENC_D; ++k) acc[k] = fmaf(enc[q][k], sv[q], acc[k]);
         __syncthreads();
     }
 #pragma unroll
@@ -1198,7 +1208,8 @@ int tc_backward(nerf_ctx* ctx, int net, const float* o, const float* d, const fl
     timing_end(1, st);
     NERF_LAUNCHED();
     // direction rows of dW_ddir from the per-ray sums the chain just took
-    dirw_grad_kernel<<<num_sms(), 128, 0, st>>>(d, B, ctx->tr_ddirsum[net], grads + off.w[10] + (int64_t)H * (H / 2));
+    dirw_grad_kernel<<<(int)(ceil_div(B, 4) < 2 * num_sms() ? ceil_div(B, 4) : 2 * num_sms()), 128, 0, st>>>(
+        d, B, ctx->tr_ddirsum[net], grads + off.w[10] + (int64_t)H * (H / 2));
     NERF_LAUNCHED();
 
     WgParams W;
