@@ -323,3 +323,49 @@ def test_training_with_reference_semantics_reduces_loss(nk):
     assert np.isfinite(list(last.values())).all()
     assert last["loss"] < 0.6 * first["loss"], (first, last)          # oracle: 0.1334 -> 0.0447
     assert last["loss_coarse"] < 1.0
+
+
+def test_direction_rows_and_input_gradient_with_ragged_rays(nk):
+    """Ray boundaries that fall INSIDE the 16-row blocks of the chain kernel's per-ray dZ_ddir sums (23 samples per ray)
+    and a ragged last tile (37 rays x 23 = 851 rows): the direction rows of dW_ddir (rows 256..282, models.py:48-54), every
+    other tensor and the fused input gradient against torch.autograd on the fp32 oracle."""
+    g = load_golden("lego_small")
+    wc, wf = golden_weights(g)
+    B, N = 37, 23
+    gen = torch.Generator().manual_seed(11)
+    o = torch.randn(B, 3, generator=gen) * 0.3 + torch.tensor([0.0, 0.0, 3.5])
+    d = torch.nn.functional.normalize(torch.randn(B, 3, generator=gen) * 0.2 + torch.tensor([0.0, 0.0, -1.0]), dim=-1)
+    t = (torch.sort(torch.rand(B, N, generator=gen), -1).values * 4.0 + 2.0).requires_grad_(True)
+    d_preds = torch.randn(B, N, 4, generator=gen) * 0.1
+    params = _params(wf)
+    for p in params:
+        p.requires_grad_(True)
+    rays, dirs = O.sample_rays(o, d, t)
+    pred = O.nerf_mlp(wf, O.encode_position(rays, 10), O.encode_position(dirs.detach(), 4))
+    grads_ref = torch.autograd.grad((pred * d_preds).sum(), params + [t])
+    for p in params:
+        p.requires_grad_(False)
+    ref = np.concatenate([x.numpy().reshape(-1) for x in grads_ref[:-1]])
+    dtp_ref = grads_ref[-1].numpy()
+
+    mc = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    mf = nk.create_nerf_complete_model(8, 256, 4, 10, 4)
+    mc.set_flat_weights(O.flatten_weights(wc)); mf.set_flat_weights(O.flatten_weights(wf))
+    tr = nk.NeRFTrainer(mc, mf, B, 10, 13, 10, 4, stop_grad_samples=False)
+    tr.compile(nk.Adam(learning_rate=5e-4), nk.MeanSquaredError())
+    tn = t.detach().numpy()
+    _, grads, dtp = tr.debug_mlp_grads("fine", o.numpy(), d.numpy(), tn, d_preds.numpy(), return_input_grad="fused")
+    _, _, dtp_alone = tr.debug_mlp_grads("fine", o.numpy(), d.numpy(), tn, d_preds.numpy(), return_input_grad=True)
+    got, shapes = grads.cpu().numpy(), O.layer_shapes()
+    a, b = _split(got, shapes), _split(ref, shapes)
+    wd_got, wd_ref = a["ddir/W"].reshape(283, 128)[256:], b["ddir/W"].reshape(283, 128)[256:]
+    cos = float((wd_got * wd_ref).sum() / (np.linalg.norm(wd_got) * np.linalg.norm(wd_ref)))
+    assert cos >= 0.995 and abs(np.linalg.norm(wd_got) / np.linalg.norm(wd_ref) - 1.0) <= 0.03, cos
+    for k in a:
+        nb = np.linalg.norm(b[k]) + 1e-20
+        c = float(a[k] @ b[k]) / (np.linalg.norm(a[k]) * nb + 1e-20)
+        assert c >= 0.97 and abs(np.linalg.norm(a[k]) / nb - 1.0) <= 0.08, (k, c)
+    dtp, dtp_alone = dtp.cpu().numpy(), dtp_alone.cpu().numpy()
+    assert np.abs(dtp - dtp_alone).max() <= 2e-5 * np.abs(dtp_alone).max() + 1e-9
+    c = float((dtp * dtp_ref).sum() / (np.linalg.norm(dtp) * np.linalg.norm(dtp_ref)))
+    assert c > 0.97, c
