@@ -275,11 +275,15 @@ def timed_region(step_fn, steps, flush, world, dev, torch):
     return total_ms
 
 
+BACKWARD_OVERLAP_SMS = 0      # --backward-overlap: the opt-in schedule of DESIGN.md 4.3 (weight gradient next to the dX chain)
+
+
 def make_trainer(nk, conf, B, Nc, Nf, train, use_graph=True, seed=42):
     nk.set_random_seed(seed)
     mk = lambda: nk.create_nerf_complete_model(conf["NUM_LAYERS"], conf["HIDDEN_DIM"], conf["SKIP_LAYER"],
                                                conf["L_XYZ"], conf["L_DIR"], bn=conf["BATCH_NORM"])
-    trainer = nk.NeRFTrainer(mk(), mk(), B, Nc, Nf, conf["L_XYZ"], conf["L_DIR"], use_cuda_graph=use_graph)
+    trainer = nk.NeRFTrainer(mk(), mk(), B, Nc, Nf, conf["L_XYZ"], conf["L_DIR"], use_cuda_graph=use_graph,
+                             backward_overlap_sms=BACKWARD_OVERLAP_SMS)
     if train:
         trainer.compile(nk.Adam(learning_rate=conf["LEARNING_RATE"]), nk.MeanSquaredError())
     else:
@@ -412,7 +416,11 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after the whole backward (N > 1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--backward-overlap", type=int, default=0,
+                    help="experiment (DESIGN.md 4.3): weight-gradient kernel on this many SMs next to the dX chain")
     args = ap.parse_args()
+    global BACKWARD_OVERLAP_SMS
+    BACKWARD_OVERLAP_SMS = args.backward_overlap
     conf = load_conf(args.config)
     if args.ns_fine is not None:
         conf["NS_FINE"] = args.ns_fine

@@ -391,7 +391,7 @@ class NeRFTrainer:
 
     def __init__(self, coarse_model, fine_model, batch_size, ns_coarse, ns_fine, l_xyz, l_dir,
                  precision=PRECISION_BF16_TC, stop_grad_samples=False, process_group=None, use_cuda_graph=True,
-                 overlap_allreduce=True, exact_far_sigma=False):
+                 overlap_allreduce=True, exact_far_sigma=False, backward_overlap_sms=0):
         if not isinstance(coarse_model, NerfModel):
             raise TypeError("coarse_model must be a NerfModel (create_nerf_complete_model) instance")
         if not isinstance(fine_model, NerfModel):
@@ -409,6 +409,9 @@ class NeRFTrainer:
         # rendering option: the last sample of every ray (delta = 1e10, data_utils.py:82: colour is discontinuous in its raw
         # sigma at 0) takes its sigma from the fp32 path, so bf16 rounding cannot flip that decision
         self.exact_far_sigma = bool(exact_far_sigma)
+        # training option (default off, measured slower -- DESIGN.md 4.3): the weight-gradient kernel on this many SMs
+        # NEXT TO the dX chain, consuming every tile's dZ images as the chain publishes them (nerf_set_backward_overlap)
+        self.backward_overlap_sms = int(backward_overlap_sms)
         self.optimizer = None
         self.loss_fn = None
         self._ctx: Optional[_Ctx] = None
@@ -575,6 +578,8 @@ class NeRFTrainer:
                          self.stop_grad_samples)
         _lib.check(_lib.lib().nerf_set_seed(self._ctx.handle, int(self._seed) & 0xFFFFFFFFFFFFFFFF), "nerf_set_seed")
         _lib.check(_lib.lib().nerf_set_exact_far_sigma(self._ctx.handle, int(self.exact_far_sigma)), "exact_far_sigma")
+        if training and self.backward_overlap_sms:
+            _lib.check(_lib.lib().nerf_set_backward_overlap(self._ctx.handle, self.backward_overlap_sms), "backward_overlap")
         for net, (m, blob) in enumerate(zip((self.coarse_model, self.fine_model), blobs)):
             m._owner = (self._ctx, net)
             self._ctx.set_weights(net, torch.from_numpy(blob))
