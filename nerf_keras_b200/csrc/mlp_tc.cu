@@ -152,6 +152,9 @@ constexpr bool kCoalescedSave = true;
 constexpr bool kDirectSave = false;
 constexpr bool kCoalescedSave = false;
 #endif
+// The three named barriers of a saving trunk epilogue (previous store has read the tile / tile halves complete before the
+// elected thread issues their bulk stores) cost 0.035 ms per step of forward (timing experiment without them, round 2):
+// a dedicated store-issuing thread fed by mbarriers could win back at most that much.
 constexpr bool kSplitImageStore = true;
 constexpr bool kHybridSave = false;       // K-blocks 0,1 by 256-bit register stores during the first epilogue half, K-blocks 2,3 by
                                           // one bulk store: measured 1.90 ms per step vs 1.65 with two bulk stores -- off   // bulk-store K-blocks 0,1 as soon as they are written (two 32 KB stores per phase)
