@@ -78,12 +78,25 @@ __global__ void __launch_bounds__(256) col_reduce_kernel(const float* __restrict
     const int64_t r0 = blockIdx.y * rows_per, r1 = (r0 + rows_per < M) ? r0 + rows_per : M;
     double a0 = 0.0, a1 = 0.0;
     if (col < C) {
-        for (int64_t r = r0 + ry; r < r1; r += 8) {
-            float v = x[r * ldx + col];
-            if (mode == 0) { a0 += v; a1 += (double)v * v; }
-            else {
-                if (!(a[r * C + col] > 0.f)) v = 0.f;
-                a0 += v; a1 += (double)v * zhat[r * C + col];
+        // four rows per iteration, all loads issued before the first use (one dependent HBM round trip per row made this
+        // kernel 7x slower than its bytes)
+        for (int64_t r = r0 + ry; r < r1; r += 32) {
+            float v[4], av[4], zv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t rr = r + 8 * q;
+                const bool ok = rr < r1;
+                v[q] = ok ? x[rr * ldx + col] : 0.f;
+                av[q] = (ok && mode != 0) ? a[rr * C + col] : 1.f;
+                zv[q] = (ok && mode != 0) ? zhat[rr * C + col] : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (mode == 0) { a0 += v[q]; a1 += (double)v[q] * v[q]; }
+                else {
+                    const float dy = (av[q] > 0.f) ? v[q] : 0.f;
+                    a0 += dy; a1 += (double)dy * zv[q];
+                }
             }
         }
     }
@@ -131,6 +144,31 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const float* __restrict__ d
                                                      const double* __restrict__ s_dy, const double* __restrict__ s_dyz,
                                                      const float* __restrict__ gamma, const float* __restrict__ rstd,
                                                      float* __restrict__ dz) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    if ((C & 3) == 0 && stride % C == 0 && (n & 3) == 0) {
+        // four consecutive columns per thread, the SAME four in every iteration (the grid stride is a multiple of C): the
+        // per-column constants (two double divisions each) leave the loop
+        const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        const int c0 = (int)(i0 % C);
+        float gr[4], mdy[4], mdz[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            gr[q] = gamma[c0 + q] * rstd[c0 + q];
+            mdy[q] = (float)(s_dy[c0 + q] / (double)M);
+            mdz[q] = (float)(s_dyz[c0 + q] / (double)M);
+        }
+        for (int64_t i = i0; i < n; i += stride) {
+            const float4 d4 = *reinterpret_cast<const float4*>(da + i), a4 = *reinterpret_cast<const float4*>(a + i),
+                         z4 = *reinterpret_cast<const float4*>(zhat + i);
+            float4 o;
+            o.x = gr[0] * (((a4.x > 0.f) ? d4.x : 0.f) - mdy[0] - z4.x * mdz[0]);
+            o.y = gr[1] * (((a4.y > 0.f) ? d4.y : 0.f) - mdy[1] - z4.y * mdz[1]);
+            o.z = gr[2] * (((a4.z > 0.f) ? d4.z : 0.f) - mdy[2] - z4.z * mdz[2]);
+            o.w = gr[3] * (((a4.w > 0.f) ? d4.w : 0.f) - mdy[3] - z4.w * mdz[3]);
+            *reinterpret_cast<float4*>(dz + i) = o;
+        }
+        return;
+    }
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         const float dy = (a[i] > 0.f) ? da[i] : 0.f;
@@ -195,7 +233,7 @@ inline int egrid(int64_t n) { int64_t g = (n + 255) / 256; int64_t cap = 8 * (in
 int batch_norm_fwd(cudaStream_t st, float* z, float* a, int64_t M, int C, const float* bias, const float* gamma, const float* beta,
                    float* mov_mean, float* mov_var, float* mu, float* rstd, double* sums) {
     NERF_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * 8, st));
-    dim3 grid((C + 31) / 32, (unsigned)((M + 4095) / 4096 < 256 ? (M + 4095) / 4096 : 256));
+    dim3 grid((C + 31) / 32, (unsigned)((M + 511) / 512 < 2048 ? (M + 511) / 512 : 2048));     // 512 rows per block
     col_reduce_kernel<<<grid, 256, 0, st>>>(z, C, nullptr, nullptr, M, C, 0, sums, sums + C);
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, sums + C, M, C, bias, mu, rstd, mov_mean, mov_var);
     bn_apply_kernel<<<egrid(M * C), 256, 0, st>>>(z, a, M * C, C, mu, rstd, gamma, beta);
@@ -207,7 +245,7 @@ int batch_norm_fwd(cudaStream_t st, float* z, float* a, int64_t M, int C, const 
 int batch_norm_bwd(cudaStream_t st, const float* da, const float* a, const float* zhat, int64_t M, int C, const float* gamma,
                    const float* rstd, float* dz, float* dgamma, float* dbeta, double* sums) {
     NERF_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * 8, st));
-    dim3 grid((C + 31) / 32, (unsigned)((M + 4095) / 4096 < 256 ? (M + 4095) / 4096 : 256));
+    dim3 grid((C + 31) / 32, (unsigned)((M + 511) / 512 < 2048 ? (M + 511) / 512 : 2048));     // 512 rows per block
     col_reduce_kernel<<<grid, 256, 0, st>>>(da, C, a, zhat, M, C, 1, sums, sums + C);
     bn_bwd_kernel<<<egrid(M * C), 256, 0, st>>>(da, a, zhat, M * C, C, M, sums, sums + C, gamma, rstd, dz);
     store_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dbeta);
@@ -218,7 +256,7 @@ int batch_norm_bwd(cudaStream_t st, const float* da, const float* a, const float
 
 int col_sums(cudaStream_t st, const float* x, int ldx, int64_t M, int C, float* dst, double* sums) {
     NERF_CUDA(cudaMemsetAsync(sums, 0, (size_t)C * 8, st));
-    dim3 grid((C + 31) / 32, (unsigned)((M + 4095) / 4096 < 256 ? (M + 4095) / 4096 : 256));
+    dim3 grid((C + 31) / 32, (unsigned)((M + 511) / 512 < 2048 ? (M + 511) / 512 : 2048));     // 512 rows per block
     col_reduce_kernel<<<grid, 256, 0, st>>>(x, ldx, nullptr, nullptr, M, C, 0, sums, nullptr);
     store_sums_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dst);
     NERF_LAUNCHED();

@@ -499,11 +499,18 @@ __global__ void __launch_bounds__(256) small_tn_kernel(const float* __restrict__
     const int64_t m0 = (int64_t)blockIdx.x * per, m1 = (m0 + per < Ms) ? m0 + per : Ms;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (j < Mo) {
-        for (int64_t m = m0; m < m1; ++m) {
-            const float a = A[m * lda + j];
+        for (int64_t m = m0; m < m1; m += 8) {          // eight rows in flight
+            float av[8];
 #pragma unroll
-            for (int n = 0; n < 4; ++n)
-                if (n < N) acc[n] = fmaf(a, __ldg(B + m * ldb + n), acc[n]);
+            for (int q = 0; q < 8; ++q) av[q] = (m + q < m1) ? A[(m + q) * lda + j] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (m + q < m1) {
+#pragma unroll
+                    for (int n = 0; n < 4; ++n)
+                        if (n < N) acc[n] = fmaf(av[q], __ldg(B + (m + q) * ldb + n), acc[n]);
+                }
+            }
         }
 #pragma unroll
         for (int n = 0; n < 4; ++n)
@@ -538,7 +545,7 @@ int tc_gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, cons
         if (beta != 1.f) return fail(NERF_ERR_INVALID, "tc_gemm_f32: the transposed product accumulates into C (beta = 1)");
         if (M > 256 || N > 256) return fail(NERF_ERR_INVALID, "tc_gemm_f32: transposed product limited to 256 x 256 outputs");
         if (N <= 4) {
-            const int grid = (int)(ceil_div(K, 2048) < 4 * num_sms() ? ceil_div(K, 2048) : 4 * num_sms());
+            const int grid = (int)(ceil_div(K, 256) < 16 * num_sms() ? ceil_div(K, 256) : 16 * num_sms());     // ~256 samples per block
             small_tn_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, (int64_t)K, (int)M, N);
             NERF_LAUNCHED();
             return NERF_OK;
