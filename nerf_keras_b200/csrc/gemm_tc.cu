@@ -150,58 +150,67 @@ __global__ void __launch_bounds__(256) pack_b_split_kernel(const float* __restri
 }
 
 // one K-block (columns [col0, col0 + 64)) of rows [row0, row0 + 128) -> PARTS tiles of [128][64] at stage + part * 16 KB.
-// All loads of the block are in flight before the first conversion.
-template <int PARTS>
-__device__ __forceinline__ void convert_block(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_end, int col0,
-                                              int cols_end, uint8_t* stage, int worker) {
+// Aligned case: lane <-> four consecutive columns, 16 lanes per row, two rows per warp instruction, eight float4 per thread.
+__device__ __forceinline__ bool block_is_vec(const float* src, int64_t ld, int cols_end) {
+    return (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((cols_end & 3) == 0);
+}
+__device__ __forceinline__ void load_block_vec(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_end, int col0,
+                                               int cols_end, int worker, float4 (&v)[8]) {
     const int w = worker >> 5, lane = worker & 31;
-    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((cols_end & 3) == 0);
-    if (vec) {
-        const int c = 4 * (lane & 15), rr = 2 * w + (lane >> 4);          // 16 lanes per row, two rows per warp instruction
-        float4 v[8];
+    const int c = 4 * (lane & 15), rr = 2 * w + (lane >> 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t g = row0 + rr + 16 * i;
+        v[i] = (g < rows_end && col0 + c < cols_end) ? __ldg(reinterpret_cast<const float4*>(src + g * ld + col0 + c))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <int PARTS>
+__device__ __forceinline__ void store_block_vec(const float4 (&v)[8], uint8_t* stage, int worker) {
+    const int w = worker >> 5, lane = worker & 31;
+    const int c = 4 * (lane & 15), rr = 2 * w + (lane >> 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t off = sw128_offset(rr + 16 * i, c);
+        __nv_bfloat16 a[3], b[3], cc[3], d[3];
+        split_parts<PARTS>(v[i].x, a); split_parts<PARTS>(v[i].y, b); split_parts<PARTS>(v[i].z, cc); split_parts<PARTS>(v[i].w, d);
+#pragma unroll
+        for (int q = 0; q < PARTS; ++q) {
+            uint2 o;
+            o.x = (uint32_t)__bfloat16_as_ushort(a[q]) | ((uint32_t)__bfloat16_as_ushort(b[q]) << 16);
+            o.y = (uint32_t)__bfloat16_as_ushort(cc[q]) | ((uint32_t)__bfloat16_as_ushort(d[q]) << 16);
+            *reinterpret_cast<uint2*>(stage + q * 16384 + off) = o;
+        }
+    }
+}
+// unaligned / ragged case (K = 63, 27, odd leading dimensions): lanes along the columns, scalar loads, all loads of eight rows
+// in flight before the first conversion
+template <int PARTS>
+__device__ __forceinline__ void convert_block_scalar(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_end,
+                                                     int col0, int cols_end, uint8_t* stage, int worker) {
+    const int w = worker >> 5, lane = worker & 31;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float v[8][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int64_t g = row0 + rr + 16 * i;
-            v[i] = (g < rows_end && col0 + c < cols_end) ? __ldg(reinterpret_cast<const float4*>(src + g * ld + col0 + c))
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            const int64_t g = row0 + w + 8 * (half * 8 + i);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t off = sw128_offset(rr + 16 * i, c);
-            __nv_bfloat16 a[3], b[3], cc[3], d[3];
-            split_parts<PARTS>(v[i].x, a); split_parts<PARTS>(v[i].y, b); split_parts<PARTS>(v[i].z, cc); split_parts<PARTS>(v[i].w, d);
-#pragma unroll
-            for (int q = 0; q < PARTS; ++q) {
-                uint2 o;
-                o.x = (uint32_t)__bfloat16_as_ushort(a[q]) | ((uint32_t)__bfloat16_as_ushort(b[q]) << 16);
-                o.y = (uint32_t)__bfloat16_as_ushort(cc[q]) | ((uint32_t)__bfloat16_as_ushort(d[q]) << 16);
-                *reinterpret_cast<uint2*>(stage + q * 16384 + off) = o;
+            for (int j = 0; j < 2; ++j) {
+                const int c = lane + 32 * j;
+                v[i][j] = (g < rows_end && col0 + c < cols_end) ? __ldg(src + g * ld + col0 + c) : 0.f;
             }
         }
-    } else {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float v[8][2];
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t g = row0 + w + 8 * (half * 8 + i);
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t off = sw128_offset(w + 8 * (half * 8 + i), lane + 32 * j);
+                __nv_bfloat16 parts[3];
+                split_parts<PARTS>(v[i][j], parts);
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int c = lane + 32 * j;
-                    v[i][j] = (g < rows_end && col0 + c < cols_end) ? __ldg(src + g * ld + col0 + c) : 0.f;
-                }
+                for (int q = 0; q < PARTS; ++q) *reinterpret_cast<__nv_bfloat16*>(stage + q * 16384 + off) = parts[q];
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const uint32_t off = sw128_offset(w + 8 * (half * 8 + i), lane + 32 * j);
-                    __nv_bfloat16 parts[3];
-                    split_parts<PARTS>(v[i][j], parts);
-#pragma unroll
-                    for (int q = 0; q < PARTS; ++q) *reinterpret_cast<__nv_bfloat16*>(stage + q * 16384 + off) = parts[q];
-                }
-        }
     }
 }
 
@@ -242,14 +251,36 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gemm_rows_kernel(const RowsPara
     if (warp < 8) {
         // ===================== A conversion: one K-block per stage =====================
         int s = 0; uint32_t par = 1;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
-            for (int kb = 0; kb < P.KB; ++kb) {
+        if (block_is_vec(P.A, P.lda, P.K)) {
+            // the loads of block n + 1 are issued before block n is converted and stored: two blocks (64 KB per SM) in flight
+            const int n_blocks = my_tiles * P.KB;
+            float4 cur[8], nxt[8];
+            if (n_blocks > 0) load_block_vec(P.A, P.lda, (int64_t)blockIdx.x * 128, P.M, 0, P.K, threadIdx.x, cur);
+            int it = 0, kb = 0;
+            for (int n = 0; n < n_blocks; ++n) {
+                int it2 = it, kb2 = kb + 1;
+                if (kb2 == P.KB) { kb2 = 0; ++it2; }
+                if (n + 1 < n_blocks)
+                    load_block_vec(P.A, P.lda, (blockIdx.x + (int64_t)it2 * gridDim.x) * 128, P.M, kb2 * 64, P.K, threadIdx.x, nxt);
                 mbar_wait(bar_aempty + 8 * s, par, 31);
-                convert_block<PARTS>(P.A, P.lda, tile * 128, P.M, kb * 64, P.K, smem + GR_SM_A + s * A_STAGE, threadIdx.x);
+                store_block_vec<PARTS>(cur, smem + GR_SM_A + s * A_STAGE, threadIdx.x);
                 fence_proxy_async_smem();
                 mbar_arrive(bar_afull + 8 * s);
                 if (++s == GR_A_STAGES) { s = 0; par ^= 1; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+                it = it2; kb = kb2;
+            }
+        } else {
+            for (int it = 0; it < my_tiles; ++it) {
+                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+                for (int kb = 0; kb < P.KB; ++kb) {
+                    mbar_wait(bar_aempty + 8 * s, par, 31);
+                    convert_block_scalar<PARTS>(P.A, P.lda, tile * 128, P.M, kb * 64, P.K, smem + GR_SM_A + s * A_STAGE, threadIdx.x);
+                    fence_proxy_async_smem();
+                    mbar_arrive(bar_afull + 8 * s);
+                    if (++s == GR_A_STAGES) { s = 0; par ^= 1; }
+                }
             }
         }
     } else if (warp < 12) {
