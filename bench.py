@@ -100,6 +100,8 @@ def fern_poses(n_views):
 def scene_of(conf_path, conf, rays_mode):
     """(name, focal, near, far, pose list factory) of the synthetic scene a config file names."""
     base = os.path.basename(conf_path)
+    if base.startswith("ref_"):        # config/ref_*.json: the reference's literal values
+        base = base[4:]
     if base.startswith("fern"):
         focal = float(np.float32(407.6 * conf["WIDTH"] / 504.0))
         near, far = (0.0, 1.0) if rays_mode == "ndc" else (1.2, 12.0)
@@ -433,10 +435,11 @@ def main():
               "sweep": "train_rays_per_sec"}[args.mode]
     config = {"workload": f"{args.config}: 8x256 MLP x{2 if Nf else 1} (coarse {Nc}" + (f" + fine {Nf}" if Nf else "") +
                           f" samples/ray), synthetic {scene[0].capitalize()}-shaped {conf['HEIGHT']}x{conf['WIDTH']} views"
-                          f" ({args.rays} rays), {B}-ray batch per GPU",
+                          f" ({args.rays} rays), {B}-ray batch per GPU" +
+                          (", BATCH_NORM=true (layer-by-layer path, tcgen05 split-bf16 GEMMs)" if conf.get("BATCH_NORM") else ""),
               "mode": args.mode, "rays_per_step_per_gpu": B, "samples_per_ray": spr, "parallelism": f"dp{args.gpus}",
               "l2": "8 distinct resident ray batches rotated + 256 MiB L2 flush between timed steps",
-              "step": "CUDA-graph replay" if not args.no_graph else "eager launches"}
+              "step": "eager launches" if (args.no_graph or conf.get("BATCH_NORM")) else "CUDA-graph replay"}
     rank = int(os.environ.get("RANK", "0"))
 
     if args.impl == "reference":
