@@ -13,9 +13,10 @@
 //       a 3-stage ring, a producer thread streams the pre-split B chunks ([128 n x 64 k] per part) through a 4-slot ring,
 //       one thread issues the MMAs into one of two 256-column accumulators, 4 warps write the other one out.
 //   gemm_tn_kernel     C (Mo x N) += A^T B,  A (Ms x Mo), B (Ms x N): the contraction runs over the SAMPLES
-//       a [128 samples x 64 features] tile stored K-major IS an MN-major operand of the transposed product (the trick of
-//       nerf_wgrad_tc_kernel), so the same conversion feeds it; each CTA owns a slab of sample tiles and one 128-column
-//       half of N, keeps its (<= 256 x 128) accumulator in tensor memory and adds it to C with atomics at the end.
+//       a [64 samples x 64 features] tile stored K-major IS an MN-major operand of the transposed product (the trick of
+//       nerf_wgrad_tc_kernel), so the same conversion feeds it; each CTA owns a slab of 64-sample half-tiles (two stages:
+//       one is converted while the other is multiplied) and one 128-column half of N, keeps its (<= 256 x 128) accumulator
+//       in tensor memory and adds it to C with atomics at the end.
 // Skinny shapes (N <= 4 or K <= 4: the sigma / rgb heads) are CUDA-core kernels at the end of this file.
 #include "common.cuh"
 #include "tc5.cuh"
@@ -47,23 +48,25 @@ __device__ __forceinline__ void split_store4(uint8_t* hi_tile, uint8_t* lo_tile,
     *reinterpret_cast<uint2*>(lo_tile + off) = lo;
 }
 
-// rows [row0, row0 + 128) x columns [col0, col0 + 64 * blocks) of a row-major fp32 matrix -> hi / lo bf16 tiles,
-// [block][128 rows][64] K-major 128B-swizzled; rows >= rows_end and columns >= cols_end read as zero.
+// rows [row0, row0 + 64) x columns [col0, col0 + 64 * blocks) of a row-major fp32 matrix -> hi / lo bf16 half-tiles,
+// [block][64 rows][64] K-major 128B-swizzled (8 KB per block); rows >= rows_end and columns >= cols_end read as zero.
 // `worker` = 0 .. 255 (8 warps): warp w takes rows w, w + 8, ..; lanes run along the columns (coalesced).  All loads of
-// a group of rows are issued before the first conversion (a load per iteration ran at one HBM round trip per element).
-__device__ __forceinline__ void convert_tile(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_end,
-                                             int col0, int cols_end, int blocks, uint8_t* hi_tile, uint8_t* lo_tile,
-                                             int worker) {
+// a batch of rows are issued before the first conversion.
+__device__ __forceinline__ void convert_half_tile(const float* __restrict__ src, int64_t ld, int64_t row0, int64_t rows_end,
+                                                  int col0, int cols_end, int blocks, uint8_t* hi_tile, uint8_t* lo_tile,
+                                                  int worker) {
     const int w = worker >> 5, lane = worker & 31;
     const int ncols = blocks * 64;
-    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src + col0) & 15) == 0) && ((cols_end - col0) % 4 == 0 || cols_end - col0 >= ncols);
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(src + col0) & 15) == 0) &&
+                     ((cols_end - col0) % 4 == 0 || cols_end - col0 >= ncols);
     if (vec) {
         // lane <-> four consecutive columns; up to two float4 per row and lane (256 columns), four rows in flight
-        for (int r0 = w; r0 < 128; r0 += 32) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
             float4 v[4][2];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int64_t g = row0 + r0 + 8 * i;
+                const int64_t g = row0 + w + 8 * (half * 4 + i);
                 const float* __restrict__ p = src + g * ld + col0;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -76,16 +79,17 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ src, int6
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const int c = 4 * lane + 128 * j, r = r0 + 8 * i;
-                    if (c < ncols) split_store4(hi_tile, lo_tile, (uint32_t)(c >> 6) * 16384u + sw128_offset(r, c & 63), v[i][j]);
+                    const int c = 4 * lane + 128 * j, r = w + 8 * (half * 4 + i);
+                    if (c < ncols) split_store4(hi_tile, lo_tile, (uint32_t)(c >> 6) * 8192u + sw128_offset(r, c & 63), v[i][j]);
                 }
         }
     } else {
-        for (int r0 = w; r0 < 128; r0 += 16) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
             float v[2][8];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const int64_t g = row0 + r0 + 8 * i;
+                const int64_t g = row0 + w + 8 * (q4 * 2 + i);
                 const float* __restrict__ p = src + g * ld + col0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -97,8 +101,8 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ src, int6
             for (int i = 0; i < 2; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int c = lane + 32 * j, r = r0 + 8 * i;
-                    if (c < ncols) split_store(hi_tile, lo_tile, (uint32_t)(c >> 6) * 16384u + sw128_offset(r, c & 63), v[i][j]);
+                    const int c = lane + 32 * j, r = w + 8 * (q4 * 2 + i);
+                    if (c < ncols) split_store(hi_tile, lo_tile, (uint32_t)(c >> 6) * 8192u + sw128_offset(r, c & 63), v[i][j]);
                 }
         }
     }
@@ -115,8 +119,11 @@ constexpr int GR_A_STAGES = 3;       // stage = one 64-wide K-block of a 128-row
 constexpr int GR_B_STAGES = 4;       // 16 KB chunks [128 n x 64 k] of one part of B
 constexpr int GR_SM_A = 0;
 constexpr int GR_SM_B = GR_A_STAGES * 3 * 16384;
-constexpr int GR_SM_BAR = GR_SM_B + GR_B_STAGES * 16384;
+constexpr int GR_SM_OUT = GR_SM_B + GR_B_STAGES * 16384;      // 4 epilogue warps x [16 rows][36 floats]: transpose staging
+constexpr int GR_OUT_WARP = 16 * 36 * 4;
+constexpr int GR_SM_BAR = GR_SM_OUT + 4 * GR_OUT_WARP;
 constexpr int GR_SMEM = GR_SM_BAR + 256 + 1024;
+static_assert(GR_SMEM <= 232448, "shared memory of gemm_rows_kernel");
 
 template <int PARTS>
 __device__ __forceinline__ void split_parts(float v, __nv_bfloat16 (&o)[3]) {
@@ -298,29 +305,47 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gemm_rows_kernel(const RowsPara
                 uint32_t v[32];
                 tmem_ld32(tmem_base + (uint32_t(32 * q) << 16) + buf * 256 + cg * 32, v);
                 tmem_ld_wait();
-                if (row < P.M) {
-                    float* dst = P.C + row * P.ldc + cg * 32;
-                    if (vec && cg * 32 + 32 <= P.N) {
+                if (vec && cg * 32 + 32 <= P.N) {
+                    // through shared memory: thread <-> row on the way in, 8 lanes <-> one row's 128 bytes on the way out, so
+                    // that a warp store writes four complete 128-byte lines instead of 16 bytes of 32 different ones
+                    float* stg = reinterpret_cast<float*>(smem + GR_SM_OUT + q * GR_OUT_WARP);
+                    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float4 o = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]),
-                                                   __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
-                            if (P.beta != 0.f) {
-                                const float4 c = *reinterpret_cast<const float4*>(dst + 4 * e);
-                                o.x = fmaf(P.beta, c.x, o.x); o.y = fmaf(P.beta, c.y, o.y);
-                                o.z = fmaf(P.beta, c.z, o.z); o.w = fmaf(P.beta, c.w, o.w);
-                            }
-                            *reinterpret_cast<float4*>(dst + 4 * e) = o;
+                    for (int p = 0; p < 2; ++p) {                      // sixteen rows at a time (staging fits next to the rings)
+                        if ((lane >> 4) == p) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                *reinterpret_cast<float4*>(stg + (lane & 15) * 36 + 4 * e) =
+                                    make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                                __uint_as_float(v[4 * e + 3]));
                         }
-                    } else {
+                        __syncwarp();
 #pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (cg * 32 + e < P.N) {
-                                float o = __uint_as_float(v[e]);
-                                if (P.beta != 0.f) o = fmaf(P.beta, dst[e], o);
-                                dst[e] = o;
+                        for (int e = 0; e < 4; ++e) {
+                            const int rl = 4 * e + rsub;
+                            const int64_t grow = tile * 128 + 32 * q + 16 * p + rl;
+                            float4 o = *reinterpret_cast<const float4*>(stg + rl * 36 + c4);
+                            if (grow < P.M) {
+                                float* dst = P.C + grow * P.ldc + cg * 32 + c4;
+                                if (P.beta != 0.f) {
+                                    const float4 c = *reinterpret_cast<const float4*>(dst);
+                                    o.x = fmaf(P.beta, c.x, o.x); o.y = fmaf(P.beta, c.y, o.y);
+                                    o.z = fmaf(P.beta, c.z, o.z); o.w = fmaf(P.beta, c.w, o.w);
+                                }
+                                *reinterpret_cast<float4*>(dst) = o;
                             }
+                        }
+                        __syncwarp();
                     }
+                } else if (row < P.M) {
+                    float* dst = P.C + row * P.ldc + cg * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (cg * 32 + e < P.N) {
+                            float o = __uint_as_float(v[e]);
+                            if (P.beta != 0.f) o = fmaf(P.beta, dst[e], o);
+                            dst[e] = o;
+                        }
                 }
             }
             tc_fence_before();
@@ -384,11 +409,10 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gemm_rows_kernel(const RowsPara
 // ------------------------------------------------------------------------------------------------
 // C (Mo x N) += A^T B over the samples:  A (Ms x Mo), B (Ms x N) row-major fp32.  grid = (slabs, N halves)
 // ------------------------------------------------------------------------------------------------
-constexpr int TN_SM_AHI = 0;                      // [4 blocks of 64 features][128 samples][64]
-constexpr int TN_SM_ALO = 65536;
-constexpr int TN_SM_BHI = 131072;                 // [2 blocks][128][64]
-constexpr int TN_SM_BLO = 131072 + 32768;
-constexpr int TN_SM_BAR = 196608;
+// Two stages of 64-sample half-tiles: A [4 blocks of 64 features][64 samples][64] hi + lo (64 KB), B [2 blocks] hi + lo (32 KB)
+constexpr int TN_STAGE = 98304;
+constexpr int TN_A_HI = 0, TN_A_LO = 32768, TN_B_HI = 65536, TN_B_LO = 65536 + 16384;
+constexpr int TN_SM_BAR = 2 * TN_STAGE;
 constexpr int TN_SMEM = TN_SM_BAR + 128 + 1024;
 
 struct TnParams {
@@ -404,57 +428,63 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tn_kernel(const TnParams P
     const uint32_t base = (raw_addr + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw_addr);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_ready = base + TN_SM_BAR, bar_done = bar_ready + 8;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TN_SM_BAR + 32);
+    const uint32_t bar_full = base + TN_SM_BAR, bar_empty = bar_full + 16, bar_done = bar_empty + 16;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + TN_SM_BAR + 64);
     if (threadIdx.x == 0) {
-        mbar_init(bar_ready, GT_WORKERS);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, GT_WORKERS); mbar_init(bar_empty + 8 * i, 1); }
         mbar_init(bar_done, 1);
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(base + TN_SM_BAR + 32, 256);
+    if (warp == 9) tmem_alloc(base + TN_SM_BAR + 64, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nh = blockIdx.y;
     const int MB = (P.Mo + 127) / 128;                 // M = 128 blocks of the transposed operand
-    const int64_t n_tiles = (P.Ms + 127) / 128;
-    const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int64_t n_half = (P.Ms + 63) / 64;           // 64-sample half-tiles, dealt round-robin to the slabs
+    const int my_half = (n_half > blockIdx.x) ? (int)((n_half - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
     if (warp == 9) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);      // both operands MN-major
-            for (int it = 0; it < my_tiles; ++it) {
-                mbar_wait(bar_ready, (uint32_t)(it & 1), 36);
+            int s = 0; uint32_t par = 0;
+            for (int it = 0; it < my_half; ++it) {
+                mbar_wait(bar_full + 8 * s, par, 36);
                 tc_fence_after();
+                const uint32_t st = base + s * TN_STAGE;
                 for (int mb = 0; mb < MB; ++mb) {
-                    const uint32_t ahi = base + TN_SM_AHI + mb * 32768, alo = base + TN_SM_ALO + mb * 32768;
-                    const uint32_t bhi = base + TN_SM_BHI, blo = base + TN_SM_BLO;
+                    const uint32_t ahi = st + TN_A_HI + mb * 16384, alo = st + TN_A_LO + mb * 16384;
                     const uint32_t d = tmem_base + mb * 128;
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {                       // 16 samples = 16 rows = 2048 bytes
-                        const uint64_t dah = make_sdesc_sw128(ahi + k * 2048, 16384, 1024), dal = make_sdesc_sw128(alo + k * 2048, 16384, 1024);
-                        const uint64_t dbh = make_sdesc_sw128(bhi + k * 2048, 16384, 1024), dbl = make_sdesc_sw128(blo + k * 2048, 16384, 1024);
+                    for (int k = 0; k < 4; ++k) {                       // 16 samples = 16 rows = 2048 bytes; 64-feature blocks 8 KB apart
+                        const uint64_t dah = make_sdesc_sw128(ahi + k * 2048, 8192, 1024), dal = make_sdesc_sw128(alo + k * 2048, 8192, 1024);
+                        const uint64_t dbh = make_sdesc_sw128(st + TN_B_HI + k * 2048, 8192, 1024), dbl = make_sdesc_sw128(st + TN_B_LO + k * 2048, 8192, 1024);
                         mma_bf16_ss(d, dah, dbh, idesc, (it > 0 || k > 0) ? 1u : 0u);
                         mma_bf16_ss(d, dal, dbh, idesc, 1u);
                         mma_bf16_ss(d, dah, dbl, idesc, 1u);
                     }
                 }
-                mma_commit(bar_done);
+                mma_commit(bar_empty + 8 * s);
+                if (++s == 2) { s = 0; par ^= 1; }
             }
+            mma_commit(bar_done);
         }
     } else if (warp < 8) {
         const int worker = threadIdx.x;
-        for (int it = 0; it < my_tiles; ++it) {
-            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
-            if (it > 0) mbar_wait(bar_done, (uint32_t)((it - 1) & 1), 37);      // the previous tile's MMAs have read the tiles
-            convert_tile(P.A, P.lda, tile * 128, P.Ms, 0, P.Mo, MB * 2, smem + TN_SM_AHI, smem + TN_SM_ALO, worker);
-            convert_tile(P.B, P.ldb, tile * 128, P.Ms, nh * 128, P.N, 2, smem + TN_SM_BHI, smem + TN_SM_BLO, worker);
+        int s = 0; uint32_t par = 1;
+        for (int it = 0; it < my_half; ++it) {
+            const int64_t ht = blockIdx.x + (int64_t)it * gridDim.x;
+            mbar_wait(bar_empty + 8 * s, par, 37);                      // the MMAs that read this stage have completed
+            uint8_t* st = smem + s * TN_STAGE;
+            convert_half_tile(P.A, P.lda, ht * 64, P.Ms, 0, P.Mo, MB * 2, st + TN_A_HI, st + TN_A_LO, worker);
+            convert_half_tile(P.B, P.ldb, ht * 64, P.Ms, nh * 128, P.N, 2, st + TN_B_HI, st + TN_B_LO, worker);
             fence_proxy_async_smem();
-            mbar_arrive(bar_ready);
+            mbar_arrive(bar_full + 8 * s);
+            if (++s == 2) { s = 0; par ^= 1; }
         }
-        if (my_tiles > 0 && warp < 4) {
-            mbar_wait(bar_done, (uint32_t)((my_tiles - 1) & 1), 38);
+        if (my_half > 0 && warp < 4) {
+            mbar_wait(bar_done, 0, 38);
             tc_fence_after();
             for (int mb = 0; mb < MB; ++mb) {
                 const int r = mb * 128 + 32 * warp + lane;              // row of C = feature of A
@@ -582,7 +612,7 @@ int tc_gemm_f32(cudaStream_t st, bool ta, bool tb, int64_t M, int N, int K, cons
             return NERF_OK;
         }
         TnParams P = {A, lda, B, ldb, C, ldc, (int64_t)K, (int)M, N};
-        const int64_t tiles = ceil_div(K, 128);
+        const int64_t tiles = ceil_div(K, 64);           // 64-sample half-tiles
         const int NH = (N + 127) / 128;
         int slabs = num_sms() / NH;
         if (slabs > tiles) slabs = (int)tiles;
