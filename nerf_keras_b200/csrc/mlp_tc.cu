@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                 for (int j = 0; j < 4; ++j) st_global_pair(genc, rs.off[2 * j], (rs.off[0] >> 7) & 1, E + 8 * j);
             } else if (SAVE) {
                 named_bar_sync(1 + s, TILE_M);
-                if (elected) { bulk_s2g(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
+                if (elected) { bulk_s2g_stream(save_tile + SAVE_ENC, act_base, 16384); bulk_commit(); }
             }
             arrive(bar_lo);
             arrive(bar_hi);
@@ -575,8 +575,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                                 named_bar_sync(1 + s, TILE_M);
                                 if (elected) {
                                     int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
-                                    bulk_s2g(save_tile + off, act_base, 32768);
-                                    bulk_s2g(save_tile + off + 32768, act_base + 32768, 32768);
+                                    bulk_s2g_stream(save_tile + off, act_base, 32768);
+                                    bulk_s2g_stream(save_tile + off + 32768, act_base + 32768, 32768);
                                     bulk_commit();
                                 }
                             }
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                         named_bar_sync(1 + s, TILE_M);
                         if (elected) {
                             int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
-                            bulk_s2g(save_tile + off, act_base, 32768);
+                            bulk_s2g_stream(save_tile + off, act_base, 32768);
                             bulk_commit();
                         }
                     }
@@ -629,8 +629,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                             named_bar_sync(1 + s, TILE_M);
                             if (elected) {
                                 int64_t off = (layer < 8) ? SAVE_H + 65536 * layer : SAVE_FEAT;
-                                if (kSplitImageStore) bulk_s2g(save_tile + off + 32768, act_base + 32768, 32768);
-                                else bulk_s2g(save_tile + off, act_base, 65536);
+                                if (kSplitImageStore) bulk_s2g_stream(save_tile + off + 32768, act_base + 32768, 32768);
+                                else bulk_s2g_stream(save_tile + off, act_base, 65536);
                                 bulk_commit();
                             }
                         }
@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_fwd_tc_kernel(const F
                         if (!kDirectSave) {
                             fence_async();
                             named_bar_sync(1 + s, TILE_M);
-                            if (elected) { bulk_s2g(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
+                            if (elected) { bulk_s2g_stream(save_tile + SAVE_HD, act_base, 32768); bulk_commit(); }
                         }
                     }
                 }

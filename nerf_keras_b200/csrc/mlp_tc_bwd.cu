@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
             fence_proxy_async_smem();
             named_bar_sync(1 + s, TILE_M);
             if (elected) {
-                bulk_s2g(dz_tile + DZ_DDIR, act_base, 32768);
-                bulk_s2g(dz_tile + DZ_HEAD, act_base + 2 * 16384, 16384);
+                bulk_s2g_stream(dz_tile + DZ_DDIR, act_base, 32768);
+                bulk_s2g_stream(dz_tile + DZ_HEAD, act_base + 2 * 16384, 16384);
                 bulk_commit();
             }
             mbar_arrive(bar_lo);
@@ -360,14 +360,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) nerf_mlp_bwd_tc_kernel(const B
                 // first half of the dZ image (K-blocks 0,1) leaves now, under the second half of the epilogue: one 64 KB
                 // burst of TMA shared-memory reads at the start of the next MMA phase costs more than two 32 KB ones
                 named_bar_sync(1 + s, TILE_M);
-                if (elected) { bulk_s2g(dz_tile + dst, act_base, 32768); bulk_commit(); }
+                if (elected) { bulk_s2g_stream(dz_tile + dst, act_base, 32768); bulk_commit(); }
                 if (ph == 0) chain_part2<false, false>(t_lane, 0.f, wsig, mask, rs);
                 else if (ph == 1) chain_part2<true, true>(t_lane, dp.w, wsig, mask, rs);
                 else chain_part2<false, true>(t_lane, 0.f, wsig, mask, rs);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 named_bar_sync(1 + s, TILE_M);
-                if (elected) { bulk_s2g(dz_tile + dst + 32768, act_base + 32768, 32768); bulk_commit(); }
+                if (elected) { bulk_s2g_stream(dz_tile + dst + 32768, act_base + 32768, 32768); bulk_commit(); }
                 if (ph < B_PHASES - 1) mbar_arrive(bar_hi);
             }
             prev_tile = tile;

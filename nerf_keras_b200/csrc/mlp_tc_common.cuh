@@ -152,7 +152,7 @@ __device__ __forceinline__ void producer_loop(uint32_t base, const Barriers& B, 
     for (int g = 0; g < total_chunks; ++g) {
         mbar_wait(B.empty + 8 * slot, par, 1);
         mbar_arrive_expect_tx(B.full + 8 * slot, CHUNK_BYTES);
-        bulk_g2s(base + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)c * CHUNK_ELEMS, CHUNK_BYTES, B.full + 8 * slot);
+        bulk_g2s_keep(base + SM_RING + slot * CHUNK_BYTES, chunks + (size_t)c * CHUNK_ELEMS, CHUNK_BYTES, B.full + 8 * slot);
         if (++c == n_chunks) c = 0;
         if (++slot == STAGES) { slot = 0; par ^= 1; }
     }
@@ -422,7 +422,7 @@ __device__ __forceinline__ void producer_loop_pair(uint32_t base, const Barriers
                                          (single ? rank * (CHUNK_BYTES / 2) : 0);
                     mbar_wait(B.empty + 8 * slot, par, 1);
                     mbar_arrive_expect_tx(B.full + 8 * slot, bytes);
-                    bulk_g2s(base + SM_RING + slot * CHUNK_BYTES, src, bytes, B.full + 8 * slot);
+                    bulk_g2s_keep(base + SM_RING + slot * CHUNK_BYTES, src, bytes, B.full + 8 * slot);
                     if (++slot == STAGES) { slot = 0; par ^= 1; }
                 }
             }

@@ -100,6 +100,30 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t 
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
                  : "memory");
 }
+// L2 eviction hints.  The saved activation / dZ images stream through L2 once on their way to HBM (evict first); the
+// 1.2 MB weight chunk stream of a net is re-read by every CTA for every tile and must survive that stream (evict last).
+// Measured on one box (4096 rays, both nets): forward 1.61 -> 1.57 ms, dX chain 1.52 -> 1.44 ms per step.  Evict-first on
+// the weight-gradient kernel's operand loads as well: that kernel 3 % slower (two jobs share some operands), not used.
+__device__ __forceinline__ uint64_t l2_policy_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_keep(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(l2_policy_last())
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_stream(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src_smem), "r"(bytes),
+                 "l"(l2_policy_first())
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk stores have finished READING shared memory (smem may be overwritten)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
